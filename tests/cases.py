@@ -1,0 +1,129 @@
+"""Seeded test cases shared by the golden generator, the oracle tests and the GPU parity tests."""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pynbody_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@dataclass
+class SmoothCase:
+    gen: str
+    n: int
+    dtype: type
+    boxsize: float | None
+    k: int
+    kernel_id: int
+    seed: int
+    leafsize: int = 16
+    nn_stride: int = 10
+    ball_centre: tuple = (0.9, 0.5, 0.5)
+    ball_radius: float = 0.2
+    shift: float = 0.0
+
+    def make(self):
+        if self.gen == "uniform":
+            pos, vel, mass = synth.uniform_box(self.n, self.seed, self.dtype, 1.0)
+            rng = np.random.default_rng(self.seed + 100)
+            mass = (rng.uniform(0.5, 1.5, self.n) / self.n).astype(self.dtype)
+            pos = (pos - self.shift).astype(self.dtype)
+        elif self.gen == "blobs":
+            pos, vel, mass = synth.gaussian_blobs(self.n, self.seed, self.dtype)
+        elif self.gen == "zeldovich":
+            pos, vel, mass = synth.zeldovich_box(int(round(self.n ** (1 / 3))), self.seed, self.dtype)
+        else:
+            raise ValueError(self.gen)
+        return pos, vel, mass
+
+
+SMOOTH_CASES = {
+    # C1-like: uniform periodic, k=32, cubic spline, both dtypes
+    "uniform_f64": SmoothCase("uniform", 4000, np.float64, 1.0, 32, 0, 11),
+    "uniform_f32": SmoothCase("uniform", 4000, np.float32, 1.0, 32, 0, 12),
+    # positions in [-0.5, 0.5) as in the reference's particles_in_sphere test
+    "uniform_shift_f64": SmoothCase("uniform", 3000, np.float64, 1.0, 16, 1, 13, shift=0.5,
+                                    ball_centre=(0.5, 0.0, 0.0), ball_radius=0.3),
+    # C2-like: clustered, k=64, WendlandC2
+    "zeldovich_f64": SmoothCase("zeldovich", 16 ** 3, np.float64, 1.0, 64, 1, 14),
+    "zeldovich_f32": SmoothCase("zeldovich", 16 ** 3, np.float32, 1.0, 64, 1, 15),
+    # isolated (non-periodic) clustered set
+    "blobs_f64": SmoothCase("blobs", 5000, np.float64, None, 32, 0, 16, ball_centre=(0.0, 0.0, 0.0), ball_radius=0.5),
+    "blobs_f32": SmoothCase("blobs", 5000, np.float32, None, 40, 1, 17, ball_centre=(0.0, 0.0, 0.0), ball_radius=0.5),
+}
+
+
+@dataclass
+class RenderCase:
+    lut: str
+    h_power: int
+    dtype: type
+    nx: int
+    ny: int
+    nz: int = 0
+    grid: bool = False
+    z_camera: float = 0.0
+    periodic: bool = True
+    seed: int = 21
+    n: int = 6000
+    smooth_lo: float = 0.0
+    smooth_hi: float = np.inf
+    min_smooth: float = 0.0
+    h_scale: float = 0.03
+    mixed: bool = False
+    extra: dict = field(default_factory=dict)
+
+    def make(self):
+        rng = np.random.default_rng(self.seed)
+        n = self.n
+        pos = rng.uniform(-0.5, 0.5, (n, 3)).astype(self.dtype)
+        sm = rng.lognormal(np.log(self.h_scale), 0.9, n).astype(self.dtype)
+        mass = (rng.uniform(0.5, 1.5, n) / n).astype(self.dtype)
+        rho = rng.uniform(0.5, 2.0, n).astype(self.dtype)
+        qty = rng.uniform(0.5, 2.0, n).astype(np.float32 if self.mixed else self.dtype)
+        # NaN weights are skipped by render_image but NOT by to_3d_grid (_render.pyx:278 vs :430):
+        # give the grid cases a NaN on their most compact particle so it stays local
+        qty[int(np.argmin(sm)) if self.grid else 7] = np.nan
+        return dict(pos=pos, sm=sm, mass=mass, rho=rho, qty=qty)
+
+    def args(self, a, kern):
+        pos = a["pos"]
+        x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+        wrap = list(np.linspace(-1.0, 1.0, 3)) if self.periodic else [0.0]
+        ar = self.ny / self.nx
+        if self.grid:
+            return (self.nx, self.ny, self.nz, x, y, z, a["sm"], -0.5, 0.5, -0.5 * ar, 0.5 * ar, -0.5, 0.5,
+                    a["qty"], a["mass"], a["rho"], self.smooth_lo, self.smooth_hi, kern, wrap, wrap, wrap)
+        return (self.nx, self.ny, x, y, z, a["sm"], -0.5, 0.5, -0.5 * ar, 0.5 * ar, self.z_camera, 0.013,
+                a["qty"], a["mass"], a["rho"], self.smooth_lo, self.smooth_hi, -np.inf, np.inf,
+                self.min_smooth, kern, wrap, wrap)
+
+
+RENDER_CASES = {
+    "slice_cubic_f64": RenderCase("cubic3d", 3, np.float64, 64, 64),
+    "proj_cubic_f64": RenderCase("cubic2d", 2, np.float64, 64, 64),
+    "proj_wendland_f32": RenderCase("wendland2d", 2, np.float32, 80, 40, mixed=True),
+    "slice_wendland_f32": RenderCase("wendland3d", 3, np.float32, 50, 50, periodic=False),
+    "proj_persp_f64": RenderCase("cubic2d", 2, np.float64, 48, 48, z_camera=2.0, periodic=False),
+    "proj_range_f64": RenderCase("cubic2d", 2, np.float64, 64, 64, smooth_lo=1.0, smooth_hi=8.0, min_smooth=0.01),
+    "proj_big_h_f64": RenderCase("cubic2d", 2, np.float64, 96, 96, h_scale=0.15, n=1500),
+    "grid_cubic_f64": RenderCase("cubic3d", 3, np.float64, 16, 16, 16, grid=True),
+    "grid_wendland_f32": RenderCase("wendland3d", 3, np.float32, 20, 12, 9, grid=True, periodic=False, mixed=True),
+}
+
+
+def load_luts():
+    return dict(np.load(os.path.join(GOLDEN, "luts.npz")))
+
+
+def load_golden(kind, name):
+    return dict(np.load(os.path.join(GOLDEN, f"{kind}_{name}.npz")))
