@@ -1,0 +1,176 @@
+/* pnb_b200.h -- C ABI of libpnb_b200.so, the B200 (sm_100a) implementation of pynbody's SPH
+ * smoothing hot path.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the pynbody
+ * source tree).  The reference's native layer is two CPython extension modules:
+ *     pynbody.kdtree.kdmain   (method table pynbody/kdtree/kdmain.cpp:63-85)
+ *     pynbody.sph._render     (pynbody/sph/_render.pyx:209, :373)
+ * INTEGRATION.md shows the ctypes binding a pynbody maintainer would add.
+ *
+ * Conventions
+ *   - every function returns PNB_OK (0) or a negative PNB_ERR_* code; pnb_last_error() gives the
+ *     message (thread-local).  The Python host layer maps codes to the exception types the
+ *     reference raises (ValueError / TypeError / RuntimeError, kdmain.cpp:136-182,367-372,795-800).
+ *   - dtype codes: PNB_F32 = 0, PNB_F64 = 1.
+ *   - mem codes:  PNB_HOST = 0 (pageable or pinned host memory), PNB_DEVICE = 1 (device memory on
+ *     the current CUDA device, e.g. a torch tensor's data_ptr()).
+ *   - strides are in BYTES, as in the numpy buffers the reference borrows (kd.h:163-190).
+ *   - all per-particle outputs are written in FILE order (the order of the input arrays), as the
+ *     reference does through particleOffsets (kd.h:205-206).
+ *   - there is no CPU fallback: every compute entry point fails with PNB_ERR_CUDA if no sm_100
+ *     device is usable.
+ */
+#ifndef PNB_B200_H
+#define PNB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_OK            0
+#define PNB_ERR_VALUE    -1   /* -> ValueError   */
+#define PNB_ERR_TYPE     -2   /* -> TypeError    */
+#define PNB_ERR_RUNTIME  -3   /* -> RuntimeError (gather overflow, smooth.h:253-267) */
+#define PNB_ERR_CUDA     -4   /* -> RuntimeError (CUDA failure / no device) */
+#define PNB_ERR_MEMORY   -5   /* -> MemoryError  */
+
+#define PNB_F32 0
+#define PNB_F64 1
+#define PNB_HOST 0
+#define PNB_DEVICE 1
+
+/* array slots of kdmain.set_arrayref (kdmain.cpp:511-579) */
+#define PNB_ARR_SMOOTH 0
+#define PNB_ARR_RHO    1
+#define PNB_ARR_MASS   2
+#define PNB_ARR_QTY    3
+#define PNB_ARR_QTY_SM 4
+
+/* property ids of kdmain.populate (kdmain.cpp:53-60; pynbody/kdtree/__init__.py:70-77) */
+#define PNB_PROP_HSM         1
+#define PNB_PROP_RHO         2
+#define PNB_PROP_QTYMEAN_1D  3
+#define PNB_PROP_QTYMEAN_ND  4
+#define PNB_PROP_QTYDISP_1D  5
+#define PNB_PROP_QTYDISP_ND  6
+#define PNB_PROP_QTYDIV      7
+#define PNB_PROP_QTYCURL     8
+
+/* kernel ids of sph/kernels.hpp:21-33 */
+#define PNB_KERNEL_CUBIC_SPLINE 0
+#define PNB_KERNEL_WENDLAND_C2  1
+
+typedef struct pnb_tree pnb_tree;
+
+/* ---- library -------------------------------------------------------------------------------- */
+const char *pnb_last_error(void);
+const char *pnb_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int pnb_device_count(void);
+/* select the device subsequent calls from this thread use */
+int pnb_set_device(int device);
+
+/* ---- tree: kdmain.init + kdmain.build (kdmain.cpp:189-302; kd.cpp:98-238) --------------------
+ * Uploads pos (N x 3) and mass (N), builds a balanced median-split kd-tree on the GPU and keeps
+ * the particles resident in tree order as structure-of-arrays.  `leafsize` is the reference's
+ * user-visible leaf size: it only shapes pnb_tree_node_count / pnb_tree_export_kdnodes; the
+ * device tree always uses 32-particle buckets (one warp lane per particle).
+ * `boxsize` <= 0 means non-periodic (kdmain.cpp:360-361).  mass may be NULL. */
+pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stride1,
+                          const void *mass, int64_t mass_stride,
+                          int64_t n, int dtype, int leafsize, int mem);
+/* kdmain.free (kdmain.cpp:304-342) */
+void pnb_tree_destroy(pnb_tree *t);
+
+int64_t pnb_tree_num_particles(const pnb_tree *t);
+/* tight bounds of all particles: double[6] = min xyz, max xyz (root cell, kd.cpp:120-135) */
+int pnb_tree_bounds(const pnb_tree *t, double *out6);
+/* kdmain.get_node_count (kd.cpp:98-111): 2 * nSplit for the user's leafsize */
+int64_t pnb_tree_node_count(const pnb_tree *t);
+/* particle_offsets (tree order -> file order), int64[N], host memory */
+int pnb_tree_order(pnb_tree *t, int64_t *out);
+/* reference-layout KDNode[node_count] records (kd.h:29-40, 80 bytes each), host memory.
+ * Together with pnb_tree_order this is what KDTree.serialize() returns
+ * (pynbody/kdtree/__init__.py:136-163). */
+int pnb_tree_export_kdnodes(pnb_tree *t, void *out, int64_t n_nodes);
+/* device-tree introspection used by the tests: number of 32-particle buckets, their start offsets
+ * (int64[n_buckets + 1]) and tight bounds (double[n_buckets][6] = min xyz, max xyz), host memory */
+int64_t pnb_tree_num_buckets(const pnb_tree *t);
+int pnb_tree_buckets(pnb_tree *t, int64_t *start, double *bounds);
+
+/* ---- kdmain.set_arrayref (kdmain.cpp:511-579) ------------------------------------------------
+ * Registers a borrowed array for slot `id`.  ncols is 1 (N) or 3 (N x 3, qty / qty_sm only).
+ * smooth/rho/mass must have the tree dtype, qty and qty_sm a common dtype (TypeError otherwise,
+ * pynbody/kdtree/__init__.py:262-267). */
+int pnb_set_array(pnb_tree *t, int id, void *ptr, int64_t stride0, int64_t stride1,
+                  int ncols, int dtype, int mem);
+
+/* ---- kdmain.nn_start + domain_decomposition + populate + nn_stop ------------------------------
+ * (kdmain.cpp:344-382, 622-653, 681-806; smooth.h:331-480, 626-918).
+ * Runs property `propid` with `k` neighbours (k counts the particle itself) and SPH kernel
+ * `kernel_id`, writing the registered output array in file order.  `period` <= 0 disables
+ * periodicity; if the particles span more than `period` along any axis periodicity is disabled
+ * and *period_ignored (if non-NULL) is set to 1 -- the caller issues the reference's
+ * RuntimeWarning (smooth.h:92-102).  k > N -> PNB_ERR_VALUE (kdmain.cpp:367-372); more than
+ * k + 500 particles inside 2h -> PNB_ERR_RUNTIME (smooth.h:15,253-267). */
+int pnb_populate(pnb_tree *t, int propid, int k, int kernel_id, double period, int *period_ignored);
+
+/* ---- kdmain.nn_next, all particles at once (kdmain.cpp:390-440) -------------------------------
+ * Neighbour lists for every particle: idx_out int64[N][k] (file-order ids, unsorted, self
+ * included with d2 = 0), d2_out T[N][k], h_out T[N] (may be NULL); rows in file order; host memory. */
+int pnb_knn(pnb_tree *t, int k, double period, int64_t *idx_out, void *d2_out, void *h_out,
+            int *period_ignored);
+
+/* ---- kdmain.particles_in_sphere (kdmain.cpp:655-679) ------------------------------------------
+ * File-order ids of particles with d2 <= r*r of (cx,cy,cz) (centre and radius are rounded to the
+ * tree dtype first, as the reference's 'f'/'d' argument parsing does).  Writes at most `cap` ids
+ * to out (host memory, ascending) and the total count to *n_found. */
+int pnb_ball_query(pnb_tree *t, double cx, double cy, double cz, double r, double period,
+                   int64_t *out, int64_t cap, int64_t *n_found);
+
+/* ---- _render.render_image (pynbody/sph/_render.pyx:209-365) -----------------------------------
+ * x,y,z share pos_dtype and a common byte stride; sm/qty/mass/rho are 1-D with their own dtype
+ * and byte stride (the five fused types of _render.pyx:20-38).  lut holds n_lut float32 kernel
+ * samples (kernel.get_samples()), h_power = kernel.h_power, max_d = kernel.max_d.  wrap_x/wrap_y
+ * are the periodic offsets (converted to float32 as the reference does).  out: float32[ny][nx]. */
+typedef struct pnb_render_arrays {
+    const void *x, *y, *z;      int64_t pos_stride; int pos_dtype;
+    const void *sm;             int64_t sm_stride;  int sm_dtype;
+    const void *qty;            int64_t qty_stride; int qty_dtype;
+    const void *mass;           int64_t mass_stride; int mass_dtype;
+    const void *rho;            int64_t rho_stride; int rho_dtype;
+    int64_t n;
+    int mem;                    /* PNB_HOST or PNB_DEVICE, applies to all seven arrays */
+} pnb_render_arrays;
+
+int pnb_render_image(int nx, int ny, const pnb_render_arrays *a,
+                     double x1, double x2, double y1, double y2, double z_camera, double z0,
+                     double smooth_lo, double smooth_hi, double z_lo, double z_hi, double min_smooth,
+                     const float *lut, int n_lut, int h_power, double max_d,
+                     const double *wrap_x, int n_wrap_x, const double *wrap_y, int n_wrap_y,
+                     float *out, int out_mem);
+
+/* ---- _render.to_3d_grid (pynbody/sph/_render.pyx:373-497) -------------------------------------
+ * out: float32[nx][ny][nz]. */
+int pnb_render_grid(int nx, int ny, int nz, const pnb_render_arrays *a,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double smooth_lo, double smooth_hi,
+                    const float *lut, int n_lut, int h_power, double max_d,
+                    const double *wrap_x, int n_wrap_x, const double *wrap_y, int n_wrap_y,
+                    const double *wrap_z, int n_wrap_z,
+                    float *out, int out_mem);
+
+/* ---- timing hooks (bench.py) ------------------------------------------------------------------
+ * Device time in milliseconds of the kernels launched by the last pnb_tree_create (stage 0),
+ * pnb_populate / pnb_knn (stage 1) or render call (stage 2) on this thread, measured with CUDA
+ * events on the library's stream; also the number of kernel launches of that call. */
+double pnb_last_device_ms(int stage);
+int64_t pnb_last_launch_count(int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNB_B200_H */

@@ -1,0 +1,371 @@
+// api.cu -- the extern "C" boundary of libpnb_b200.so (include/pnb_b200.h).
+//
+// Host-side orchestration of what kdmain.cpp does around its kernels: argument checks with the
+// reference's error classes (kdmain.cpp:136-182, 200-208, 367-372, 511-579), the periodicity check of
+// smInit (smooth.h:71-124), array registration, and moving results back to the caller's borrowed
+// arrays in file order.
+#include "common.cuh"
+
+namespace pnb {
+
+static thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+static thread_local double g_stage_ms[3] = {0, 0, 0};
+static thread_local int64_t g_stage_launches[3] = {0, 0, 0};
+
+void set_last_error(const std::string &m) { g_error = m; }
+void record_stage(int stage, double ms, int64_t launches)
+{
+    g_stage_ms[stage] = ms;
+    g_stage_launches[stage] = launches;
+}
+
+StageTimer::StageTimer(int st, cudaStream_t s) : stage(st), stream(s), launches0(g_launches)
+{
+    PNB_CUDA(cudaEventCreate(&a));
+    PNB_CUDA(cudaEventCreate(&b));
+    PNB_CUDA(cudaEventRecord(a, stream));
+}
+void StageTimer::stop()
+{
+    if (!a) return;
+    PNB_CUDA(cudaEventRecord(b, stream));
+    PNB_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    PNB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    g_stage_ms[stage] = ms;
+    g_stage_launches[stage] = g_launches - launches0;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    a = b = nullptr;
+}
+StageTimer::~StageTimer()
+{
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+}
+
+static void require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error(PNB_ERR_CUDA, "no CUDA device available: pnb_b200 has no CPU fallback");
+    }
+}
+
+// smooth.h:71-102: periodicity is honoured only if the particles fit inside one period
+static double effective_period(const Tree &t, double period, int *ignored)
+{
+    if (ignored) *ignored = 0;
+    if (!(period > 0)) return 0;
+    for (int d = 0; d < 3; ++d)
+        if (t.root_max[d] - t.root_min[d] > period) {
+            if (ignored) *ignored = 1;
+            return 0;
+        }
+    return period;
+}
+
+template <typename F>
+static int guarded(F &&f)
+{
+    try {
+        f();
+        return PNB_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        set_last_error("out of host memory");
+        return PNB_ERR_MEMORY;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return PNB_ERR_RUNTIME;
+    }
+}
+
+static const ArrRef &need(const Tree &t, int id, const char *name)
+{
+    if (!t.arr[id].set()) throw Error(PNB_ERR_VALUE, std::string(name) + " array has not been set");
+    return t.arr[id];
+}
+
+// fetch a registered 1-D / N x ncols array into dense device columns in TREE order
+static DevBuf fetch_tree_order(Tree &t, const ArrRef &r)
+{
+    const size_t elem = tsize(r.dtype);
+    DevBuf file_cols(elem * r.ncols * t.n), tree_cols(elem * r.ncols * t.n);
+    fetch_columns(r.ptr, r.stride0, r.stride1, r.ncols, r.dtype, r.mem, t.n, file_cols.p, t.stream);
+    permute_to_tree(t, file_cols.p, tree_cols.p, r.ncols, (int)elem, t.stream);
+    PNB_CUDA(cudaStreamSynchronize(t.stream));
+    return tree_cols;
+}
+static void store_from_tree_order(Tree &t, const ArrRef &r, const void *tree_cols)
+{
+    const size_t elem = tsize(r.dtype);
+    DevBuf file_cols(elem * r.ncols * t.n);
+    permute_to_file(t, tree_cols, file_cols.p, r.ncols, (int)elem, t.stream);
+    store_columns(r.ptr, r.stride0, r.stride1, r.ncols, r.dtype, r.mem, t.n, file_cols.p, t.stream);
+    PNB_CUDA(cudaStreamSynchronize(t.stream));
+}
+
+__global__ void k_all_equal(const unsigned char *a, const unsigned char *b, size_t bytes, int *differs)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a), *b4 = reinterpret_cast<const uint32_t *>(b);
+    bool d = false;
+    for (size_t j = i; j < bytes / 4; j += stride) d |= a4[j] != b4[j];
+    if (d) *differs = 1;
+}
+static bool device_equal(Tree &t, const void *a, const void *b, size_t bytes)
+{
+    DevBuf flag(sizeof(int));
+    PNB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), t.stream));
+    PNB_LAUNCH(k_all_equal, 1184, 256, 0, t.stream, (const unsigned char *)a, (const unsigned char *)b, bytes, flag.as<int>());
+    int h = 0;
+    PNB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
+    PNB_CUDA(cudaStreamSynchronize(t.stream));
+    return h == 0;
+}
+
+static void populate(Tree &t, int propid, int k, int kernel_id, double period_in, int *period_ignored)
+{
+    require_device();
+    if (kernel_id != PNB_KERNEL_CUBIC_SPLINE && kernel_id != PNB_KERNEL_WENDLAND_C2)
+        throw Error(PNB_ERR_VALUE, "unknown SPH kernel id");
+    if (k > t.n) throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
+    if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
+    const double period = effective_period(t, period_in, period_ignored);
+    const KernelParams kp = make_kernel_params(kernel_id, k);
+    const size_t ts = tsize(t.dtype);
+    StageTimer timer(1, t.stream);
+
+    if (propid == PNB_PROP_HSM) {
+        const ArrRef &sm = need(t, PNB_ARR_SMOOTH, "smooth");       // kdmain.cpp:633-639
+        run_knn(t, k, period, /*fuse_rho=*/t.has_mass, kp, nullptr, nullptr);
+        store_from_tree_order(t, sm, t.smooth_t.p);
+        timer.stop();
+        return;
+    }
+    if (propid < PNB_PROP_RHO || propid > PNB_PROP_QTYCURL) throw Error(PNB_ERR_VALUE, "unknown smoothing property id");
+
+    const ArrRef &smr = need(t, PNB_ARR_SMOOTH, "smooth");
+    DevBuf smooth_tree = fetch_tree_order(t, smr);
+    // is the caller's smooth array the one this tree produced (the usual sim['smooth'] -> sim['rho'] flow)?
+    const bool own_smooth = t.smooth_valid && t.smooth_k == k && t.smooth_period == (period > 0 ? period : 0)
+                            && device_equal(t, smooth_tree.p, t.smooth_t.p, ts * t.n);
+
+    if (propid == PNB_PROP_RHO) {
+        const ArrRef &out = need(t, PNB_ARR_RHO, "rho");
+        if (own_smooth && t.rho_valid && t.rho_kernel == kernel_id) {
+            store_from_tree_order(t, out, t.rho_t.p);                // density fused with the kNN pass
+        } else {
+            DevBuf rho_tree(ts * t.n);
+            if (run_gather(t, propid, k, period, kp, smooth_tree.p, nullptr, nullptr, t.dtype, rho_tree.p))
+                throw Error(PNB_ERR_RUNTIME, "Buffer overflow in smoothing operation. This probably means that your smoothing lengths are too large compared to the number of neighbours you specified.");
+            store_from_tree_order(t, out, rho_tree.p);
+        }
+        timer.stop();
+        return;
+    }
+
+    const ArrRef &rhor = need(t, PNB_ARR_RHO, "rho");
+    const ArrRef &qty = need(t, PNB_ARR_QTY, "qty");
+    const ArrRef &out = need(t, PNB_ARR_QTY_SM, "qty_sm");
+    const bool nd = propid == PNB_PROP_QTYMEAN_ND || propid == PNB_PROP_QTYDISP_ND || propid == PNB_PROP_QTYDIV
+                    || propid == PNB_PROP_QTYCURL;
+    const bool out_nd = propid == PNB_PROP_QTYMEAN_ND || propid == PNB_PROP_QTYCURL;
+    if (qty.ncols != (nd ? 3 : 1)) throw Error(PNB_ERR_VALUE, "qty array has the wrong shape for this operation");
+    if (out.ncols != (out_nd ? 3 : 1)) throw Error(PNB_ERR_VALUE, "qty_sm array has the wrong shape for this operation");
+    if (qty.dtype != out.dtype) throw Error(PNB_ERR_TYPE, "qty and qty_sm must have the same dtype");
+    DevBuf rho_tree = fetch_tree_order(t, rhor);
+    DevBuf qty_tree = fetch_tree_order(t, qty);
+    DevBuf out_tree(tsize(out.dtype) * out.ncols * t.n);
+    if (run_gather(t, propid, k, period, kp, smooth_tree.p, rho_tree.p, qty_tree.p, qty.dtype, out_tree.p))
+        throw Error(PNB_ERR_RUNTIME, "Buffer overflow in smoothing operation. This probably means that your smoothing lengths are too large compared to the number of neighbours you specified.");
+    store_from_tree_order(t, out, out_tree.p);
+    timer.stop();
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+extern "C" {
+
+const char *pnb_last_error(void) { return g_error.c_str(); }
+const char *pnb_version(void) { return "pnb_b200 0.1.0 (sm_100a)"; }
+
+int pnb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pnb_set_device(int device)
+{
+    return guarded([&] { PNB_CUDA(cudaSetDevice(device)); });
+}
+
+pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stride1, const void *mass,
+                          int64_t mass_stride, int64_t n, int dtype, int leafsize, int mem)
+{
+    Tree *t = nullptr;
+    int rc = guarded([&] {
+        require_device();
+        if (dtype != PNB_F32 && dtype != PNB_F64) throw Error(PNB_ERR_VALUE, "Unsupported array dtype for kdtree");
+        if (!pos) throw Error(PNB_ERR_VALUE, "pos is null");
+        if (n < 1) throw Error(PNB_ERR_VALUE, "kd-tree needs at least one particle");
+        if (leafsize < 1) throw Error(PNB_ERR_VALUE, "leafsize must be positive");
+        t = new Tree();
+        t->dtype = dtype; t->n = n; t->user_leafsize = leafsize;
+        StageTimer timer(0, t->stream);
+        const size_t ts = tsize(dtype);
+        DevBuf cols(ts * 3 * n), mass_dev;
+        fetch_columns(pos, pos_stride0, pos_stride1, 3, dtype, mem, n, cols.p, t->stream);
+        if (mass) {
+            mass_dev.alloc(ts * n);
+            fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
+        }
+        build_tree(*t, cols, mass ? mass_dev.p : nullptr);
+        timer.stop();
+    });
+    if (rc != PNB_OK) { delete t; return nullptr; }
+    return reinterpret_cast<pnb_tree *>(t);
+}
+
+void pnb_tree_destroy(pnb_tree *h) { delete reinterpret_cast<Tree *>(h); }
+
+int64_t pnb_tree_num_particles(const pnb_tree *h) { return reinterpret_cast<const Tree *>(h)->n; }
+
+int pnb_tree_bounds(const pnb_tree *h, double *out6)
+{
+    const Tree *t = reinterpret_cast<const Tree *>(h);
+    for (int d = 0; d < 3; ++d) { out6[d] = t->root_min[d]; out6[3 + d] = t->root_max[d]; }
+    return PNB_OK;
+}
+
+int64_t pnb_tree_node_count(const pnb_tree *h)
+{
+    const Tree *t = reinterpret_cast<const Tree *>(h);
+    int64_t n = t->n, l = 1;                      // kd.cpp:98-111
+    while (n > t->user_leafsize) { n >>= 1; l <<= 1; }
+    return l << 1;
+}
+
+int pnb_tree_order(pnb_tree *h, int64_t *out)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        std::vector<uint32_t> o((size_t)t->n);
+        PNB_CUDA(cudaMemcpy(o.data(), t->order.p, sizeof(uint32_t) * (size_t)t->n, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < t->n; ++i) out[i] = (int64_t)o[(size_t)i];
+    });
+}
+
+int64_t pnb_tree_num_buckets(const pnb_tree *h) { return reinterpret_cast<const Tree *>(h)->nsplit; }
+
+int pnb_tree_buckets(pnb_tree *h, int64_t *start, double *bounds)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        std::vector<int32_t> s((size_t)t->nsplit + 1);
+        PNB_CUDA(cudaMemcpy(s.data(), t->bucket_start.p, sizeof(int32_t) * s.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < s.size(); ++i) start[i] = s[i];
+        const size_t nb = (size_t)t->nsplit * 6;
+        if (t->dtype == PNB_F64) {
+            PNB_CUDA(cudaMemcpy(bounds, t->box.as<double>() + nb, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> b(nb);
+            PNB_CUDA(cudaMemcpy(b.data(), t->box.as<float>() + nb, sizeof(float) * nb, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nb; ++i) bounds[i] = (double)b[i];
+        }
+    });
+}
+
+int pnb_tree_export_kdnodes(pnb_tree *h, void *out, int64_t n_nodes)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] { export_kdnodes(*t, out, n_nodes); });
+}
+
+int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        if (id < 0 || id > 4) throw Error(PNB_ERR_VALUE, "invalid array id");
+        if (dtype != PNB_F32 && dtype != PNB_F64) throw Error(PNB_ERR_VALUE, "Unsupported array dtype for kdtree");
+        if (id <= PNB_ARR_MASS) {
+            if (dtype != t->dtype) throw Error(PNB_ERR_TYPE, "array dtype must match the dtype of the positions");
+            if (ncols != 1) throw Error(PNB_ERR_VALUE, "array must be one-dimensional");
+        } else if (ncols != 1 && ncols != 3) {
+            throw Error(PNB_ERR_VALUE, "qty array must be one-dimensional or N x 3");
+        }
+        if (!ptr) throw Error(PNB_ERR_VALUE, "array pointer is null");
+        ArrRef r;
+        r.ptr = ptr; r.stride0 = stride0; r.stride1 = stride1; r.ncols = ncols; r.dtype = dtype; r.mem = mem;
+        if (id == PNB_ARR_MASS) {
+            // mass lives on the device in tree order; refresh it (the reference re-reads the borrowed buffer)
+            require_device();
+            DevBuf m = fetch_tree_order(*t, r);
+            const bool same = t->has_mass && device_equal(*t, m.p, t->mass.p, tsize(dtype) * (size_t)t->n);
+            if (!same) {
+                t->mass = std::move(m);
+                t->has_mass = true;
+                t->rho_valid = false;
+            }
+        }
+        t->arr[id] = r;
+    });
+}
+
+int pnb_populate(pnb_tree *h, int propid, int k, int kernel_id, double period, int *period_ignored)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] { populate(*t, propid, k, kernel_id, period, period_ignored); });
+}
+
+int pnb_knn(pnb_tree *h, int k, double period_in, int64_t *idx_out, void *d2_out, void *h_out, int *period_ignored)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        require_device();
+        if (k > t->n) throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
+        if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
+        const double period = effective_period(*t, period_in, period_ignored);
+        const size_t ts = tsize(t->dtype);
+        StageTimer timer(1, t->stream);
+        DevBuf idx(sizeof(int64_t) * (size_t)t->n * k), d2(ts * (size_t)t->n * k);
+        run_knn(*t, k, period, false, make_kernel_params(0, k), idx.as<int64_t>(), d2.p);
+        PNB_CUDA(cudaMemcpyAsync(idx_out, idx.p, idx.bytes, cudaMemcpyDeviceToHost, t->stream));
+        PNB_CUDA(cudaMemcpyAsync(d2_out, d2.p, d2.bytes, cudaMemcpyDeviceToHost, t->stream));
+        if (h_out) {
+            DevBuf hf(ts * t->n);
+            permute_to_file(*t, t->smooth_t.p, hf.p, 1, (int)ts, t->stream);
+            PNB_CUDA(cudaMemcpyAsync(h_out, hf.p, hf.bytes, cudaMemcpyDeviceToHost, t->stream));
+            PNB_CUDA(cudaStreamSynchronize(t->stream));
+        }
+        PNB_CUDA(cudaStreamSynchronize(t->stream));
+        timer.stop();
+    });
+}
+
+int pnb_ball_query(pnb_tree *h, double cx, double cy, double cz, double r, double period_in, int64_t *out,
+                   int64_t cap, int64_t *n_found)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        require_device();
+        const double period = effective_period(*t, period_in, nullptr);
+        int64_t f = run_ball_query(*t, cx, cy, cz, r, period, out, out ? cap : 0);
+        if (n_found) *n_found = f;
+    });
+}
+
+double pnb_last_device_ms(int stage) { return (stage >= 0 && stage < 3) ? g_stage_ms[stage] : 0.0; }
+int64_t pnb_last_launch_count(int stage) { return (stage >= 0 && stage < 3) ? g_stage_launches[stage] : 0; }
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// common.cuh -- shared definitions of libpnb_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/pnb_b200.h"
+
+namespace pnb {
+
+// ------------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside the library, translated to status codes at the C boundary
+// ------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string &m);
+
+#define PNB_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            throw ::pnb::Error(PNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// every kernel launch of the library goes through this so bench.py can report gpu_launches
+extern thread_local int64_t g_launches;
+#define PNB_LAUNCH(kernel, grid, block, smem, stream, ...)                                        \
+    do {                                                                                          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                               \
+        ++::pnb::g_launches;                                                                      \
+        PNB_CUDA(cudaGetLastError());                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device buffer with RAII (stream-ordered allocator)
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t b) { alloc(b); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t b) {
+        release();
+        if (b == 0) b = 16;
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            throw Error(PNB_ERR_MEMORY, "cudaMalloc of " + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        bytes = b;
+    }
+    void release() { if (p) { cudaFree(p); p = nullptr; bytes = 0; } }
+    template <typename U> U *as() const { return reinterpret_cast<U *>(p); }
+};
+
+// a borrowed array registered through pnb_set_array (kdmain.cpp:511-579)
+struct ArrRef {
+    void *ptr = nullptr;
+    int64_t stride0 = 0, stride1 = 0;
+    int ncols = 0, dtype = -1, mem = 0;
+    bool set() const { return ptr != nullptr; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the tree handle
+// ------------------------------------------------------------------------------------------------
+struct Tree {
+    int dtype = PNB_F64;          // PNB_F32 / PNB_F64: dtype of pos/mass/smooth/rho ("T")
+    int64_t n = 0;
+    int user_leafsize = 16;
+    int levels = 0;               // depth of the device tree: buckets live at heap level `levels`
+    int64_t nsplit = 1;           // number of buckets = 1 << levels
+    cudaStream_t stream = nullptr;
+
+    // particles in tree order (T), structure of arrays
+    DevBuf x, y, z, mass;
+    bool has_mass = false;
+    DevBuf order;                 // uint32[n]: tree position -> file index
+    DevBuf box;                   // T[2*nsplit][6]: tight bounds of every node (heap index, root = 1)
+    DevBuf bucket_start;          // int32[nsplit + 1]
+    DevBuf split_dim, split_val;  // int8 / T [2*nsplit]: split axis and value of internal nodes (export only)
+    double root_min[3] = {0, 0, 0}, root_max[3] = {0, 0, 0};
+
+    // results kept resident in tree order between populate calls
+    DevBuf smooth_t, rho_t;       // T[n]
+    bool smooth_valid = false;    // smooth_t holds this tree's own kNN smoothing lengths ...
+    int smooth_k = 0;             // ... for this k
+    double smooth_period = 0;     // ... and this effective period (<=0: open)
+    bool rho_valid = false;       // rho_t was computed from smooth_t (fused with the kNN pass)
+    int rho_kernel = -1;
+
+    ArrRef arr[5];
+};
+
+inline size_t tsize(int dtype) { return dtype == PNB_F64 ? 8 : 4; }
+
+// ---- stage timing (pnb_last_device_ms) ----------------------------------------------------------
+struct StageTimer {
+    int stage;
+    cudaStream_t stream;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int64_t launches0;
+    StageTimer(int stage, cudaStream_t s);
+    void stop();
+    ~StageTimer();
+};
+
+// ---- host <-> device movement of strided arrays (io.cu) ------------------------------------------
+// Bring `ncols` columns of a strided [n][ncols] array (host or device) into a dense device buffer
+// laid out column-major ([ncols][n]) in FILE order.
+void fetch_columns(const void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem,
+                   int64_t n, void *dev_out, cudaStream_t stream);
+// Write a dense column-major device buffer ([ncols][n], file order) back to a strided destination.
+void store_columns(void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem,
+                   int64_t n, const void *dev_in, cudaStream_t stream);
+// tree-order <-> file-order permutations on the device (element size 4 or 8, ncols columns)
+void permute_to_tree(const Tree &t, const void *file_in, void *tree_out, int ncols, int elem, cudaStream_t s);
+void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int ncols, int elem, cudaStream_t s);
+
+// ---- stages --------------------------------------------------------------------------------------
+// cols: file-order coordinates as dense columns T[3][n]; mass_dev: T[n] in file order or null
+void build_tree(Tree &t, DevBuf &cols, const void *mass_dev);
+
+struct KernelParams {
+    int kernel_id;
+    int k;
+    double wendland_self;   // (21/16)*(1-0.0294*pow(k*0.01,-0.977)), sph/kernels.hpp:85-86
+};
+KernelParams make_kernel_params(int kernel_id, int k);
+
+// kNN pass: writes t.smooth_t (and t.rho_t when fuse_rho); optional neighbour lists (file order rows)
+void run_knn(Tree &t, int k, double period /* <=0: open */, bool fuse_rho, const KernelParams &kp,
+             int64_t *nn_idx_dev, void *nn_d2_dev);
+// gather pass for property ids 2..8.  All inputs are dense device arrays in TREE order.
+// smooth/rho: T[n]; qty: Tq [ncols][n]; out: T[n] (rho) or Tq[ncols_out][n].
+// Returns true if some particle found more than k+500 neighbours (smooth.h:253-267).
+bool run_gather(Tree &t, int propid, int k, double period, const KernelParams &kp,
+                const void *smooth_tree, const void *rho_tree, const void *qty_tree, int qdtype,
+                void *out_tree);
+// reference-layout KDNode records (kd.h:29-40) for the user's leafsize (export.cu)
+void export_kdnodes(Tree &t, void *out, int64_t n_nodes);
+void record_stage(int stage, double ms, int64_t launches);
+int64_t run_ball_query(Tree &t, double cx, double cy, double cz, double r, double period,
+                       int64_t *out_host, int64_t cap);
+
+}  // namespace pnb

@@ -1,0 +1,133 @@
+// io.cu -- movement of the borrowed, possibly strided, host or device arrays of the reference ABI
+// (numpy buffers accessed through PyArray_GETPTR in kd.h:163-190) into dense device columns and back,
+// and the tree-order <-> file-order permutations (particleOffsets, kd.h:205-206).
+#include "common.cuh"
+
+namespace pnb {
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <typename E>
+__global__ void k_strided_to_columns(const unsigned char *__restrict__ src, int64_t s0, int64_t s1, int ncols,
+                                     int64_t n, E *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < ncols; ++c)
+        out[(int64_t)c * n + i] = *reinterpret_cast<const E *>(src + i * s0 + c * s1);
+}
+template <typename E>
+__global__ void k_columns_to_strided(const E *__restrict__ in, int64_t s0, int64_t s1, int ncols, int64_t n,
+                                     unsigned char *__restrict__ dst)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < ncols; ++c)
+        *reinterpret_cast<E *>(dst + i * s0 + c * s1) = in[(int64_t)c * n + i];
+}
+template <typename E>
+__global__ void k_to_tree(const uint32_t *__restrict__ order, const E *__restrict__ in, E *__restrict__ out,
+                          int ncols, int64_t n)
+{
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t id = order[p];
+    for (int c = 0; c < ncols; ++c) out[(int64_t)c * n + p] = in[(int64_t)c * n + id];
+}
+template <typename E>
+__global__ void k_to_file(const uint32_t *__restrict__ order, const E *__restrict__ in, E *__restrict__ out,
+                          int ncols, int64_t n)
+{
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t id = order[p];
+    for (int c = 0; c < ncols; ++c) out[(int64_t)c * n + id] = in[(int64_t)c * n + p];
+}
+
+static bool dense_rows(int64_t s0, int64_t s1, int ncols, int64_t elem)
+{
+    return (ncols == 1 || s1 == elem) && s0 == (int64_t)ncols * elem;
+}
+
+void fetch_columns(const void *ptr, int64_t s0, int64_t s1, int ncols, int dtype, int mem, int64_t n, void *dev_out,
+                   cudaStream_t stream)
+{
+    const int64_t elem = (int64_t)tsize(dtype);
+    if (s0 % elem || (ncols > 1 && s1 % elem) || ((uintptr_t)ptr % elem))
+        throw Error(PNB_ERR_VALUE, "array is not aligned to its element size");
+    const int BS = 256;
+    if (mem == PNB_DEVICE) {
+        if (elem == 8) PNB_LAUNCH((k_strided_to_columns<uint64_t>), nblk(n, BS), BS, 0, stream, (const unsigned char *)ptr, s0, s1, ncols, n, (uint64_t *)dev_out);
+        else PNB_LAUNCH((k_strided_to_columns<uint32_t>), nblk(n, BS), BS, 0, stream, (const unsigned char *)ptr, s0, s1, ncols, n, (uint32_t *)dev_out);
+        return;
+    }
+    if (ncols == 1 && s0 == elem) {                                    // dense 1-D: straight copy
+        PNB_CUDA(cudaMemcpyAsync(dev_out, ptr, (size_t)(n * elem), cudaMemcpyHostToDevice, stream));
+        PNB_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
+    DevBuf stage((size_t)(n * ncols * elem));
+    if (dense_rows(s0, s1, ncols, elem)) {
+        PNB_CUDA(cudaMemcpyAsync(stage.p, ptr, stage.bytes, cudaMemcpyHostToDevice, stream));
+    } else {                                                           // arbitrary strides: pack on the host
+        std::vector<unsigned char> packed((size_t)(n * ncols * elem));
+        const unsigned char *src = (const unsigned char *)ptr;
+        for (int64_t i = 0; i < n; ++i)
+            for (int c = 0; c < ncols; ++c)
+                memcpy(&packed[(size_t)((i * ncols + c) * elem)], src + i * s0 + c * s1, (size_t)elem);
+        PNB_CUDA(cudaMemcpyAsync(stage.p, packed.data(), stage.bytes, cudaMemcpyHostToDevice, stream));
+        PNB_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (elem == 8) PNB_LAUNCH((k_strided_to_columns<uint64_t>), nblk(n, BS), BS, 0, stream, stage.as<unsigned char>(), ncols * elem, elem, ncols, n, (uint64_t *)dev_out);
+    else PNB_LAUNCH((k_strided_to_columns<uint32_t>), nblk(n, BS), BS, 0, stream, stage.as<unsigned char>(), ncols * elem, elem, ncols, n, (uint32_t *)dev_out);
+    PNB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void store_columns(void *ptr, int64_t s0, int64_t s1, int ncols, int dtype, int mem, int64_t n, const void *dev_in,
+                   cudaStream_t stream)
+{
+    const int64_t elem = (int64_t)tsize(dtype);
+    if (s0 % elem || (ncols > 1 && s1 % elem) || ((uintptr_t)ptr % elem))
+        throw Error(PNB_ERR_VALUE, "array is not aligned to its element size");
+    const int BS = 256;
+    if (mem == PNB_DEVICE) {
+        if (elem == 8) PNB_LAUNCH((k_columns_to_strided<uint64_t>), nblk(n, BS), BS, 0, stream, (const uint64_t *)dev_in, s0, s1, ncols, n, (unsigned char *)ptr);
+        else PNB_LAUNCH((k_columns_to_strided<uint32_t>), nblk(n, BS), BS, 0, stream, (const uint32_t *)dev_in, s0, s1, ncols, n, (unsigned char *)ptr);
+        return;
+    }
+    if (ncols == 1 && s0 == elem) {
+        PNB_CUDA(cudaMemcpyAsync(ptr, dev_in, (size_t)(n * elem), cudaMemcpyDeviceToHost, stream));
+        PNB_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
+    DevBuf stage((size_t)(n * ncols * elem));
+    if (elem == 8) PNB_LAUNCH((k_columns_to_strided<uint64_t>), nblk(n, BS), BS, 0, stream, (const uint64_t *)dev_in, ncols * elem, elem, ncols, n, stage.as<unsigned char>());
+    else PNB_LAUNCH((k_columns_to_strided<uint32_t>), nblk(n, BS), BS, 0, stream, (const uint32_t *)dev_in, ncols * elem, elem, ncols, n, stage.as<unsigned char>());
+    if (dense_rows(s0, s1, ncols, elem)) {
+        PNB_CUDA(cudaMemcpyAsync(ptr, stage.p, stage.bytes, cudaMemcpyDeviceToHost, stream));
+        PNB_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        std::vector<unsigned char> packed(stage.bytes);
+        PNB_CUDA(cudaMemcpyAsync(packed.data(), stage.p, stage.bytes, cudaMemcpyDeviceToHost, stream));
+        PNB_CUDA(cudaStreamSynchronize(stream));
+        unsigned char *dst = (unsigned char *)ptr;
+        for (int64_t i = 0; i < n; ++i)
+            for (int c = 0; c < ncols; ++c)
+                memcpy(dst + i * s0 + c * s1, &packed[(size_t)((i * ncols + c) * elem)], (size_t)elem);
+    }
+}
+
+void permute_to_tree(const Tree &t, const void *file_in, void *tree_out, int ncols, int elem, cudaStream_t s)
+{
+    const int BS = 256;
+    if (elem == 8) PNB_LAUNCH((k_to_tree<uint64_t>), nblk(t.n, BS), BS, 0, s, t.order.as<uint32_t>(), (const uint64_t *)file_in, (uint64_t *)tree_out, ncols, t.n);
+    else PNB_LAUNCH((k_to_tree<uint32_t>), nblk(t.n, BS), BS, 0, s, t.order.as<uint32_t>(), (const uint32_t *)file_in, (uint32_t *)tree_out, ncols, t.n);
+}
+void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int ncols, int elem, cudaStream_t s)
+{
+    const int BS = 256;
+    if (elem == 8) PNB_LAUNCH((k_to_file<uint64_t>), nblk(t.n, BS), BS, 0, s, t.order.as<uint32_t>(), (const uint64_t *)tree_in, (uint64_t *)file_out, ncols, t.n);
+    else PNB_LAUNCH((k_to_file<uint32_t>), nblk(t.n, BS), BS, 0, s, t.order.as<uint32_t>(), (const uint32_t *)tree_in, (uint32_t *)file_out, ncols, t.n);
+}
+
+}  // namespace pnb

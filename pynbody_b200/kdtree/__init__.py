@@ -1,0 +1,284 @@
+"""GPU drop-in for ``pynbody.kdtree`` (pynbody/kdtree/__init__.py).
+
+``KDTree`` keeps the reference's constructor, attributes and public methods
+(pynbody/kdtree/__init__.py:79-128, 136-163, 167-231, 249-375, 377-538) and drives
+``pynbody_b200.kdtree.kdmain`` -- the drop-in for the native module -- in the same
+sequence the reference drives its C++ extension.  Threads are not used: one call
+runs the whole pass on the GPU.
+"""
+from __future__ import annotations
+
+import logging
+import time
+import warnings
+
+import numpy as np
+
+from ..configuration import config
+from . import kdmain
+from .kdmain import Boundary, KDNode  # noqa: F401  (re-exported like the reference)
+
+logger = logging.getLogger("pynbody_b200.kdtree")
+
+
+class KDTree:
+    """KDTree for smoothing, interpolation and geometrical queries, on the GPU."""
+
+    PROPID_HSM = 1
+    PROPID_RHO = 2
+    PROPID_QTYMEAN_1D = 3
+    PROPID_QTYMEAN_ND = 4
+    PROPID_QTYDISP_1D = 5
+    PROPID_QTYDISP_ND = 6
+    PROPID_QTYDIV = 7
+    PROPID_QTYCURL = 8
+
+    def __init__(self, pos, mass, leafsize=32, boxsize=None, num_threads=None, shared_mem=False):
+        """Create a KDTree (same signature as the reference, pynbody/kdtree/__init__.py:79).
+
+        ``num_threads`` is accepted for compatibility and ignored.  ``shared_mem`` trees (a
+        cross-process host feature of the reference) are not supported.
+        """
+        if shared_mem:
+            raise NotImplementedError("shared_mem trees are a host-side feature outside the GPU path")
+        self._set_num_threads(num_threads)
+        self.leafsize = int(leafsize)
+        self.kdtree = kdmain.init(pos, mass, self.leafsize)
+        self._kdnodes = None
+        self._particle_offsets = None
+        kdmain.build(self.kdtree, None, None, 1)
+        self.boxsize = boxsize
+        self._pos = pos
+        self.set_kernel(_config_kernel())
+
+    # -- reference-layout views, materialised on first access --------------------------------
+    @property
+    def particle_offsets(self):
+        if self._particle_offsets is None:
+            from .. import _lib
+            out = np.empty(self.kdtree.n, dtype=np.intp)
+            _lib.check(_lib.lib().pnb_tree_order(self.kdtree.require_built(), out.ctypes.data))
+            self._particle_offsets = out
+        return self._particle_offsets
+
+    @property
+    def kdnodes(self):
+        if self._kdnodes is None:
+            from .. import _lib
+            out = np.zeros(kdmain.get_node_count(self.kdtree), dtype=KDNode)
+            _lib.check(_lib.lib().pnb_tree_export_kdnodes(self.kdtree.require_built(), out.ctypes.data, len(out)))
+            self._kdnodes = out
+        return self._kdnodes
+
+    def _set_num_threads(self, num_threads):
+        if num_threads is None:
+            num_threads = int(config["number_of_threads"])
+        self.num_threads = num_threads
+        return num_threads
+
+    def serialize(self):
+        """Produce a serialized description of the tree (pynbody/kdtree/__init__.py:136-138)."""
+        return self.leafsize, self.boxsize, self.kdnodes, self.particle_offsets, self._kernel_id
+
+    @classmethod
+    def deserialize(cls, pos, mass, serialized_state, num_threads=None, boxsize=None):
+        """Reconstruct a KDTree from a serialized state (pynbody/kdtree/__init__.py:140-163)."""
+        self = object.__new__(cls)
+        self._set_num_threads(num_threads)
+        leafsize, boxsize_s, kdnodes, particle_offsets, kernel_id = serialized_state
+        if boxsize is not None and boxsize_s is not None and abs(boxsize - boxsize_s) > 1e-6:
+            warnings.warn("Boxsize in serialized state does not match boxsize passed to deserialize")
+        self.kdtree = kdmain.init(pos, mass, leafsize)
+        self.leafsize = leafsize
+        nodes = kdmain.get_node_count(self.kdtree)
+        if len(kdnodes) != nodes:
+            raise ValueError("Number of nodes in serialized state does not match number of nodes in kdtree")
+        if len(particle_offsets) != len(pos):
+            raise ValueError("Number of particle offsets in serialized state does not match number of particles")
+        self._kdnodes = kdnodes
+        self._particle_offsets = particle_offsets
+        self.boxsize = boxsize
+        self._pos = pos
+        self._kernel_id = kernel_id
+        kdmain.import_prebuilt(self.kdtree, kdnodes, particle_offsets, 0)
+        return self
+
+    def _period(self):
+        return -1.0 if self.boxsize is None else float(self.boxsize)
+
+    def particles_in_sphere(self, center, radius):
+        """Indices of the particles within ``radius`` of ``center`` (pynbody/kdtree/__init__.py:167-189)."""
+        smx = kdmain.nn_start(self.kdtree, 1, self._period())
+        try:
+            return kdmain.particles_in_sphere(self.kdtree, smx, center[0], center[1], center[2], radius)
+        finally:
+            kdmain.nn_stop(self.kdtree, smx)
+
+    def nn(self, nn=None):
+        """Generator of ``[i, h_i, [neighbour ids], [d2]]`` (pynbody/kdtree/__init__.py:191-227)."""
+        if nn is None:
+            nn = 64
+        smx = kdmain.nn_start(self.kdtree, int(nn), self._period())
+        kdmain.domain_decomposition(self.kdtree, 1)
+        while True:
+            nbr_list = kdmain.nn_next(self.kdtree, smx)
+            if nbr_list is None:
+                break
+            yield nbr_list
+        kdmain.nn_stop(self.kdtree, smx)
+
+    def all_nn(self, nn=None):
+        """A list of neighbours information for all the particles."""
+        return [x for x in self.nn(nn)]
+
+    def all_nn_arrays(self, nn=None):
+        """Array form of :meth:`all_nn`: ``(idx[N,k], d2[N,k], h[N])`` in file order (GPU-side addition)."""
+        if nn is None:
+            nn = 64
+        smx = kdmain.nn_start(self.kdtree, int(nn), self._period())
+        try:
+            return kdmain.all_neighbours(self.kdtree, smx)
+        finally:
+            smx.nn_result = None
+
+    @staticmethod
+    def array_name_to_id(name):
+        try:
+            return {"smooth": 0, "rho": 1, "mass": 2, "qty": 3, "qty_sm": 4}[name]
+        except KeyError:
+            raise ValueError("Unknown KDTree array") from None
+
+    def set_array_ref(self, name, ar):
+        """Give the native code access to an array (pynbody/kdtree/__init__.py:249-269)."""
+        if self.array_name_to_id(name) < 3:
+            if _np_dtype(self._pos) != _np_dtype(ar):
+                raise TypeError("KDTree requires matching dtypes for %s (%s) and pos (%s) arrays"
+                                % (name, ar.dtype, self._pos.dtype))
+        kdmain.set_arrayref(self.kdtree, self.array_name_to_id(name), ar)
+        assert self.get_array_ref(name) is ar
+
+    def get_array_ref(self, name):
+        return kdmain.get_arrayref(self.kdtree, self.array_name_to_id(name))
+
+    def smooth_operation_to_id(self, name):
+        """Name of a smoothing operation -> property id (pynbody/kdtree/__init__.py:275-320)."""
+        if name == "hsm":
+            return self.PROPID_HSM
+        elif name == "rho":
+            return self.PROPID_RHO
+        elif name in ("qty_mean", "qty_disp"):
+            input_array = self.get_array_ref("qty")
+            one, nd = ((self.PROPID_QTYMEAN_1D, self.PROPID_QTYMEAN_ND) if name == "qty_mean"
+                       else (self.PROPID_QTYDISP_1D, self.PROPID_QTYDISP_ND))
+            if len(input_array.shape) == 1:
+                return one
+            elif len(input_array.shape) == 2:
+                if input_array.shape[1] != 3:
+                    raise ValueError("Currently only able to smooth 3D or 1D arrays")
+                return nd
+            raise ValueError("Currently only able to smooth 3D or 1D arrays")
+        elif name in ("qty_div", "qty_curl"):
+            input_array = self.get_array_ref("qty")
+            if len(input_array.shape) != 2 or input_array.shape[1] != 3:
+                raise ValueError("Can only compute %s of 3D arrays" % ("divergence" if name == "qty_div" else "curl"))
+            return self.PROPID_QTYDIV if name == "qty_div" else self.PROPID_QTYCURL
+        else:
+            raise ValueError("Unknown smoothing request %s" % name)
+
+    def set_kernel(self, kernel=None):
+        """Set the kernel for smoothing operations (pynbody/kdtree/__init__.py:322-334)."""
+        from ..sph import kernels
+        self._kernel_id = kernels.create_kernel(kernel).get_c_kernel_id()
+
+    def populate(self, mode, nn):
+        """Run the operation ``mode`` with ``nn`` neighbours (pynbody/kdtree/__init__.py:338-375)."""
+        if nn is None:
+            nn = 64
+        smx = kdmain.nn_start(self.kdtree, int(nn), self._period())
+        try:
+            propid = self.smooth_operation_to_id(mode)
+            if propid == self.PROPID_HSM:
+                kdmain.domain_decomposition(self.kdtree, 1)
+            kdmain.populate(self.kdtree, smx, propid, 0, self._kernel_id)
+        finally:
+            kdmain.nn_stop(self.kdtree, smx)
+
+    def _output_like(self, array, shape=None, units=None):
+        if kdmain._lib._is_torch(array):
+            import torch
+            return torch.empty(shape if shape is not None else tuple(array.shape), dtype=array.dtype, device=array.device)
+        out = np.empty_like(array) if shape is None else np.empty(shape, dtype=array.dtype)
+        if hasattr(array, "units"):
+            out = out.view(type(array))
+            out.units = array.units if units is None else units
+        return out
+
+    def sph_mean(self, array, nsmooth=64):
+        """SPH mean of an array (pynbody/kdtree/__init__.py:377-419)."""
+        output = self._output_like(array)
+        self.set_array_ref("qty", array)
+        self.set_array_ref("qty_sm", output)
+        logger.info("Smoothing array with %d nearest neighbours" % nsmooth)
+        start = time.time()
+        self.populate("qty_mean", nsmooth)
+        logger.info("SPH smooth done in %5.3g s" % (time.time() - start))
+        return output
+
+    def sph_dispersion(self, array, nsmooth=64):
+        """SPH dispersion of an array (pynbody/kdtree/__init__.py:421-470).
+
+        As in the reference the output is allocated with the input's shape; for N x 3 input the
+        single dispersion per particle lands in column 0 (smDispQtyND writes through a 1-D accessor).
+        """
+        output = self._output_like(array)
+        self.set_array_ref("qty", array)
+        self.set_array_ref("qty_sm", output)
+        logger.info("Getting dispersion of array with %d nearest neighbours" % nsmooth)
+        start = time.time()
+        self.populate("qty_disp", nsmooth)
+        logger.info("SPH dispersion done in %5.3g s" % (time.time() - start))
+        return output
+
+    def _sph_differential_operator(self, array, op, nsmooth=64):
+        if op == "div":
+            op_label = "divergence"
+            output = self._output_like(array, shape=(len(array),),
+                                       units=(array.units / self._pos.units) if hasattr(array, "units") and hasattr(self._pos, "units") else None)
+        elif op == "curl":
+            op_label = "curl"
+            output = self._output_like(array,
+                                       units=(array.units / self._pos.units) if hasattr(array, "units") and hasattr(self._pos, "units") else None)
+        else:
+            raise ValueError("Can only compute curl or divergence")
+        self.set_array_ref("qty", array)
+        self.set_array_ref("qty_sm", output)
+        logger.info("Getting %s of array with %d nearest neighbours" % (op_label, nsmooth))
+        start = time.time()
+        self.populate("qty_%s" % op, nsmooth)
+        logger.info(f"SPH {op_label} done in {time.time() - start:5.3g} s")
+        return output
+
+    def sph_curl(self, array, nsmooth=64):
+        return self._sph_differential_operator(array, "curl", nsmooth)
+
+    def sph_divergence(self, array, nsmooth=64):
+        return self._sph_differential_operator(array, "div", nsmooth)
+
+    def __del__(self):
+        if hasattr(self, "kdtree"):
+            try:
+                kdmain.free(self.kdtree)
+            except Exception:
+                pass
+
+
+def _np_dtype(a):
+    from .. import _lib
+    return _lib.dtype_code(a)
+
+
+def _config_kernel():
+    try:
+        return config["sph"].get("kernel", "CubicSplineKernel")
+    except Exception:
+        return "CubicSplineKernel"
