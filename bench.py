@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the SPH smoothing hot path: particles/s for ``sim['rho']`` (k = 64).
+
+One *step* = one pass of the path pynbody runs for ``sim['rho']`` on one particle set:
+kd-tree build -> k-nearest-neighbour smoothing lengths (``sim['smooth']``) -> SPH density, through
+the reference-facing ``KDTree`` API (``KDTree(pos, mass)``, ``populate('hsm')``, ``populate('rho')``).
+
+Workload: BASELINE.json configs[1] -- 16 777 216-particle (256^3) clustered Zel'dovich-like periodic box,
+WendlandC2 kernel, 64 neighbours, float64, one B200 per rank.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+``value``   whole-job particles/s with positions and masses resident in HBM (torch CUDA tensors handed
+            to the C ABI by pointer), timed with CUDA events, max over ranks.
+``e2e``     the same step from HOST arrays in pinned memory through the same public API: host->device
+            copies of pos/mass (and smooth/mass again for populate('rho'), as the reference ABI
+            re-reads its borrowed arrays) and device->host copies of smooth/rho are inside the timed region.
+``--impl reference``  the reference's own compiled C++ path (oracle/_ref, built from /root/reference by
+            oracle/Makefile) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_NEIGHBOURS = 64
+KERNEL = "WendlandC2Kernel"
+METRIC = "particles/sec for sim['rho'] (k=64)"
+UNIT = "particles/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_particles(n_side, seed, dtype):
+    from pynbody_b200 import synth
+    return synth.zeldovich_box(n_side, seed, dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_step(pos, mass, threads):
+    """The reference's own path for sim['rho'] (sph/__init__.py:40-94), via its compiled modules."""
+    from oracle import ref
+    kd = ref.RefKDTree(pos, mass, 16, 1.0, threads, 1)
+    kd.smooth(K_NEIGHBOURS)
+    kd.rho(K_NEIGHBOURS)
+    return kd
+
+
+def oracle_step(pos, mass, threads):
+    from oracle import oracle
+    kd = oracle.OracleKDTree(pos, mass, 16, 1.0, threads, 1)
+    kd.smooth(K_NEIGHBOURS)
+    kd.rho(K_NEIGHBOURS)
+    return kd
+
+
+def cpu_arm(sample_side, dtype, steps, warmup):
+    from oracle import ref
+    threads = os.cpu_count() or 1
+    pos, vel, mass = make_particles(sample_side, 2, dtype)
+    if ref.available():
+        kind, fn = "reference", reference_step
+    else:
+        kind, fn = "port", oracle_step
+    for _ in range(warmup):
+        fn(pos, mass, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn(pos, mass, threads)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": len(pos) / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{sample_side}^3 = {len(pos)} particles of the same Zel'dovich box recipe, {np.dtype(dtype).name}, "
+                      f"k={K_NEIGHBOURS}, WendlandC2: tree build + smooth + rho, {steps} timed run(s)",
+            "seconds_per_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    res = cpu_arm(args.cpu_sample_side, dtype, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, reference=True),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, reference=False):
+    n = args.n_side ** 3
+    return {"workload": f"C2: {n}-particle ({args.n_side}^3) clustered Zel'dovich-like periodic box per GPU, "
+                        f"sim['rho'] = kd-tree build + smooth + rho, k={K_NEIGHBOURS}, WendlandC2, {args.dtype}",
+            "particles_per_gpu": n, "k": K_NEIGHBOURS, "kernel": "WendlandC2", "boxsize": 1.0,
+            "parallelism": "one independent box per GPU (no data-path collective)" if args.gpus > 1 else "single GPU",
+            "l2_policy": "inputs (pos+mass, 32 B/particle f64) exceed the 126 MB L2; no explicit flush",
+            **({"reference_sample_side": args.cpu_sample_side} if reference else {})}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pynbody_b200.kdtree import KDTree, kdmain
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tsz = np.dtype(dtype).itemsize
+
+    pos, vel, mass = make_particles(args.n_side, 2 + rank, dtype)
+    n = len(pos)
+    # pinned host copies (what the e2e leg reads / writes) and device-resident copies (the value leg)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:1]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    h_pos, h_mass = pinned(pos), pinned(mass)
+    h_sm = torch.empty(n, dtype=h_mass.dtype, pin_memory=True)
+    h_rho = torch.empty(n, dtype=h_mass.dtype, pin_memory=True)
+    d_pos, d_mass = h_pos.cuda(), h_mass.cuda()
+    d_sm, d_rho = torch.empty_like(d_mass), torch.empty_like(d_mass)
+    del pos, mass
+
+    stats = {"build_ms": [], "knn_ms": [], "knn_kernel_ms": [], "rho_ms": [], "launches": 0}
+
+    def step(p, m, sm, rho, record):
+        kd = KDTree(p, m, leafsize=16, boxsize=1.0)
+        kd.set_kernel(KERNEL)
+        b_ms, b_l = kdmain.last_device_ms(0), kdmain.last_launch_count(0)
+        kd.set_array_ref("smooth", sm)
+        kd.populate("hsm", K_NEIGHBOURS)
+        k_ms, k_l, kk_ms = kdmain.last_device_ms(1), kdmain.last_launch_count(1), kdmain.last_kernel_ms(0)
+        kd.set_array_ref("mass", m)
+        kd.set_array_ref("rho", rho)
+        kd.populate("rho", K_NEIGHBOURS)
+        r_ms, r_l = kdmain.last_device_ms(1), kdmain.last_launch_count(1)
+        if args.verbose and rank == 0:
+            print(f"[step] build {b_ms:.1f} ms ({b_l} launches) | hsm {k_ms:.1f} ms (kernel {kk_ms:.1f}) | rho {r_ms:.1f} ms",
+                  file=sys.stderr, flush=True)
+        if record:
+            stats["build_ms"].append(b_ms); stats["knn_ms"].append(k_ms); stats["knn_kernel_ms"].append(kk_ms)
+            stats["rho_ms"].append(r_ms); stats["launches"] += b_l + k_l + r_l
+        return kd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(d_pos, d_mass, d_sm, d_rho, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(lambda: step(d_pos, d_mass, d_sm, d_rho, True), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # end to end from pinned host memory through the same public API
+    step(h_pos.numpy(), h_mass.numpy(), h_sm.numpy(), h_rho.numpy(), False)
+    e2e_ms = timed(lambda: step(h_pos.numpy(), h_mass.numpy(), h_sm.numpy(), h_rho.numpy(), False), args.steps) / args.steps
+    e2e_value = world * n / (e2e_ms * 1e-3)
+    h2d = n * tsz * (3 + 1) + n * tsz * 2        # pos + mass at build; smooth + mass re-read by populate('rho')
+    d2h = n * tsz * 2                            # smooth, rho
+
+    # other stages of the path, for the record (not part of `value`)
+    kd = step(d_pos, d_mass, d_sm, d_rho, False)
+    d_vel = torch.from_numpy(vel).cuda()
+    extra = {}
+    for name, fn in (("v_mean", kd.sph_mean), ("v_disp", kd.sph_dispersion), ("v_div", kd.sph_divergence),
+                     ("v_curl", kd.sph_curl)):
+        fn(d_vel, K_NEIGHBOURS)
+        torch.cuda.synchronize()
+        extra[name + "_ms"] = round(kdmain.last_device_ms(1), 3)
+        extra[name + "_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+    sm2 = d_sm.clone(); sm2[0] = sm2[0] * (1 + 1e-7)
+    kd.set_array_ref("smooth", sm2); kd.set_array_ref("rho", d_rho)
+    kd.populate("rho", K_NEIGHBOURS)
+    extra["rho_gather_ms"] = round(kdmain.last_device_ms(1), 3)
+    extra["rho_gather_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    knn_kernel_ms = float(np.mean(stats["knn_kernel_ms"]))
+    alg_bytes = n * 6 * tsz                      # read pos 3s + mass s, write smooth s + rho s
+    achieved = alg_bytes / (knn_kernel_ms * 1e-3) / 1e9
+    gather_bytes = n * K_NEIGHBOURS * 4 * tsz + alg_bytes
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": stats["launches"],
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_knn (kNN smoothing lengths + fused density)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_particle": 6 * tsz,
+                     "kernel_ms": knn_kernel_ms,
+                     "logical_gather_gbs": gather_bytes / (knn_kernel_ms * 1e-3) / 1e9,
+                     "neighbour_interactions_per_s": n * K_NEIGHBOURS / (knn_kernel_ms * 1e-3),
+                     "note": "irregular tree search: bound by on-chip queue updates and L2 latency, not by HBM bytes "
+                             "(SURVEY.md 8d); traffic from ncu is in profiles/"},
+        "stages_ms": {"build": float(np.mean(stats["build_ms"])), "smooth_incl_fused_rho": float(np.mean(stats["knn_ms"])),
+                      "knn_kernel": knn_kernel_ms, "rho_readback": float(np.mean(stats["rho_ms"])), **extra},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        res = cpu_arm(args.cpu_sample_side, dtype, 1, 0)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--n-side", type=int, default=256, help="particles per GPU = n_side^3 (256 -> 16.7M)")
+    ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
+    ap.add_argument("--cpu-sample-side", type=int, default=128, help="CPU baseline sample = side^3 particles")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="per-step stage times on stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -163,12 +163,19 @@ int pnb_render_grid(int nx, int ny, int nz, const pnb_render_arrays *a,
                     const double *wrap_z, int n_wrap_z,
                     float *out, int out_mem);
 
+/* Return the device memory the library keeps cached for re-use (freed work buffers) to the driver. */
+void pnb_release_cached_memory(void);
+
 /* ---- timing hooks (bench.py) ------------------------------------------------------------------
  * Device time in milliseconds of the kernels launched by the last pnb_tree_create (stage 0),
  * pnb_populate / pnb_knn (stage 1) or render call (stage 2) on this thread, measured with CUDA
  * events on the library's stream; also the number of kernel launches of that call. */
 double pnb_last_device_ms(int stage);
 int64_t pnb_last_launch_count(int stage);
+/* Duration (ms, CUDA events on the launching stream) of the last launch of one of the dominant
+ * kernels on this thread: 0 = kNN (+fused density) kernel, 1 = gather/reduction kernel,
+ * 2 = image/grid render kernel.  This is what bench.py's roofline block divides by. */
+double pnb_last_kernel_ms(int which);
 
 #ifdef __cplusplus
 }

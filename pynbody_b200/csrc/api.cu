@@ -5,6 +5,8 @@
 // smInit (smooth.h:71-124), array registration, and moving results back to the caller's borrowed
 // arrays in file order.
 #include "common.cuh"
+#include <map>
+#include <mutex>
 
 namespace pnb {
 
@@ -18,6 +20,30 @@ void record_stage(int stage, double ms, int64_t launches)
 {
     g_stage_ms[stage] = ms;
     g_stage_launches[stage] = launches;
+}
+
+static thread_local double g_kernel_ms[3] = {0, 0, 0};
+KernelTimer::KernelTimer(int w, cudaStream_t s) : which(w), stream(s)
+{
+    PNB_CUDA(cudaEventCreate(&a));
+    PNB_CUDA(cudaEventCreate(&b));
+    PNB_CUDA(cudaEventRecord(a, stream));
+}
+void KernelTimer::stop()
+{
+    if (!a) return;
+    PNB_CUDA(cudaEventRecord(b, stream));
+    PNB_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    PNB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    g_kernel_ms[which] = ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    a = b = nullptr;
+}
+KernelTimer::~KernelTimer()
+{
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
 }
 
 StageTimer::StageTimer(int st, cudaStream_t s) : stage(st), stream(s), launches0(g_launches)
@@ -42,6 +68,67 @@ StageTimer::~StageTimer()
 {
     if (a) cudaEventDestroy(a);
     if (b) cudaEventDestroy(b);
+}
+
+// ---- caching device allocator ---------------------------------------------------------------------
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void *>> free_lists;   // (device, bytes) -> blocks
+    size_t cached_bytes = 0;
+    void trim_locked()
+    {
+        for (auto &kv : free_lists)
+            for (void *q : kv.second) cudaFree(q);
+        free_lists.clear();
+        cached_bytes = 0;
+    }
+};
+BlockCache &block_cache() { static BlockCache c; return c; }
+}  // namespace
+
+void *cache_alloc(size_t bytes)
+{
+    int dev = 0;
+    PNB_CUDA(cudaGetDevice(&dev));
+    BlockCache &c = block_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_lists.find({dev, bytes});
+    if (it != c.free_lists.end() && !it->second.empty()) {
+        void *p = it->second.back();
+        it->second.pop_back();
+        c.cached_bytes -= bytes;
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {                     // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        c.trim_locked();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw Error(PNB_ERR_MEMORY, "device allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    return p;
+}
+void cache_free(void *p, size_t bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+    BlockCache &c = block_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.free_lists[{dev, bytes}].push_back(p);
+    c.cached_bytes += bytes;
+}
+void cache_trim()
+{
+    BlockCache &c = block_cache();
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.trim_locked();
 }
 
 static void require_device()
@@ -128,6 +215,40 @@ static bool device_equal(Tree &t, const void *a, const void *b, size_t bytes)
     PNB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
     PNB_CUDA(cudaStreamSynchronize(t.stream));
     return h == 0;
+}
+
+template <typename T>
+__global__ void k_any_differs_from_first(const T *m, int64_t n, int *differs)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const T m0 = m[0];
+    bool d = false;
+    for (int64_t j = i; j < n; j += stride) d |= m[j] != m0;
+    if (d) *differs = 1;
+}
+static void update_mass_uniformity(Tree &t)
+{
+    t.mass_is_uniform = false;
+    if (!t.has_mass) return;
+    DevBuf flag(sizeof(int));
+    PNB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), t.stream));
+    if (t.dtype == PNB_F64) PNB_LAUNCH((k_any_differs_from_first<double>), 1184, 256, 0, t.stream, t.mass.as<double>(), t.n, flag.as<int>());
+    else PNB_LAUNCH((k_any_differs_from_first<float>), 1184, 256, 0, t.stream, t.mass.as<float>(), t.n, flag.as<int>());
+    int h = 0;
+    double m0 = 0;
+    PNB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
+    if (t.dtype == PNB_F64) {
+        PNB_CUDA(cudaMemcpyAsync(&m0, t.mass.p, sizeof(double), cudaMemcpyDeviceToHost, t.stream));
+        PNB_CUDA(cudaStreamSynchronize(t.stream));
+    } else {
+        float f = 0;
+        PNB_CUDA(cudaMemcpyAsync(&f, t.mass.p, sizeof(float), cudaMemcpyDeviceToHost, t.stream));
+        PNB_CUDA(cudaStreamSynchronize(t.stream));
+        m0 = f;
+    }
+    t.mass_is_uniform = h == 0;
+    t.uniform_mass = m0;
 }
 
 static void populate(Tree &t, int propid, int k, int kernel_id, double period_in, int *period_ignored)
@@ -231,6 +352,7 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
             fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
         }
         build_tree(*t, cols, mass ? mass_dev.p : nullptr);
+        update_mass_uniformity(*t);
         timer.stop();
     });
     if (rc != PNB_OK) { delete t; return nullptr; }
@@ -316,6 +438,7 @@ int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t strid
                 t->mass = std::move(m);
                 t->has_mass = true;
                 t->rho_valid = false;
+                update_mass_uniformity(*t);
             }
         }
         t->arr[id] = r;
@@ -365,7 +488,10 @@ int pnb_ball_query(pnb_tree *h, double cx, double cy, double cz, double r, doubl
     });
 }
 
+void pnb_release_cached_memory(void) { cache_trim(); }
+
 double pnb_last_device_ms(int stage) { return (stage >= 0 && stage < 3) ? g_stage_ms[stage] : 0.0; }
+double pnb_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? g_kernel_ms[which] : 0.0; }
 int64_t pnb_last_launch_count(int stage) { return (stage >= 0 && stage < 3) ? g_stage_launches[stage] : 0; }
 
 }  // extern "C"

@@ -40,31 +40,36 @@ extern thread_local int64_t g_launches;
 // ------------------------------------------------------------------------------------------------
 // device buffer with RAII (stream-ordered allocator)
 // ------------------------------------------------------------------------------------------------
+// Device memory comes from a small caching allocator (api.cu): blocks are cudaMalloc'ed once, kept
+// on per-size free lists when released and handed out again to the next request of the same size.
+// All library work is issued on one stream, so re-use in stream order is safe without
+// synchronisation; a steady-state step performs no driver allocation at all (cudaMalloc/cudaFree
+// synchronise the device and were measured to stall for hundreds of ms).
+void *cache_alloc(size_t bytes);
+void cache_free(void *p, size_t bytes);
+void cache_trim();
 struct DevBuf {
     void *p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0;     // requested size
+    size_t cap = 0;       // allocated size (cache size class)
     DevBuf() = default;
     explicit DevBuf(size_t b) { alloc(b); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), cap(o.cap) { o.p = nullptr; o.bytes = o.cap = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; cap = o.cap; o.p = nullptr; o.bytes = o.cap = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(size_t b) {
         release();
-        if (b == 0) b = 16;
-        cudaError_t e = cudaMalloc(&p, b);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            cudaGetLastError();
-            throw Error(PNB_ERR_MEMORY, "cudaMalloc of " + std::to_string(b) + " bytes failed: " + cudaGetErrorString(e));
-        }
+        cap = (b + 511) & ~(size_t)511;
+        if (cap == 0) cap = 512;
+        p = cache_alloc(cap);
         bytes = b;
     }
-    void release() { if (p) { cudaFree(p); p = nullptr; bytes = 0; } }
+    void release() { if (p) { cache_free(p, cap); p = nullptr; bytes = cap = 0; } }
     template <typename U> U *as() const { return reinterpret_cast<U *>(p); }
 };
 
@@ -90,6 +95,8 @@ struct Tree {
     // particles in tree order (T), structure of arrays
     DevBuf x, y, z, mass;
     bool has_mass = false;
+    bool mass_is_uniform = false; // every particle has the same mass (then density can ride along the kNN pass)
+    double uniform_mass = 0;
     DevBuf order;                 // uint32[n]: tree position -> file index
     DevBuf box;                   // T[2*nsplit][6]: tight bounds of every node (heap index, root = 1)
     DevBuf bucket_start;          // int32[nsplit + 1]
@@ -118,6 +125,16 @@ struct StageTimer {
     StageTimer(int stage, cudaStream_t s);
     void stop();
     ~StageTimer();
+};
+
+// times one kernel launch with CUDA events on its stream (pnb_last_kernel_ms)
+struct KernelTimer {
+    int which;
+    cudaStream_t stream;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(int which, cudaStream_t s);
+    void stop();        // records the end event, waits for it, stores the duration
+    ~KernelTimer();
 };
 
 // ---- host <-> device movement of strided arrays (io.cu) ------------------------------------------

@@ -190,8 +190,10 @@ template <typename T, typename Q, int OP>
 static void launch_gather(Tree &t, GatherArgs<T, Q> &a)
 {
     const unsigned grid = (unsigned)((t.nsplit + GATHER_WARPS - 1) / GATHER_WARPS);
+    KernelTimer timer(1, t.stream);
     if (a.tv.periodic) PNB_LAUNCH((k_gather<T, Q, OP, true>), grid, GATHER_WARPS * 32, 0, t.stream, a);
     else PNB_LAUNCH((k_gather<T, Q, OP, false>), grid, GATHER_WARPS * 32, 0, t.stream, a);
+    timer.stop();
 }
 
 template <typename T, typename Q>

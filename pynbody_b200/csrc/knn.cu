@@ -10,53 +10,77 @@
 // with a per-lane periodic box test (kd.h:68-154) combined by a warp vote.  A candidate bucket is
 // staged in shared memory (3 coalesced lines) and every lane measures all 32 candidates against its
 // own query; survivors (d2 < current k-th distance) are remembered in a 32-bit register mask and
-// then inserted into the lane's private bounded max-heap.  The heaps live in shared memory in
-// lane-interleaved layout (entry e of lane l at [e*32+l]: conflict-free), the current k-th distance
-// and the query in registers.  Insertions of all lanes run together, so a sift-down step is useful
-// work for every lane that has something pending.
+// then inserted into the lane's private bounded neighbour queue, all lanes inserting together.
+//
+// The queue (the reference's max-heap, pq.h) is a "grouped max-cache": the k distances live in
+// shared memory, lane-interleaved (entry e of lane l at [e*32+l]: conflict-free), split into 8 groups
+// of S = ceil(k/8) slots; the maximum of every group, its slot, and the overall maximum (the current
+// k-th distance) live in registers.  Replacing the current maximum is one store plus one rescan of a
+// single group: S independent shared-memory loads (one latency) instead of the log2(k) dependent
+// load/compare/store rounds of a binary heap sift-down -- the v1 profile (profiles/r1_knn_v1_*)
+// showed that sift-down as 45 % of all issue slots at 9 of 32 lanes active.
 #include "traverse.cuh"
 
 namespace pnb {
 
-constexpr int KNN_WARPS = 4;
+constexpr int KNN_WARPS = 2;
+constexpr int NGROUP = 8;
 
 template <typename T>
 struct KnnArgs {
     TreeView<T> tv;
     int k;
+    int S;                  // slots per group, ceil(k / NGROUP)
     T *smooth_t;            // [n] tree order
-    T *rho_t;               // [n] tree order (FUSE_RHO)
+    T *rho_t;               // [n] tree order (FUSE_RHO: all particles have mass `uniform_mass`)
+    double uniform_mass;
     int kernel_id;
     double wendland_self;
     int64_t *nn_idx;        // [n][k] file-order rows, or null
     T *nn_d2;               // [n][k]
 };
 
-// replace the root of lane's max-heap (stride-32 layout) by (v,id) and restore heap order
+template <typename T>
+struct TopK {
+    T gm[NGROUP];           // maximum of each group
+    unsigned long long gp;  // slot (within its group) of each group's maximum, 8 bits per group
+    T top;                  // overall maximum = k-th smallest d2 so far (+inf until k are held, pq.h:185-192)
+};
+
+// replace the current maximum by (v, id)
 template <typename T, bool WITH_IDX>
-__device__ __forceinline__ void heap_replace_top(T *hd, int32_t *hi, int k, T v, int32_t id)
+__device__ __forceinline__ void topk_replace_max(TopK<T> &q, T *hd, int32_t *hi, int S, T v, int32_t id)
 {
-    int p = 0;
-    for (;;) {
-        int c = 2 * p + 1;
-        if (c >= k) break;
-        T dc = hd[c * 32];
-        if (c + 1 < k) {
-            T dr = hd[(c + 1) * 32];
-            if (dr > dc) { dc = dr; ++c; }
-        }
-        if (!(v < dc)) break;
-        hd[p * 32] = dc;
-        if (WITH_IDX) hi[p * 32] = hi[c * 32];
-        p = c;
+    int g = 0;
+#pragma unroll
+    for (int i = NGROUP - 1; i >= 0; --i)
+        if (q.gm[i] == q.top) g = i;
+    const int s = (int)((q.gp >> (8 * g)) & 0xffull);
+    T *grp = hd + (size_t)g * S * 32;
+    grp[s * 32] = v;
+    if (WITH_IDX) hi[(g * S + s) * 32] = id;
+    // rescan the group: S independent loads
+    T m = grp[0];
+    int pos = 0;
+#pragma unroll 4
+    for (int t = 1; t < S; ++t) {
+        T val = grp[t * 32];
+        if (val > m) { m = val; pos = t; }
     }
-    hd[p * 32] = v;
-    if (WITH_IDX) hi[p * 32] = id;
+#pragma unroll
+    for (int i = 0; i < NGROUP; ++i)
+        if (i == g) q.gm[i] = m;
+    q.gp = (q.gp & ~(0xffull << (8 * g))) | ((unsigned long long)pos << (8 * g));
+    T a0 = q.gm[0] > q.gm[1] ? q.gm[0] : q.gm[1], a1 = q.gm[2] > q.gm[3] ? q.gm[2] : q.gm[3];
+    T a2 = q.gm[4] > q.gm[5] ? q.gm[4] : q.gm[5], a3 = q.gm[6] > q.gm[7] ? q.gm[6] : q.gm[7];
+    a0 = a0 > a1 ? a0 : a1;
+    a2 = a2 > a3 ? a2 : a3;
+    q.top = a0 > a2 ? a0 : a2;
 }
 
-template <typename T, bool WITH_IDX, bool PERIODIC>
+template <typename T, bool WITH_IDX>
 __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t bucket, bool pass, T sx, T sy, T sz,
-                                                 T &top, T *hd, int32_t *hi, int k, T *tile, int lane)
+                                                 TopK<T> &q, T *hd, int32_t *hi, int S, T *tile, int lane)
 {
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -69,24 +93,28 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
     __syncwarp();
     // phase A: all candidates against this lane's query, branch-free
     unsigned mask = 0;
+    const T top0 = q.top;
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
         T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-        mask |= (unsigned)(d2 < top) << j;
+        mask |= (unsigned)(d2 < top0) << j;
     }
     if (!pass) mask = 0;
     // phase B: all lanes insert their survivors together
     while (__any_sync(FULL, mask != 0)) {
         if (mask) {
-            int j = __ffs(mask) - 1;
+            const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (d2 < top) {
-                heap_replace_top<T, WITH_IDX>(hd, hi, k, d2, start + j);
-                top = hd[0];
-            }
+            const T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+            if (d2 < q.top) topk_replace_max<T, WITH_IDX>(q, hd, hi, S, d2, start + j);
         }
     }
+}
+
+template <typename T, bool WITH_IDX>
+__host__ __device__ inline size_t knn_smem_per_warp(int S)
+{
+    return (size_t)NGROUP * S * 32 * sizeof(T) + (WITH_IDX ? (size_t)NGROUP * S * 32 * 4 : 0) + 96 * sizeof(T);
 }
 
 template <typename T, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
@@ -97,29 +125,33 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t bucket = (int64_t)blockIdx.x * KNN_WARPS + wib;
     if (bucket >= tv.nsplit) return;                // whole warp exits together; no block barriers below
-    const int k = a.k;
+    const int k = a.k, S = a.S, nslot = NGROUP * S;
 
-    const size_t per_warp = (size_t)k * 32 * sizeof(T) + (WITH_IDX ? (size_t)k * 32 * 4 : 0) + 96 * sizeof(T);
-    unsigned char *base = smem_raw + per_warp * wib;
+    unsigned char *base = smem_raw + knn_smem_per_warp<T, WITH_IDX>(S) * wib;
     T *hd = reinterpret_cast<T *>(base) + lane;
-    int32_t *hi = WITH_IDX ? reinterpret_cast<int32_t *>(base + (size_t)k * 32 * sizeof(T)) + lane : nullptr;
-    T *tile = reinterpret_cast<T *>(base + (size_t)k * 32 * sizeof(T) + (WITH_IDX ? (size_t)k * 32 * 4 : 0));
+    int32_t *hi = WITH_IDX ? reinterpret_cast<int32_t *>(base + (size_t)nslot * 32 * sizeof(T)) + lane : nullptr;
+    T *tile = reinterpret_cast<T *>(base + (size_t)nslot * 32 * sizeof(T) + (WITH_IDX ? (size_t)nslot * 32 * 4 : 0));
 
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
     const bool active = lane < cnt;
     T qx = 0, qy = 0, qz = 0;
     if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
-    for (int e = 0; e < k; ++e) {
-        hd[e * 32] = Ex<T>::inf();
+
+    // slots [0,k) start at +inf (replaced first), padding slots [k, 8S) at -inf (never the maximum)
+    for (int e = 0; e < nslot; ++e) {
+        hd[e * 32] = e < k ? Ex<T>::inf() : -Ex<T>::inf();
         if (WITH_IDX) hi[e * 32] = -1;
     }
-    // k-th smallest d2 so far; +inf until the heap is full (pq.h:185-192); idle lanes never match
-    T top = active ? Ex<T>::inf() : (T)-1;
+    TopK<T> q;
+#pragma unroll
+    for (int g = 0; g < NGROUP; ++g) q.gm[g] = (g * S < k) ? Ex<T>::inf() : -Ex<T>::inf();
+    q.gp = 0;
+    q.top = active ? Ex<T>::inf() : (T)-1;          // idle lanes never match
     const T L = tv.period;
 
     // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
-    knn_visit_bucket<T, WITH_IDX, PERIODIC>(tv, bucket, active, qx, qy, qz, top, hd, hi, k, tile, lane);
+    knn_visit_bucket<T, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, hd, hi, S, tile, lane);
 
     // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
     int64_t cell = tv.nsplit + bucket;
@@ -130,10 +162,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
             Box6<T> b = load_box(tv.box, cp);
             T sx, sy, sz;
             T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
-            bool pass = gap2 <= top * Ex<T>::slack();
+            bool pass = gap2 <= q.top * Ex<T>::slack();
             if (__any_sync(FULL, pass)) {
                 if (cp < tv.nsplit) { cp = 2 * cp; continue; }
-                knn_visit_bucket<T, WITH_IDX, PERIODIC>(tv, cp - tv.nsplit, pass, sx, sy, sz, top, hd, hi, k, tile, lane);
+                knn_visit_bucket<T, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, hd, hi, S, tile, lane);
             }
             cp = next_node(cp);
             if (cp == stop) break;
@@ -143,21 +175,22 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
 
     if (!active) return;
     const int64_t p = start + lane;
-    const T h = (T)0.5 * Ex<T>::sqrt(top);          // smooth.h:429
+    const T h = (T)0.5 * Ex<T>::sqrt(q.top);        // smooth.h:429
     a.smooth_t[p] = h;
 
     if (FUSE_RHO) {
-        // smDensity (smooth.h:626-647) over the heap: the gather set of radius 2h differs from the
-        // heap only by entries at q = 2 where both kernels vanish.
+        // smDensity (smooth.h:626-647) over the queue: the gather set of radius 2h differs from the
+        // k nearest only by entries at q = 2 where both kernels vanish.  All masses are equal here.
         const T ih = (T)(1.0 / (double)h);
         const T ih2 = ih * ih;
         const T norm = (T)(0.31830988618379067154 * (double)ih * (double)ih2);
+        const T m = (T)a.uniform_mass;
         T rho = 0;
         for (int e = 0; e < k; ++e) {
             T q2 = hd[e * 32] * ih2;
             T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)q2);
             w *= norm;
-            rho += w * tv.mass[hi[e * 32]];
+            rho += w * m;
         }
         a.rho_t[p] = rho;
     }
@@ -182,13 +215,11 @@ KernelParams make_kernel_params(int kernel_id, int k)
 template <typename T, bool WITH_IDX, bool FUSE_RHO>
 static void launch_knn(Tree &t, KnnArgs<T> &a)
 {
-    const size_t per_warp = (size_t)a.k * 32 * sizeof(T) + (WITH_IDX ? (size_t)a.k * 32 * 4 : 0) + 96 * sizeof(T);
-    const size_t smem = per_warp * KNN_WARPS;
-    if (smem > 227 * 1024)
-        throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues (k <= "
-                                       + std::to_string((227 * 1024 / KNN_WARPS - 96 * sizeof(T)) / (32 * (sizeof(T) + (WITH_IDX ? 4 : 0))))
-                                       + " for this dtype)");
+    const size_t smem = knn_smem_per_warp<T, WITH_IDX>(a.S) * KNN_WARPS;
+    if (smem > 227 * 1024 || a.S > 255)
+        throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues");
     const unsigned grid = (unsigned)((t.nsplit + KNN_WARPS - 1) / KNN_WARPS);
+    KernelTimer timer(0, t.stream);
     if (a.tv.periodic) {
         auto kern = k_knn<T, WITH_IDX, FUSE_RHO, true>;
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -198,6 +229,7 @@ static void launch_knn(Tree &t, KnnArgs<T> &a)
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PNB_LAUNCH(kern, grid, KNN_WARPS * 32, smem, t.stream, a);
     }
+    timer.stop();
 }
 
 template <typename T>
@@ -209,14 +241,16 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     KnnArgs<T> a;
     a.tv = make_view<T>(t, period);
     a.k = k;
+    a.S = (k + NGROUP - 1) / NGROUP;
     a.smooth_t = t.smooth_t.as<T>();
     a.rho_t = t.rho_t.as<T>();
+    a.uniform_mass = t.uniform_mass;
     a.kernel_id = kp.kernel_id;
     a.wendland_self = kp.wendland_self;
     a.nn_idx = nn_idx_dev;
     a.nn_d2 = (T *)nn_d2_dev;
     if (nn_idx_dev) launch_knn<T, true, false>(t, a);
-    else if (fuse_rho) launch_knn<T, true, true>(t, a);
+    else if (fuse_rho) launch_knn<T, false, true>(t, a);
     else launch_knn<T, false, false>(t, a);
 }
 
@@ -225,13 +259,15 @@ void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &k
     if (k > t.n)
         throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
     if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
-    if (fuse_rho && !t.has_mass) fuse_rho = false;
+    // the density can ride along only when every particle has the same mass (no neighbour ids are kept)
+    if (fuse_rho && !(t.has_mass && t.mass_is_uniform)) fuse_rho = false;
+    if (nn_idx_dev) fuse_rho = false;
     if (t.dtype == PNB_F64) run_knn_typed<double>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
     else run_knn_typed<float>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
     t.smooth_valid = true;
     t.smooth_k = k;
     t.smooth_period = period > 0 ? period : 0;
-    t.rho_valid = fuse_rho && !nn_idx_dev;
+    t.rho_valid = fuse_rho;
     t.rho_kernel = kp.kernel_id;
 }
 

@@ -273,3 +273,8 @@ def last_device_ms(stage):
 
 def last_launch_count(stage):
     return _lib.lib().pnb_last_launch_count(int(stage))
+
+
+def last_kernel_ms(which):
+    """Duration (ms) of the last kNN (0) / gather (1) / render (2) kernel launch on this thread."""
+    return _lib.lib().pnb_last_kernel_ms(int(which))
