@@ -23,6 +23,7 @@ void record_stage(int stage, double ms, int64_t launches)
 }
 
 static thread_local double g_kernel_ms[3] = {0, 0, 0};
+void set_kernel_ms(int which, double ms) { g_kernel_ms[which] = ms; }
 KernelTimer::KernelTimer(int w, cudaStream_t s) : which(w), stream(s)
 {
     PNB_CUDA(cudaEventCreate(&a));

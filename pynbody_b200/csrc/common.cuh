@@ -172,6 +172,7 @@ bool run_gather(Tree &t, int propid, int k, double period, const KernelParams &k
 // reference-layout KDNode records (kd.h:29-40) for the user's leafsize (export.cu)
 void export_kdnodes(Tree &t, void *out, int64_t n_nodes);
 void record_stage(int stage, double ms, int64_t launches);
+void set_kernel_ms(int which, double ms);
 int64_t run_ball_query(Tree &t, double cx, double cy, double cz, double r, double period,
                        int64_t *out_host, int64_t cap);
 

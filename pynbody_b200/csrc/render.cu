@@ -1,19 +1,651 @@
-// render.cu -- K6/K7 (placeholder until the renderer lands)
+// render.cu -- K6/K7: SPH image and 3-D grid rendering.
+//
+// Replaces _render.render_image / _render.to_3d_grid (pynbody/sph/_render.pyx:209-365, 373-497) and
+// their kernel lookup get_kernel (:186-193).  The reference is a per-particle SCATTER: every particle
+// loops over the pixels its 2h footprint covers and does `image[y,x] += qty_i * LUT(d2) / h^dim`.
+//
+// On the GPU the same sums are evaluated as a tile-binned GATHER:
+//   1. footprint pass: per particle (and per periodic image) the cull tests and the inclusive-exclusive
+//      pixel rectangle [xa,xb) x [ya,yb) (x [za,zb)) are computed with the reference's double
+//      arithmetic and C integer truncation (_render.pyx:297-346, 436-480); the number of 16x16-pixel
+//      (4x8x8-voxel) tiles it overlaps is counted;
+//   2. a prefix sum and a second footprint pass emit (tile, particle) pairs, which one radix sort
+//      groups by tile;
+//   3. a record pass writes one 64-byte record per pair (position relative to the tile origin, 1/kernel
+//      support, weight, rectangle clipped to the tile) in sorted order, so that a tile's particles are
+//      contiguous;
+//   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
+//      balance for clustered data), streams the records through shared memory with TMA bulk copies
+//      (cp.async.bulk + mbarrier, double buffered), and each of its 256 threads accumulates ONE pixel
+//      of the current tile in a register.  Pixels are flushed with one double-precision atomicAdd per
+//      (pixel, slice) -- 256 per tile switch instead of one per particle-pixel pair.
+//
+// LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
+// evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
+// coordinates (absolute error < 4e-4 of an index step) and falls back to the reference's exact double
+// expression whenever the float value lies within 2e-3 of an integer, so the selected table entry is
+// the reference's in every case.
+//
+// Perspective images (z_camera != 0) rescale the pixel grid per particle (_render.pyx:281-295); they go
+// through an exact per-particle scatter kernel with double atomics instead of the tile path.
 #include "common.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace pnb {
+
+namespace {
+
+constexpr int TILE2 = 16;                       // image tile: 16 x 16 pixels
+constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
+constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
+constexpr int CHUNK = 64;                       // records per TMA transfer
+constexpr int64_t MAX_PAIRS = (int64_t)96 << 20;  // pairs handled per sort/render batch (6 GiB of records)
+constexpr float BORDER = 2e-3f;
+
+struct Geom {
+    int nx, ny, nz, grid;
+    double x1, x2, y1, y2, z1, z2;
+    double pdx, pdy, pdz, xs, ys, zs;
+    double z_camera, z0, smooth_lo, smooth_hi, z_lo, z_hi, min_smooth, max_d;
+    float per_z_dx, per_z_dy, mid_x, mid_y;
+    int ns, h_power, use_z;
+    int tiles_x, tiles_y, tiles_z;
+};
+
+struct Cols {
+    const void *x, *y, *z;
+    int pos_f64;
+    const double *h, *w;
+    int64_t n;
+};
+
+struct Footprint {
+    double xi, yi, zi, h, w;
+    int xa, xb, ya, yb, za, zb;
+};
+
+struct alignas(16) Rec {
+    double xi, yi, zd, kmax2;     // zd: image -> dz = (z - z0) * use_z ; grid -> z
+    float xr, yr, zr, inv;        // tile-relative position; image: zr = dz^2; inv = ns / kmax2 (<0: exact path only)
+    float wq;                     // weight / h^dim
+    uint32_t box;                 // lxa | wx << 8 | lya << 16 | wy << 24   (rectangle clipped to the tile)
+    uint32_t boxz;                // lza | wz << 8
+    uint32_t tile;
+};
+static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
+
+__device__ __forceinline__ int c_int(double v)
+{
+    // C's (int) on x86-64 (cvttsd2si): out-of-range and NaN give INT_MIN
+    return (v >= 2147483648.0 || v < -2147483648.0 || v != v) ? INT_MIN : (int)v;
+}
+__device__ __forceinline__ double ld_pos(const void *p, int f64, int64_t i, float off)
+{
+    // x[i] + (float)offset evaluated in the element type of x (_render.pyx:270-272)
+    if (f64) return ((const double *)p)[i] + (double)off;
+    return (double)(((const float *)p)[i] + off);
+}
+
+// cull tests and pixel rectangle of particle i for one periodic image; false if it contributes nothing
+__device__ __forceinline__ bool footprint(const Geom &g, const Cols &c, int64_t i, float ox, float oy, float oz,
+                                          Footprint &f)
+{
+    const double xi = ld_pos(c.x, c.pos_f64, i, ox), yi = ld_pos(c.y, c.pos_f64, i, oy);
+    const double zi = ld_pos(c.z, c.pos_f64, i, g.grid ? oz : 0.0f);
+    double h = c.h[i];
+    const double w = c.w[i];
+    if (!g.grid) {
+        if (zi < g.z_lo || zi > g.z_hi) return false;                      // _render.pyx:275
+        if (w != w) return false;                                          // :278
+        if (h < g.min_smooth) h = g.min_smooth;                            // :297
+    }
+    if (h < g.pdx * g.smooth_lo || h > g.pdx * g.smooth_hi) return false;  // :299, :438
+    if (!g.grid) {
+        if (!((g.use_z * fabs(zi - g.z0) < g.max_d * h) && xi > g.x1 - 2 * h && xi < g.x2 + 2 * h
+              && yi > g.y1 - 2 * h && yi < g.y2 + 2 * h))
+            return false;                                                  // :303-306
+    } else {
+        if (!(zi > g.z1 - 2 * h && zi < g.z2 + 2 * h && xi > g.x1 - 2 * h && xi < g.x2 + 2 * h
+              && yi > g.y1 - 2 * h && yi < g.y2 + 2 * h))
+            return false;                                                  // :441-444
+    }
+    f.xi = xi; f.yi = yi; f.zi = zi; f.h = h; f.w = w;
+    f.za = 0; f.zb = 1;
+    if (g.max_d * h / g.pdx < 1 && g.max_d * h / g.pdy < 1) {              // single pixel (:316, :455)
+        const int px = c_int((xi - g.x1) / g.pdx), py = c_int((yi - g.y1) / g.pdy);
+        if (!(px >= 0 && px < g.nx && py >= 0 && py < g.ny)) return false;
+        f.xa = px; f.xb = px + 1; f.ya = py; f.yb = py + 1;
+        if (g.grid) {
+            const int pz = c_int((zi - g.z1) / g.pdz);
+            if (!(pz >= 0 && pz < g.nz)) return false;
+            f.za = pz; f.zb = pz + 1;
+        }
+        return true;
+    }
+    int xa = c_int((xi - g.max_d * h - g.x1) / g.pdx), xb = c_int((xi + g.max_d * h - g.x1) / g.pdx);
+    int ya = c_int((yi - g.max_d * h - g.y1) / g.pdy), yb = c_int((yi + g.max_d * h - g.y1) / g.pdy);
+    if (xa < 0) xa = 0; if (xb > g.nx) xb = g.nx;
+    if (ya < 0) ya = 0; if (yb > g.ny) yb = g.ny;
+    f.xa = xa; f.xb = xb; f.ya = ya; f.yb = yb;
+    if (g.grid) {
+        int za = c_int((zi - g.max_d * h - g.z1) / g.pdz), zb = c_int((zi + g.max_d * h - g.z1) / g.pdz);
+        if (za < 0) za = 0; if (zb > g.nz) zb = g.nz;
+        f.za = za; f.zb = zb;
+    }
+    return xb > xa && yb > ya && f.zb > f.za;
+}
+
+__device__ __forceinline__ void tile_span(const Geom &g, const Footprint &f, int &ta, int &tb, int &ua, int &ub,
+                                          int &va, int &vb)
+{
+    if (!g.grid) {
+        ta = f.xa / TILE2; tb = (f.xb - 1) / TILE2;
+        ua = f.ya / TILE2; ub = (f.yb - 1) / TILE2;
+        va = 0; vb = 0;
+    } else {
+        ta = f.xa / GTX; tb = (f.xb - 1) / GTX;
+        ua = f.ya / GTY; ub = (f.yb - 1) / GTY;
+        va = f.za / GTZ; vb = (f.zb - 1) / GTZ;
+    }
+}
+
+// ---- per-particle weight and smoothing length as double (C promotion rules of _render.pyx:276) -------
+__global__ void k_prepare(int64_t n, const void *sm, int sm64, const void *qty, int q64, const void *mass, int m64,
+                          const void *rho, int r64, double *h_out, double *w_out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    h_out[i] = sm64 ? ((const double *)sm)[i] : (double)((const float *)sm)[i];
+    double w;
+    if (!q64 && !m64) {
+        float qm = ((const float *)qty)[i] * ((const float *)mass)[i];
+        if (!r64) w = (double)(qm / ((const float *)rho)[i]);
+        else w = (double)qm / ((const double *)rho)[i];
+    } else {
+        double q = q64 ? ((const double *)qty)[i] : (double)((const float *)qty)[i];
+        double m = m64 ? ((const double *)mass)[i] : (double)((const float *)mass)[i];
+        double r = r64 ? ((const double *)rho)[i] : (double)((const float *)rho)[i];
+        w = q * m / r;
+    }
+    w_out[i] = w;
+}
+
+__global__ void k_count_tiles(Geom g, Cols c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+                              unsigned long long *__restrict__ counts)
+{
+    int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    Footprint f;
+    unsigned long long cnt = 0;
+    if (footprint(g, c, i, ox, oy, oz, f)) {
+        int ta, tb, ua, ub, va, vb;
+        tile_span(g, f, ta, tb, ua, ub, va, vb);
+        cnt = (unsigned long long)(tb - ta + 1) * (unsigned long long)(ub - ua + 1) * (unsigned long long)(vb - va + 1);
+    }
+    counts[i - i0] = cnt;
+}
+
+__global__ void k_emit_pairs(Geom g, Cols c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+                             const unsigned long long *__restrict__ offsets, uint32_t *__restrict__ keys,
+                             uint32_t *__restrict__ vals)
+{
+    int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    Footprint f;
+    if (!footprint(g, c, i, ox, oy, oz, f)) return;
+    int ta, tb, ua, ub, va, vb;
+    tile_span(g, f, ta, tb, ua, ub, va, vb);
+    unsigned long long o = offsets[i - i0];
+    for (int t = ta; t <= tb; ++t)
+        for (int u = ua; u <= ub; ++u)
+            for (int v = va; v <= vb; ++v) {
+                uint32_t tile = g.grid ? (uint32_t)((t * g.tiles_y + u) * g.tiles_z + v) : (uint32_t)(u * g.tiles_x + t);
+                keys[o] = tile;
+                vals[o] = (uint32_t)(i - i0);
+                ++o;
+            }
+}
+
+__global__ void k_make_records(Geom g, Cols c, int64_t i0, float ox, float oy, float oz, int64_t npairs,
+                               const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                               Rec *__restrict__ recs)
+{
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= npairs) return;
+    const uint32_t tile = keys[j];
+    Footprint f;
+    footprint(g, c, i0 + vals[j], ox, oy, oz, f);
+    int tx, ty, tz = 0, px0, py0, pz0 = 0, sx, sy, sz = 1;
+    if (!g.grid) {
+        ty = tile / g.tiles_x; tx = tile - ty * g.tiles_x;
+        px0 = tx * TILE2; py0 = ty * TILE2; sx = sy = TILE2;
+    } else {
+        tz = tile % g.tiles_z; int r = tile / g.tiles_z; ty = r % g.tiles_y; tx = r / g.tiles_y;
+        px0 = tx * GTX; py0 = ty * GTY; pz0 = tz * GTZ; sx = GTX; sy = GTY; sz = GTZ;
+    }
+    Rec R;
+    const double h = f.h;
+    const float hk = (g.h_power == 2) ? (float)(h * h) : (float)(h * h * h);        // :309-312
+    const double kmax2 = (h * h) * (g.max_d * g.max_d);                             // :313
+    R.xi = f.xi; R.yi = f.yi; R.kmax2 = kmax2;
+    R.xr = (float)(f.xi - (g.x1 + g.pdx * px0));
+    R.yr = (float)(f.yi - (g.y1 + g.pdy * py0));
+    if (!g.grid) {
+        const double dz = (f.zi - g.z0) * g.use_z;                                  // :314
+        R.zd = dz;
+        R.zr = (float)(dz * dz);
+    } else {
+        R.zd = f.zi;
+        R.zr = (float)(f.zi - (g.z1 + g.pdz * pz0));
+    }
+    const bool single = g.max_d * h / g.pdx < 1 && g.max_d * h / g.pdy < 1;
+    const float inv = (float)((double)g.ns / kmax2);
+    R.inv = (single || !(inv > 0.0f) || inv > 1e37f) ? -1.0f : inv;                 // tiny kernels: exact path only
+    R.wq = (float)(f.w / (double)hk);
+    const int lxa = max(f.xa - px0, 0), lxb = min(f.xb - px0, sx);
+    const int lya = max(f.ya - py0, 0), lyb = min(f.yb - py0, sy);
+    const int lza = max(f.za - pz0, 0), lzb = min(f.zb - pz0, sz);
+    R.box = (uint32_t)lxa | ((uint32_t)(lxb - lxa) << 8) | ((uint32_t)lya << 16) | ((uint32_t)(lyb - lya) << 24);
+    R.boxz = (uint32_t)lza | ((uint32_t)(lzb - lza) << 8);
+    R.tile = tile;
+    recs[j] = R;
+}
+
+// ---- TMA bulk copy + mbarrier (PTX) --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+// the reference's table lookup index (_render.pyx:186-193) in exact double arithmetic
+template <bool GRID>
+__device__ __forceinline__ unsigned exact_index(const Geom &g, const Rec &R, int px, int py, int pz)
+{
+    const double ddx = R.xi - (g.pdx * (double)px + g.xs);
+    const double ddy = R.yi - (g.pdy * (double)py + g.ys);
+    double d2;
+    if (GRID) {
+        const double ddz = R.zd - (g.pdz * (double)pz + g.zs);
+        d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+    } else {
+        d2 = ddx * ddx + ddy * ddy + R.zd * R.zd;
+    }
+    const double t = g.ns * (d2 / R.kmax2);
+    return (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ recs, int64_t npairs, Geom g,
+                                                      const float *__restrict__ lut, double *__restrict__ acc)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    Rec *buf = reinterpret_cast<Rec *>(smem);                                  // [2][CHUNK]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * CHUNK * sizeof(Rec));
+    float *slut = reinterpret_cast<float *>(smem + 2 * CHUNK * sizeof(Rec) + 16);
+    const int tid = threadIdx.x;
+    const int64_t first = (int64_t)blockIdx.x * SEG;
+    const int64_t last = min(npairs, first + (int64_t)SEG);
+    const int nchunks = (int)((last - first + CHUNK - 1) / CHUNK);
+
+    for (int i = tid; i < g.ns; i += 256) slut[i] = lut[i];
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        const int64_t b = first + (int64_t)c * CHUNK;
+        const uint32_t bytes = (uint32_t)(min((int64_t)CHUNK, last - b) * sizeof(Rec));
+        mbar_expect_tx(&bar[c & 1], bytes);
+        tma_load_bulk(buf + (c & 1) * CHUNK, recs + b, bytes, &bar[c & 1]);
+    };
+    if (tid == 0) issue(0);
+
+    int lx, ly, lz = 0;
+    if (GRID) { lz = tid & (GTZ - 1); ly = (tid >> 3) & (GTY - 1); lx = tid >> 6; }
+    else { lx = tid & (TILE2 - 1); ly = tid >> 4; }
+    const float cx = (float)(g.pdx * (lx + 0.5)), cy = (float)(g.pdy * (ly + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
+    const float nsf = (float)g.ns;
+
+    double a = 0.0;
+    uint32_t cur = 0xffffffffu;
+    int px = 0, py = 0, pz = 0;
+    auto flush = [&]() {
+        if (a != 0.0) {
+            const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)py * g.nx + px;
+            atomicAdd(&acc[pix], a);
+        }
+        a = 0.0;
+    };
+
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + 1 < nchunks) issue(c + 1);       // buffer (c+1)&1 was released by the barrier below
+        mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+        const Rec *chunk = buf + (c & 1) * CHUNK;
+        const int cnt = (int)min((int64_t)CHUNK, last - (first + (int64_t)c * CHUNK));
+        for (int r = 0; r < cnt; ++r) {
+            const Rec &R = chunk[r];
+            if (R.tile != cur) {                               // block-uniform
+                flush();
+                cur = R.tile;
+                if (GRID) {
+                    const int tz = cur % g.tiles_z, q = cur / g.tiles_z;
+                    pz = tz * GTZ + lz; py = (q % g.tiles_y) * GTY + ly; px = (q / g.tiles_y) * GTX + lx;
+                } else {
+                    const int ty = cur / g.tiles_x;
+                    py = ty * TILE2 + ly; px = (cur - ty * g.tiles_x) * TILE2 + lx;
+                }
+            }
+            const uint32_t box = R.box;
+            bool in = ((unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff))
+                      & ((unsigned)(ly - (int)((box >> 16) & 0xff)) < (box >> 24));
+            if (GRID) in &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+            if (!in) continue;
+            // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a
+            // non-finite weight poisons the same pixels (w * 0 = NaN)
+            unsigned idx;
+            if (R.inv > 0.0f) {
+                const float ddx = R.xr - cx, ddy = R.yr - cy;
+                float d2 = ddx * ddx + ddy * ddy;
+                if (GRID) { const float ddz = R.zr - cz; d2 += ddz * ddz; }
+                else d2 += R.zr;
+                const float t = fminf(d2 * R.inv, nsf + 2.0f);
+                idx = (unsigned)t;
+                const float fr = t - (float)idx;
+                if ((fr < BORDER || fr > 1.0f - BORDER) && t < nsf + 1.0f) idx = exact_index<GRID>(g, R, px, py, pz);
+            } else {
+                idx = exact_index<GRID>(g, R, px, py, pz);
+            }
+            const float val = idx < (unsigned)g.ns ? slut[idx] : 0.0f;
+            a += (double)(val * R.wq);
+        }
+        __syncthreads();
+    }
+    flush();
+}
+
+// ---- exact per-particle scatter (perspective images; also the cross-check path) ------------------------
+__global__ void k_render_scatter(Geom g, Cols c, float ox, float oy, const float *__restrict__ lut,
+                                 double *__restrict__ acc)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= c.n) return;
+    Geom l = g;                                               // per-particle pixel grid in perspective mode
+    const double zi = ld_pos(c.z, c.pos_f64, i, 0.0f);
+    if (g.z_camera != 0.0) {
+        if (zi < g.z_lo || zi > g.z_hi) return;
+        if ((zi > g.z_camera && g.z_camera > 0) || (zi < g.z_camera && g.z_camera < 0)) return;   // :281-283
+        const float dzc = (float)(g.z_camera - zi);
+        l.x1 = g.mid_x - g.per_z_dx * dzc; l.x2 = g.mid_x + g.per_z_dx * dzc;                     // float arithmetic, :284-290
+        l.y1 = g.mid_y - g.per_z_dy * dzc; l.y2 = g.mid_y + g.per_z_dy * dzc;
+        l.pdx = (l.x2 - l.x1) / g.nx; l.pdy = (l.y2 - l.y1) / g.ny;
+        l.xs = l.x1 + l.pdx / 2; l.ys = l.y1 + l.pdy / 2;
+    }
+    Footprint f;
+    if (!footprint(l, c, i, ox, oy, 0.0f, f)) return;
+    const double h = f.h;
+    const float hk = (g.h_power == 2) ? (float)(h * h) : (float)(h * h * h);
+    const double kmax2 = (h * h) * (g.max_d * g.max_d);
+    const double dz = (f.zi - g.z0) * g.use_z;
+    const int wy = f.yb - f.ya, npx = (f.xb - f.xa) * wy;
+    for (int t = lane; t < npx; t += 32) {
+        const int px = f.xa + t / wy, py = f.ya + t % wy;
+        const double ddx = f.xi - (l.pdx * (double)px + l.xs), ddy = f.yi - (l.pdy * (double)py + l.ys);
+        const double d2 = ddx * ddx + ddy * ddy + dz * dz;
+        const double tt = g.ns * (d2 / kmax2);
+        const unsigned idx = (tt >= 4294967296.0 || tt != tt) ? 0xffffffffu : (unsigned)tt;
+        if (idx < (unsigned)g.ns) atomicAdd(&acc[(int64_t)py * g.nx + px], f.w * (double)(lut[idx] / hk));
+    }
+}
+
+__global__ void k_finalize(const double *__restrict__ acc, int64_t n, float *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)acc[i];
+}
+
+inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+struct Work {
+    cudaStream_t s = nullptr;
+    DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp;
+    size_t scan_bytes = 0, sort_bytes = 0;
+};
+
+// render particles [i0, i1) of one periodic image through the tile path
+void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+                  const float *lut_dev, double *acc, double &kernel_ms)
+{
+    typedef unsigned long long u64;
+    const int64_t m = i1 - i0;
+    if (m <= 0) return;
+    cudaStream_t s = wk.s;
+    const int BS = 256;
+    wk.counts.alloc(sizeof(u64) * (m + 1));
+    wk.offsets.alloc(sizeof(u64) * (m + 1));
+    PNB_CUDA(cudaMemsetAsync(wk.counts.as<u64>() + m, 0, sizeof(u64), s));
+    PNB_LAUNCH(k_count_tiles, nblk(m, BS), BS, 0, s, g, c, i0, i1, ox, oy, oz, wk.counts.as<u64>());
+    size_t need = 0;
+    PNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, wk.counts.as<u64>(), wk.offsets.as<u64>(), m + 1, s));
+    if (need > wk.scan_tmp.bytes) wk.scan_tmp.alloc(need);
+    PNB_CUDA(cub::DeviceScan::ExclusiveSum(wk.scan_tmp.p, need, wk.counts.as<u64>(), wk.offsets.as<u64>(), m + 1, s));
+    g_launches += 2;
+    u64 total = 0;
+    PNB_CUDA(cudaMemcpyAsync(&total, wk.offsets.as<u64>() + m, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    if (total == 0) return;
+    if ((int64_t)total > MAX_PAIRS && m > 1) {
+        // too many pairs for one batch: footprints are independent and the sums linear, so split
+        const int64_t mid = i0 + m / 2;
+        render_range(wk, g, c, i0, mid, ox, oy, oz, lut_dev, acc, kernel_ms);
+        render_range(wk, g, c, mid, i1, ox, oy, oz, lut_dev, acc, kernel_ms);
+        return;
+    }
+    const int64_t P = (int64_t)total;
+    wk.keys.alloc(sizeof(uint32_t) * P); wk.vals.alloc(sizeof(uint32_t) * P);
+    wk.keys2.alloc(sizeof(uint32_t) * P); wk.vals2.alloc(sizeof(uint32_t) * P);
+    PNB_LAUNCH(k_emit_pairs, nblk(m, BS), BS, 0, s, g, c, i0, i1, ox, oy, oz, wk.offsets.as<u64>(),
+               wk.keys.as<uint32_t>(), wk.vals.as<uint32_t>());
+    const int64_t ntiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_z;
+    int bits = 1;
+    while (((int64_t)1 << bits) < ntiles) ++bits;
+    need = 0;
+    PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, uint32_t, int64_t>(
+        nullptr, need, wk.keys.as<uint32_t>(), wk.keys2.as<uint32_t>(), wk.vals.as<uint32_t>(), wk.vals2.as<uint32_t>(), P, 0, bits, s)));
+    if (need > wk.sort_tmp.bytes) wk.sort_tmp.alloc(need);
+    PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, uint32_t, int64_t>(
+        wk.sort_tmp.p, need, wk.keys.as<uint32_t>(), wk.keys2.as<uint32_t>(), wk.vals.as<uint32_t>(), wk.vals2.as<uint32_t>(), P, 0, bits, s)));
+    g_launches += 3;
+    wk.recs.alloc(sizeof(Rec) * P);
+    PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, ox, oy, oz, P, wk.keys2.as<uint32_t>(),
+               wk.vals2.as<uint32_t>(), wk.recs.as<Rec>());
+    const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * (size_t)g.ns;
+    KernelTimer timer(2, s);
+    if (g.grid) {
+        PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+    } else {
+        PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+    }
+    timer.stop();
+    kernel_ms += pnb_last_kernel_ms(2);
+}
+
+void check_arrays(const pnb_render_arrays *a)
+{
+    if (!a) throw Error(PNB_ERR_VALUE, "render arrays are null");
+    if (a->n < 0) throw Error(PNB_ERR_VALUE, "negative particle count");
+    const int dts[5] = {a->pos_dtype, a->sm_dtype, a->qty_dtype, a->mass_dtype, a->rho_dtype};
+    for (int d : dts)
+        if (d != PNB_F32 && d != PNB_F64) throw Error(PNB_ERR_VALUE, "render arrays must be float32 or float64");
+    if (a->n > 0 && (!a->x || !a->y || !a->z || !a->sm || !a->qty || !a->mass || !a->rho))
+        throw Error(PNB_ERR_VALUE, "render array pointer is null");
+    if (a->n >= ((int64_t)1 << 31)) throw Error(PNB_ERR_VALUE, "at most 2^31-1 particles per render call");   // _render.pyx:229
+}
+
+void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, double x1, double x2, double y1, double y2,
+            double z1, double z2, double z_camera, double z0, double smooth_lo, double smooth_hi, double z_lo,
+            double z_hi, double min_smooth, const float *lut, int n_lut, int h_power, double max_d,
+            const double *wrap_x, int nwx, const double *wrap_y, int nwy, const double *wrap_z, int nwz, float *out,
+            int out_mem)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw Error(PNB_ERR_CUDA, "no CUDA device available: pnb_b200 has no CPU fallback");
+    }
+    check_arrays(a);
+    if (nx < 1 || ny < 1 || nz < 1) throw Error(PNB_ERR_VALUE, "image dimensions must be positive");
+    if (!lut || n_lut < 1 || n_lut > 8192) throw Error(PNB_ERR_VALUE, "kernel table must hold 1..8192 samples");
+    if (grid && h_power < 3) throw Error(PNB_ERR_VALUE, "Cannot render to 3D grid without 3-dimensional kernel or greater");
+    if (!out) throw Error(PNB_ERR_VALUE, "output pointer is null");
+    cudaStream_t s = nullptr;
+    StageTimer stage(2, s);
+
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.nx = nx; g.ny = ny; g.nz = nz; g.grid = grid ? 1 : 0;
+    g.x1 = x1; g.x2 = x2; g.y1 = y1; g.y2 = y2; g.z1 = z1; g.z2 = z2;
+    g.pdx = (x2 - x1) / nx; g.pdy = (y2 - y1) / ny;
+    g.pdz = grid ? (z2 - z1) / ny : 1.0;                     // sic: _render.pyx:391 divides by ny
+    g.xs = x1 + g.pdx / 2; g.ys = y1 + g.pdy / 2; g.zs = z1 + g.pdz / 2;
+    g.z_camera = grid ? 0.0 : z_camera; g.z0 = z0;
+    g.smooth_lo = smooth_lo; g.smooth_hi = smooth_hi; g.z_lo = z_lo; g.z_hi = z_hi; g.min_smooth = min_smooth;
+    g.max_d = max_d; g.ns = n_lut; g.h_power = h_power; g.use_z = h_power >= 3 ? 1 : 0;
+    g.per_z_dx = (float)((x2 - x1) / (2 * z_camera)); g.per_z_dy = (float)((y2 - y1) / (2 * z_camera));
+    g.mid_x = (float)((x2 + x1) / 2); g.mid_y = (float)((y2 + y1) / 2);
+    if (grid) { g.tiles_x = (nx + GTX - 1) / GTX; g.tiles_y = (ny + GTY - 1) / GTY; g.tiles_z = (nz + GTZ - 1) / GTZ; }
+    else { g.tiles_x = (nx + TILE2 - 1) / TILE2; g.tiles_y = (ny + TILE2 - 1) / TILE2; g.tiles_z = 1; }
+    if ((int64_t)g.tiles_x * g.tiles_y * g.tiles_z >= ((int64_t)1 << 31)) throw Error(PNB_ERR_VALUE, "image too large");
+
+    const int64_t n = a->n, npix = (int64_t)nx * ny * nz;
+    DevBuf acc(sizeof(double) * npix);
+    PNB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * npix, s));
+    DevBuf lut_dev(sizeof(float) * n_lut);
+    PNB_CUDA(cudaMemcpyAsync(lut_dev.p, lut, sizeof(float) * n_lut, cudaMemcpyHostToDevice, s));
+    double kernel_ms = 0;
+    if (n > 0) {
+        const size_t ps = tsize(a->pos_dtype);
+        DevBuf dx(ps * n), dy(ps * n), dz(ps * n), dsm(tsize(a->sm_dtype) * n), dq(tsize(a->qty_dtype) * n),
+            dm(tsize(a->mass_dtype) * n), dr(tsize(a->rho_dtype) * n), hd(sizeof(double) * n), wd(sizeof(double) * n);
+        fetch_columns(a->x, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dx.p, s);
+        fetch_columns(a->y, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dy.p, s);
+        fetch_columns(a->z, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dz.p, s);
+        fetch_columns(a->sm, a->sm_stride, 0, 1, a->sm_dtype, a->mem, n, dsm.p, s);
+        fetch_columns(a->qty, a->qty_stride, 0, 1, a->qty_dtype, a->mem, n, dq.p, s);
+        fetch_columns(a->mass, a->mass_stride, 0, 1, a->mass_dtype, a->mem, n, dm.p, s);
+        fetch_columns(a->rho, a->rho_stride, 0, 1, a->rho_dtype, a->mem, n, dr.p, s);
+        PNB_LAUNCH(k_prepare, nblk(n, 256), 256, 0, s, n, dsm.p, a->sm_dtype, dq.p, a->qty_dtype, dm.p, a->mass_dtype,
+                   dr.p, a->rho_dtype, hd.as<double>(), wd.as<double>());
+        Cols c;
+        c.x = dx.p; c.y = dy.p; c.z = dz.p; c.pos_f64 = a->pos_dtype; c.h = hd.as<double>(); c.w = wd.as<double>(); c.n = n;
+        Work wk;
+        wk.s = s;
+        const double zero = 0.0;
+        if (!wrap_x || nwx < 1) { wrap_x = &zero; nwx = 1; }
+        if (!wrap_y || nwy < 1) { wrap_y = &zero; nwy = 1; }
+        if (!grid || !wrap_z || nwz < 1) { wrap_z = &zero; nwz = 1; }
+        for (int i = 0; i < nwx; ++i)
+            for (int j = 0; j < nwy; ++j)
+                for (int k = 0; k < nwz; ++k) {
+                    const float ox = (float)wrap_x[i], oy = (float)wrap_y[j], oz = (float)wrap_z[k];   // :237-243, :418
+                    if (!grid && z_camera != 0.0) {
+                        KernelTimer timer(2, s);
+                        PNB_LAUNCH(k_render_scatter, nblk(n * 32, 256), 256, 0, s, g, c, ox, oy, lut_dev.as<float>(), acc.as<double>());
+                        timer.stop();
+                        kernel_ms += pnb_last_kernel_ms(2);
+                    } else {
+                        render_range(wk, g, c, 0, n, ox, oy, oz, lut_dev.as<float>(), acc.as<double>(), kernel_ms);
+                    }
+                }
+        PNB_CUDA(cudaStreamSynchronize(s));
+    }
+    if (out_mem == PNB_DEVICE) {
+        PNB_LAUNCH(k_finalize, nblk(npix, 256), 256, 0, s, acc.as<double>(), npix, out);
+        PNB_CUDA(cudaStreamSynchronize(s));
+    } else {
+        DevBuf of(sizeof(float) * npix);
+        PNB_LAUNCH(k_finalize, nblk(npix, 256), 256, 0, s, acc.as<double>(), npix, of.as<float>());
+        PNB_CUDA(cudaMemcpyAsync(out, of.p, sizeof(float) * npix, cudaMemcpyDeviceToHost, s));
+        PNB_CUDA(cudaStreamSynchronize(s));
+    }
+    stage.stop();
+    set_kernel_ms(2, kernel_ms);
+}
+
+template <typename F>
+int guarded_render(F &&f)
+{
+    try {
+        f();
+        return PNB_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return PNB_ERR_RUNTIME;
+    }
+}
+
+}  // namespace
+}  // namespace pnb
+
 using namespace pnb;
+
 extern "C" {
-int pnb_render_image(int, int, const pnb_render_arrays *, double, double, double, double, double, double, double,
-                     double, double, double, double, const float *, int, int, double, const double *, int,
-                     const double *, int, float *, int)
+
+int pnb_render_image(int nx, int ny, const pnb_render_arrays *a, double x1, double x2, double y1, double y2,
+                     double z_camera, double z0, double smooth_lo, double smooth_hi, double z_lo, double z_hi,
+                     double min_smooth, const float *lut, int n_lut, int h_power, double max_d, const double *wrap_x,
+                     int n_wrap_x, const double *wrap_y, int n_wrap_y, float *out, int out_mem)
 {
-    set_last_error("render_image: not built yet");
-    return PNB_ERR_RUNTIME;
+    return guarded_render([&] {
+        render(false, nx, ny, 1, a, x1, x2, y1, y2, 0.0, 1.0, z_camera, z0, smooth_lo, smooth_hi, z_lo, z_hi, min_smooth,
+               lut, n_lut, h_power, max_d, wrap_x, n_wrap_x, wrap_y, n_wrap_y, nullptr, 0, out, out_mem);
+    });
 }
-int pnb_render_grid(int, int, int, const pnb_render_arrays *, double, double, double, double, double, double, double,
-                    double, const float *, int, int, double, const double *, int, const double *, int, const double *,
-                    int, float *, int)
+
+int pnb_render_grid(int nx, int ny, int nz, const pnb_render_arrays *a, double x1, double x2, double y1, double y2,
+                    double z1, double z2, double smooth_lo, double smooth_hi, const float *lut, int n_lut, int h_power,
+                    double max_d, const double *wrap_x, int n_wrap_x, const double *wrap_y, int n_wrap_y,
+                    const double *wrap_z, int n_wrap_z, float *out, int out_mem)
 {
-    set_last_error("render_grid: not built yet");
-    return PNB_ERR_RUNTIME;
+    return guarded_render([&] {
+        render(true, nx, ny, nz, a, x1, x2, y1, y2, z1, z2, 0.0, 0.0, smooth_lo, smooth_hi, 0.0, 0.0, 0.0, lut, n_lut,
+               h_power, max_d, wrap_x, n_wrap_x, wrap_y, n_wrap_y, wrap_z, n_wrap_z, out, out_mem);
+    });
 }
-}
+
+}  // extern "C"
