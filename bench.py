@@ -267,6 +267,32 @@ def run_ours(args):
     extra["rho_gather_ms"] = round(kdmain.last_device_ms(1), 3)
     extra["rho_gather_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
 
+    # C3: projected density image and 3-D grid of the same particles (BASELINE.json configs[2]),
+    # device-resident inputs, periodic wrap offsets as ImageRenderer generates them (renderers.py:616-629)
+    render = {}
+    if not args.no_render:
+        from pynbody_b200.sph import _render, kernels
+        k3 = kernels.create_kernel(KERNEL)
+        k2 = k3.projection()
+        wrap = [-1.0, 0.0, 1.0]
+        res = args.render_res
+        def once():
+            return _render.render_image(res, res, d_pos[:, 0], d_pos[:, 1], d_pos[:, 2], d_sm, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5,
+                                        d_rho, d_mass, d_rho, 0.0, float("inf"), float("-inf"), float("inf"), 0.0, k2, wrap, wrap)
+        once()
+        ms = timed(once, 2) / 2
+        call_ms, kern_ms = _render.last_render_ms()
+        render["image"] = {"resolution": res, "mode": "projected density, 3x3 periodic images, exact (approximate_fast=False)",
+                           "ms": ms, "mpix_per_s": world * res * res / (ms * 1e-3) / 1e6, "tile_kernel_ms": kern_ms}
+        gres = args.grid_res
+        def gonce():
+            return _render.to_3d_grid(gres, gres, gres, d_pos[:, 0], d_pos[:, 1], d_pos[:, 2], d_sm, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0,
+                                      d_rho, d_mass, d_rho, 0.0, float("inf"), k3, wrap, wrap, wrap)
+        gonce()
+        ms = timed(gonce, 1)
+        call_ms, kern_ms = _render.last_render_ms()
+        render["grid"] = {"resolution": gres, "ms": ms, "mvox_per_s": world * gres ** 3 / (ms * 1e-3) / 1e6, "tile_kernel_ms": kern_ms}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -293,6 +319,7 @@ def run_ours(args):
                              "(SURVEY.md 8d); traffic from ncu is in profiles/"},
         "stages_ms": {"build": float(np.mean(stats["build_ms"])), "smooth_incl_fused_rho": float(np.mean(stats["knn_ms"])),
                       "knn_kernel": knn_kernel_ms, "rho_readback": float(np.mean(stats["rho_ms"])), **extra},
+        "render": render,
     }
     if world == 1 and not args.no_cpu_baseline:
         res = cpu_arm(args.cpu_sample_side, dtype, 1, 0)
@@ -313,6 +340,9 @@ def main():
     ap.add_argument("--cpu-sample-side", type=int, default=128, help="CPU baseline sample = side^3 particles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="per-step stage times on stderr")
+    ap.add_argument("--no-render", action="store_true", help="skip the C3 image / grid timings")
+    ap.add_argument("--render-res", type=int, default=2048)
+    ap.add_argument("--grid-res", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

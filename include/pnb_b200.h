@@ -118,6 +118,17 @@ int pnb_set_array(pnb_tree *t, int id, void *ptr, int64_t stride0, int64_t strid
  * k + 500 particles inside 2h -> PNB_ERR_RUNTIME (smooth.h:15,253-267). */
 int pnb_populate(pnb_tree *t, int propid, int k, int kernel_id, double period, int *period_ignored);
 
+/* ---- multi-GPU host-layer helpers (no reference counterpart: the reference is single-process) ----
+ * pnb_set_query_mask: restrict subsequent pnb_populate / pnb_knn calls to the particles whose mask
+ * byte (FILE order, n bytes) is non-zero; output entries of the other particles are left unspecified.
+ * NULL removes the restriction.  Used to re-run only the boundary particles after a halo exchange.
+ * pnb_mark_in_balls: flags_out[i] (FILE order, n bytes) = 1 iff particle i lies within radii[q] of
+ * centres[q] (periodic) for any q < nq: the halo particles another rank's boundary queries need. */
+int pnb_set_query_mask(pnb_tree *t, const uint8_t *mask, int mem);
+int pnb_mark_in_balls(pnb_tree *t, const void *centres, int64_t stride0, int64_t stride1,
+                      const void *radii, int64_t rstride, int64_t nq, double period,
+                      uint8_t *flags_out, int mem);
+
 /* ---- kdmain.nn_next, all particles at once (kdmain.cpp:390-440) -------------------------------
  * Neighbour lists for every particle: idx_out int64[N][k] (file-order ids, unsorted, self
  * included with d2 = 0), d2_out T[N][k], h_out T[N] (may be NULL); rows in file order; host memory. */

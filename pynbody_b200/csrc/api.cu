@@ -198,20 +198,26 @@ static void store_from_tree_order(Tree &t, const ArrRef &r, const void *tree_col
     PNB_CUDA(cudaStreamSynchronize(t.stream));
 }
 
-__global__ void k_all_equal(const unsigned char *a, const unsigned char *b, size_t bytes, int *differs)
+// bitwise comparison of two arrays of 4-byte words; with a mask (one byte per `words_per_elem` words)
+// only the selected elements are compared
+__global__ void k_all_equal(const unsigned char *a, const unsigned char *b, size_t bytes, const uint8_t *mask,
+                            int words_per_elem, int *differs)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a), *b4 = reinterpret_cast<const uint32_t *>(b);
     bool d = false;
-    for (size_t j = i; j < bytes / 4; j += stride) d |= a4[j] != b4[j];
+    for (size_t j = i; j < bytes / 4; j += stride)
+        if (!mask || mask[j / words_per_elem]) d |= a4[j] != b4[j];
     if (d) *differs = 1;
 }
-static bool device_equal(Tree &t, const void *a, const void *b, size_t bytes)
+static bool device_equal(Tree &t, const void *a, const void *b, size_t bytes, bool masked = false)
 {
     DevBuf flag(sizeof(int));
     PNB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), t.stream));
-    PNB_LAUNCH(k_all_equal, 1184, 256, 0, t.stream, (const unsigned char *)a, (const unsigned char *)b, bytes, flag.as<int>());
+    const uint8_t *mask = (masked && t.query_mask.p) ? t.query_mask.as<uint8_t>() : nullptr;
+    PNB_LAUNCH(k_all_equal, 1184, 256, 0, t.stream, (const unsigned char *)a, (const unsigned char *)b, bytes, mask,
+               (int)(tsize(t.dtype) / 4), flag.as<int>());
     int h = 0;
     PNB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
     PNB_CUDA(cudaStreamSynchronize(t.stream));
@@ -277,7 +283,7 @@ static void populate(Tree &t, int propid, int k, int kernel_id, double period_in
     DevBuf smooth_tree = fetch_tree_order(t, smr);
     // is the caller's smooth array the one this tree produced (the usual sim['smooth'] -> sim['rho'] flow)?
     const bool own_smooth = t.smooth_valid && t.smooth_k == k && t.smooth_period == (period > 0 ? period : 0)
-                            && device_equal(t, smooth_tree.p, t.smooth_t.p, ts * t.n);
+                            && device_equal(t, smooth_tree.p, t.smooth_t.p, ts * t.n, /*masked=*/true);
 
     if (propid == PNB_PROP_RHO) {
         const ArrRef &out = need(t, PNB_ARR_RHO, "rho");
@@ -443,6 +449,70 @@ int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t strid
             }
         }
         t->arr[id] = r;
+    });
+}
+
+__global__ void k_u8_to_tree(const uint32_t *order, const uint8_t *in_file, uint8_t *out_tree, int64_t n)
+{
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) out_tree[p] = in_file[order[p]] ? 1 : 0;
+}
+__global__ void k_u8_to_file(const uint32_t *order, const uint8_t *in_tree, uint8_t *out_file, int64_t n)
+{
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) out_file[order[p]] = in_tree[p];
+}
+
+int pnb_set_query_mask(pnb_tree *h, const uint8_t *mask, int mem)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        if (!mask) {
+            if (t->query_mask.p) { t->query_mask.release(); t->smooth_valid = false; t->rho_valid = false; }
+            return;
+        }
+        t->smooth_valid = false;
+        t->rho_valid = false;
+        require_device();
+        DevBuf file_mask;
+        const uint8_t *src = mask;
+        if (mem == PNB_HOST) {
+            file_mask.alloc((size_t)t->n);
+            PNB_CUDA(cudaMemcpyAsync(file_mask.p, mask, (size_t)t->n, cudaMemcpyHostToDevice, t->stream));
+            src = file_mask.as<uint8_t>();
+        }
+        t->query_mask.alloc((size_t)t->n);
+        PNB_LAUNCH(k_u8_to_tree, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(), src,
+                   t->query_mask.as<uint8_t>(), t->n);
+        PNB_CUDA(cudaStreamSynchronize(t->stream));
+    });
+}
+
+int pnb_mark_in_balls(pnb_tree *h, const void *centres, int64_t stride0, int64_t stride1, const void *radii,
+                      int64_t rstride, int64_t nq, double period_in, uint8_t *flags_out, int mem)
+{
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        require_device();
+        if (nq < 0) throw Error(PNB_ERR_VALUE, "negative ball count");
+        if (!flags_out) throw Error(PNB_ERR_VALUE, "flags pointer is null");
+        const double period = effective_period(*t, period_in, nullptr);
+        const size_t ts = tsize(t->dtype);
+        DevBuf flags_tree((size_t)t->n), flags_file((size_t)t->n);
+        PNB_CUDA(cudaMemsetAsync(flags_tree.p, 0, (size_t)t->n, t->stream));
+        if (nq > 0) {
+            DevBuf c(ts * 3 * nq), r(ts * nq);
+            fetch_columns(centres, stride0, stride1, 3, t->dtype, mem, nq, c.p, t->stream);
+            fetch_columns(radii, rstride, 0, 1, t->dtype, mem, nq, r.p, t->stream);
+            run_mark_in_balls(*t, c.p, r.p, nq, period, flags_tree.as<uint8_t>());
+            PNB_CUDA(cudaStreamSynchronize(t->stream));
+        }
+        uint8_t *dst = mem == PNB_DEVICE ? flags_out : flags_file.as<uint8_t>();
+        PNB_LAUNCH(k_u8_to_file, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(),
+                   flags_tree.as<uint8_t>(), dst, t->n);
+        if (mem != PNB_DEVICE)
+            PNB_CUDA(cudaMemcpyAsync(flags_out, flags_file.p, (size_t)t->n, cudaMemcpyDeviceToHost, t->stream));
+        PNB_CUDA(cudaStreamSynchronize(t->stream));
     });
 }
 

@@ -92,6 +92,72 @@ static int64_t ball_typed(Tree &t, double cx, double cy, double cz, double r, do
     return (int64_t)found;
 }
 
+// ---- many balls at once: which particles lie inside ANY of nq balls? (multi-GPU halo selection) -----
+// One warp takes 32 balls (one per lane) and sweeps the tree once for all of them, like the gather
+// kernel; accepted candidates of all lanes are OR-ed and the owning lanes set the particle flags.
+template <typename T, bool PERIODIC>
+__global__ void __launch_bounds__(128) k_mark_in_balls(TreeView<T> tv, const T *__restrict__ c, const T *__restrict__ rad,
+                                                       int64_t nq, uint8_t *__restrict__ flags)
+{
+    __shared__ T tiles[4][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t q = ((int64_t)blockIdx.x * 4 + wib) * 32 + lane;
+    if (((int64_t)blockIdx.x * 4 + wib) * 32 >= nq) return;
+    T *tile = tiles[wib];
+    const bool active = q < nq;
+    T qx = 0, qy = 0, qz = 0, r2 = -1;
+    if (active) {
+        qx = c[q]; qy = c[nq + q]; qz = c[2 * nq + q];
+        const T r = rad[q];
+        r2 = Ex<T>::mul(r, r);
+    }
+    int64_t cp = 1;
+    for (;;) {
+        Box6<T> b = load_box(tv.box, cp);
+        T sx, sy, sz;
+        T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, tv.period, sx, sy, sz);
+        bool pass = active && gap2 <= r2 * Ex<T>::slack();
+        if (__any_sync(FULL, pass)) {
+            if (cp < tv.nsplit) { cp = 2 * cp; continue; }
+            const int64_t bucket = cp - tv.nsplit;
+            const int start = tv.bucket_start[bucket];
+            const int cnt = tv.bucket_start[bucket + 1] - start;
+            __syncwarp();
+            if (lane < cnt) {
+                tile[lane] = tv.x[start + lane]; tile[32 + lane] = tv.y[start + lane]; tile[64 + lane] = tv.z[start + lane];
+            }
+            __syncwarp();
+            unsigned mask = 0;
+            for (int j = 0; j < cnt; ++j) {
+                T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+                mask |= (unsigned)(d2 <= r2) << j;
+            }
+            if (!pass) mask = 0;
+            mask = __reduce_or_sync(FULL, mask);
+            if (lane < cnt && ((mask >> lane) & 1u)) flags[start + lane] = 1;
+        }
+        cp = next_node(cp);
+        if (cp == 1) break;
+    }
+}
+
+template <typename T>
+static void mark_typed(Tree &t, const void *centres, const void *radii, int64_t nq, double period, uint8_t *flags)
+{
+    TreeView<T> tv = make_view<T>(t, period);
+    tv.query_mask = nullptr;
+    const unsigned grid = (unsigned)((nq + 127) / 128);
+    if (tv.periodic) PNB_LAUNCH((k_mark_in_balls<T, true>), grid, 128, 0, t.stream, tv, (const T *)centres, (const T *)radii, nq, flags);
+    else PNB_LAUNCH((k_mark_in_balls<T, false>), grid, 128, 0, t.stream, tv, (const T *)centres, (const T *)radii, nq, flags);
+}
+
+void run_mark_in_balls(Tree &t, const void *centres_cols, const void *radii, int64_t nq, double period, uint8_t *flags_tree)
+{
+    if (nq <= 0) return;
+    if (t.dtype == PNB_F64) mark_typed<double>(t, centres_cols, radii, nq, period, flags_tree);
+    else mark_typed<float>(t, centres_cols, radii, nq, period, flags_tree);
+}
+
 int64_t run_ball_query(Tree &t, double cx, double cy, double cz, double r, double period, int64_t *out_host,
                        int64_t cap)
 {

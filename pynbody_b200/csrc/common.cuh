@@ -111,6 +111,8 @@ struct Tree {
     bool rho_valid = false;       // rho_t was computed from smooth_t (fused with the kNN pass)
     int rho_kernel = -1;
 
+    DevBuf query_mask;            // uint8[n] tree order, or empty: restricts populate / knn to a subset
+
     ArrRef arr[5];
 };
 
@@ -173,6 +175,9 @@ bool run_gather(Tree &t, int propid, int k, double period, const KernelParams &k
 void export_kdnodes(Tree &t, void *out, int64_t n_nodes);
 void record_stage(int stage, double ms, int64_t launches);
 void set_kernel_ms(int which, double ms);
+// flags (uint8, TREE order, pre-zeroed) of the particles inside any of nq balls; centres are dense
+// device columns T[3][nq], radii T[nq]
+void run_mark_in_balls(Tree &t, const void *centres_cols, const void *radii, int64_t nq, double period, uint8_t *flags_tree);
 int64_t run_ball_query(Tree &t, double cx, double cy, double cz, double r, double period,
                        int64_t *out_host, int64_t cap);
 

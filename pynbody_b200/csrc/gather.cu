@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather(GatherArgs<T, Q> a
 
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
-    const bool active = lane < cnt;
+    const bool active = lane < cnt && (!tv.query_mask || tv.query_mask[start + lane]);
+    if (!__any_sync(FULL, active)) return;
     const int64_t p = start + lane;
     T qx = 0, qy = 0, qz = 0, h = 1;
     double qi[3] = {0, 0, 0};

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
 
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
-    const bool active = lane < cnt;
+    const bool active = lane < cnt && (!tv.query_mask || tv.query_mask[start + lane]);
+    if (!__any_sync(FULL, active)) return;          // no query of this bucket is selected
     T qx = 0, qy = 0, qz = 0;
     if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
 
@@ -264,7 +265,7 @@ void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &k
     if (nn_idx_dev) fuse_rho = false;
     if (t.dtype == PNB_F64) run_knn_typed<double>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
     else run_knn_typed<float>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
-    t.smooth_valid = true;
+    t.smooth_valid = true;                  // (for the particles selected by the query mask, if one is set)
     t.smooth_k = k;
     t.smooth_period = period > 0 ? period : 0;
     t.rho_valid = fuse_rho;

@@ -47,6 +47,7 @@ struct TreeView {
     const T *box;                 // [2*nsplit][6]
     const int32_t *bucket_start;  // [nsplit+1]
     const uint32_t *order;        // tree -> file
+    const uint8_t *query_mask;    // tree order; null = every particle is a query (pnb_set_query_mask)
     T period;                     // valid when periodic
     int periodic;
 };
@@ -61,6 +62,7 @@ inline TreeView<T> make_view(const Tree &t, double period)
     v.box = t.box.as<T>();
     v.bucket_start = t.bucket_start.as<int32_t>();
     v.order = t.order.as<uint32_t>();
+    v.query_mask = t.query_mask.p ? t.query_mask.as<uint8_t>() : nullptr;
     v.periodic = period > 0;
     v.period = v.periodic ? (T)period : (T)0;
     return v;

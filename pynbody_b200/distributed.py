@@ -1,0 +1,391 @@
+"""Multi-GPU host layer: spatial domain decomposition, halo exchange, image reduction.
+
+The reference is single-process; this module is what lets the same path run on
+the 8 B200s of one box, one process per GPU, with ``torch.distributed`` (NCCL over NVLink) for the
+exchange steps.  Per rank the work is the single-GPU path of ``libpnb_b200.so``; the only collectives
+are where the algorithm has a real exchange:
+
+  1. ``decompose``     recursive coordinate bisection of the (periodic) box into one cuboid domain per
+                       rank, split planes from an all-gathered coordinate sample (equal particle counts);
+  2. ``_alltoallv``    particles move to the rank that owns their domain (all_to_all_single);
+  3. smoothing pass    every rank searches its OWN particles first.  That already is the exact answer
+                       for every particle whose k-neighbour ball lies inside the domain, and an upper
+                       bound r_ub on the ball radius for the rest ("boundary queries");
+  4. halo exchange     boundary queries (centre, r_ub) are sent to the ranks whose domain their ball
+                       touches; those ranks mark exactly the particles inside any received ball
+                       (``pnb_mark_in_balls``) and send them back -- a need-based halo, not a fixed-width
+                       shell, so void particles with large h do not inflate it;
+  5. re-search         boundary queries only (``pnb_set_query_mask``) on owned + halo particles;
+  6. later passes      (mean / dispersion / div / curl need rho and the quantity of halo particles):
+                       the same send lists carry those per-particle values (halo exchange #2);
+  7. results return to the rank and position they came from (inverse all_to_all);
+  8. images: every rank renders its own particles into a full frame, ``reduce_image`` sums the frames.
+
+All tensor plumbing is torch (CPU tensors + gloo in the tests, CUDA tensors + NCCL in production); the
+local compute goes through a backend object -- ``GpuBackend`` (the C ABI) unless a test injects another.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+OPS = {"mean": "qty_mean", "disp": "qty_disp", "div": "qty_div", "curl": "qty_curl"}
+
+
+# ------------------------------------------------------------------------------------------------
+# local compute backend: the single-GPU C-ABI path
+# ------------------------------------------------------------------------------------------------
+class GpuLocalTree:
+    """One rank's device tree over (owned [+ halo]) particles; thin wrapper over the C ABI."""
+
+    def __init__(self, pos, mass, boxsize):
+        from .kdtree import KDTree
+        self.pos, self.mass = pos.contiguous(), mass.contiguous()
+        self.n = int(pos.shape[0])
+        self.kd = KDTree(self.pos, self.mass, leafsize=32, boxsize=boxsize)
+        self.boxsize = boxsize
+
+    def _mask(self, mask):
+        from . import _lib
+        h = self.kd.kdtree.require_built()
+        if mask is None:
+            _lib.check(_lib.lib().pnb_set_query_mask(h, None, _lib.DEVICE))
+        else:
+            m = mask.to(torch.uint8).contiguous()
+            _lib.check(_lib.lib().pnb_set_query_mask(h, m.data_ptr(), _lib.DEVICE if m.is_cuda else _lib.HOST))
+
+    def knn_smooth(self, k, mask=None, kernel_id=0):
+        self.kd._kernel_id = int(kernel_id)
+        self._mask(mask)
+        sm = torch.empty(self.n, dtype=self.pos.dtype, device=self.pos.device)
+        self.kd.set_array_ref("smooth", sm)
+        self.kd.populate("hsm", k)
+        return sm
+
+    def density(self, sm, k, kernel_id, mask=None):
+        self.kd._kernel_id = int(kernel_id)
+        self._mask(mask)
+        rho = torch.empty(self.n, dtype=self.pos.dtype, device=self.pos.device)
+        self.kd.set_array_ref("smooth", sm)
+        self.kd.set_array_ref("mass", self.mass)
+        self.kd.set_array_ref("rho", rho)
+        self.kd.populate("rho", k)
+        return rho
+
+    def reduce(self, op, sm, rho, qty, k, kernel_id, mask=None):
+        self.kd._kernel_id = int(kernel_id)
+        self._mask(mask)
+        out_shape = tuple(qty.shape) if op in ("mean", "curl") else (self.n,)
+        out = torch.empty(out_shape, dtype=qty.dtype, device=qty.device)
+        self.kd.set_array_ref("smooth", sm)
+        self.kd.set_array_ref("mass", self.mass)
+        self.kd.set_array_ref("rho", rho)
+        self.kd.set_array_ref("qty", qty.contiguous())
+        self.kd.set_array_ref("qty_sm", out)
+        self.kd.populate(OPS[op], k)
+        return out
+
+    def mark_in_balls(self, centres, radii):
+        from . import _lib
+        flags = torch.zeros(self.n, dtype=torch.uint8, device=self.pos.device)
+        nq = int(centres.shape[0])
+        if nq == 0:
+            return flags.bool()
+        c = centres.to(self.pos.dtype).contiguous()
+        r = radii.to(self.pos.dtype).contiguous()
+        es = c.element_size()
+        period = -1.0 if self.boxsize is None else float(self.boxsize)
+        _lib.check(_lib.lib().pnb_mark_in_balls(self.kd.kdtree.require_built(), c.data_ptr(), 3 * es, es, r.data_ptr(), es,
+                                                nq, period, flags.data_ptr(), _lib.DEVICE if c.is_cuda else _lib.HOST))
+        return flags.bool()
+
+
+class GpuBackend:
+    def make_tree(self, pos, mass, boxsize):
+        return GpuLocalTree(pos, mass, boxsize)
+
+
+# ------------------------------------------------------------------------------------------------
+# domain decomposition
+# ------------------------------------------------------------------------------------------------
+def _bisect(sample, lo, hi, ranks, out):
+    """Recursive coordinate bisection of box [lo,hi) among `ranks` using the coordinate sample."""
+    if len(ranks) == 1:
+        out[ranks[0]] = (lo.clone(), hi.clone())
+        return
+    nleft = len(ranks) // 2
+    if sample.shape[0] > 0:
+        ext = sample.max(dim=0).values - sample.min(dim=0).values
+    else:
+        ext = hi - lo
+    axis = int(torch.argmax(ext))
+    if sample.shape[0] > 1:
+        q = torch.quantile(sample[:, axis].double(), nleft / len(ranks)).to(sample.dtype)
+    else:
+        q = (lo[axis] + hi[axis]) / 2 if torch.isfinite(lo[axis] + hi[axis]) else torch.zeros((), dtype=lo.dtype)
+    left = sample[:, axis] < q
+    hi_l, lo_r = hi.clone(), lo.clone()
+    hi_l[axis] = q
+    lo_r[axis] = q
+    _bisect(sample[left], lo, hi_l, ranks[:nleft], out)
+    _bisect(sample[~left], lo_r, hi, ranks[nleft:], out)
+
+
+def decompose(pos, boxsize, group=None, sample_per_rank=32768, seed=0):
+    """One cuboid domain (lo[3], hi[3]) per rank; identical on every rank.
+
+    Periodic: domains tile [gmin, gmin + boxsize)^3.  Open: outer faces are +-inf.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev, dt = pos.device, pos.dtype
+    n = pos.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(seed + 7919 * (dist.get_rank(group) if dist.is_initialized() else 0))
+    m = sample_per_rank
+    samp = torch.full((m, 3), float("nan"), dtype=dt, device=dev)
+    if n > 0:
+        idx = torch.randint(0, n, (min(m, n),), generator=g).to(dev)
+        samp[: idx.numel()] = pos[idx]
+    if n > 0:
+        mn, mx = pos.min(dim=0).values, pos.max(dim=0).values
+    else:
+        mn = torch.full((3,), float("inf"), dtype=dt, device=dev)
+        mx = -mn
+    if world > 1:
+        allsamp = [torch.empty_like(samp) for _ in range(world)]
+        dist.all_gather(allsamp, samp, group=group)
+        samp = torch.cat(allsamp)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    samp = samp[~torch.isnan(samp[:, 0])].cpu()
+    mn, mx = mn.cpu(), mx.cpu()
+    periodic = boxsize is not None and boxsize > 0 and bool(((mx - mn) <= boxsize).all())
+    if periodic:
+        lo, hi = mn.clone(), mn + boxsize
+    else:
+        lo = torch.full((3,), float("-inf"), dtype=dt)
+        hi = torch.full((3,), float("inf"), dtype=dt)
+    out = [None] * world
+    _bisect(samp, lo, hi, list(range(world)), out)
+    return out, periodic
+
+
+def owner_of(pos, domains):
+    """Rank owning each particle.  Faces on the outside of the decomposed box are treated as open, so
+    a particle sitting exactly on (or rounded just past) the outer edge still has exactly one owner."""
+    owner = torch.zeros(pos.shape[0], dtype=torch.int64, device=pos.device)
+    root_lo = torch.stack([d[0] for d in domains]).min(dim=0).values
+    root_hi = torch.stack([d[1] for d in domains]).max(dim=0).values
+    for r, (lo, hi) in enumerate(domains):
+        lo = torch.where(lo <= root_lo, torch.full_like(lo, float("-inf")), lo).to(pos.device)
+        hi = torch.where(hi >= root_hi, torch.full_like(hi, float("inf")), hi).to(pos.device)
+        inside = ((pos >= lo) & (pos < hi)).all(dim=1)
+        owner = torch.where(inside, torch.full_like(owner, r), owner)
+    return owner
+
+
+def _box_gap2(x, lo, hi, period):
+    """Squared distance from points x[n,3] to the cuboid [lo,hi), nearest periodic image per axis."""
+    def gap(v):
+        return torch.clamp(torch.maximum(lo - v, v - hi), min=0)
+    g = gap(x)
+    if period is not None:
+        g = torch.minimum(g, torch.minimum(gap(x + period), gap(x - period)))
+    return (g * g).sum(dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives
+# ------------------------------------------------------------------------------------------------
+def _alltoallv(per_dest, group=None):
+    """Variable-size all-to-all: per_dest[r] goes to rank r; returns the list received from each rank."""
+    world = dist.get_world_size(group)
+    dev = per_dest[0].device
+    counts = torch.tensor([t.shape[0] for t in per_dest], dtype=torch.int64, device=dev)
+    rcounts = torch.empty_like(counts)
+    dist.all_to_all_single(rcounts, counts, group=group)
+    rc, sc = rcounts.tolist(), counts.tolist()
+    send = torch.cat(per_dest).contiguous()
+    recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return list(recv.split(rc))
+
+
+def reduce_image(img, dst=0, group=None):
+    """Sum the per-rank partial frames (each rank rendered its own particles) onto rank `dst`."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(img, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return img
+
+
+# ------------------------------------------------------------------------------------------------
+class DistributedKDTree:
+    """Smoothing lengths, densities and SPH reductions of a particle set spread over ranks.
+
+    ``pos`` / ``mass`` are this rank's share of the particles in ANY order (e.g. a file chunk); results
+    come back aligned with them.  Values equal the single-process results: neighbour searches are exact
+    and the halo is complete by construction.
+    """
+
+    def __init__(self, pos, mass, boxsize=None, group=None, backend=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.backend = backend or GpuBackend()
+        self.n_in = int(pos.shape[0])
+        self.dev, self.dt = pos.device, pos.dtype
+        self.domains, periodic = decompose(pos, boxsize, group)
+        self.boxsize = float(boxsize) if periodic else None
+        self.requested_boxsize = boxsize
+        if self.world > 1:
+            owner = owner_of(pos, self.domains)
+            order = torch.argsort(owner, stable=True)
+            counts = torch.bincount(owner, minlength=self.world).tolist()
+            src_idx = order                                         # original local index of each sent particle
+            self._ret_counts = counts                               # what I sent to each rank (returns come back so)
+            self._ret_index = src_idx
+            pos_s, mass_s = pos[order], mass[order]
+            self.pos = torch.cat(_alltoallv(list(pos_s.split(counts)), group))
+            recv_mass = _alltoallv(list(mass_s.split(counts)), group)
+            self._own_counts = [int(t.shape[0]) for t in recv_mass]  # owned particles grouped by source rank
+            self.mass = torch.cat(recv_mass)
+        else:
+            self.pos, self.mass = pos, mass
+        self.n_own = int(self.pos.shape[0])
+        self.tree1 = self.backend.make_tree(self.pos, self.mass, self.boxsize)
+        self.tree2 = None
+        self._halo_send = None          # per destination rank: indices (into owned) of the particles it needs
+        self._k = None
+        self.stats = {}
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _to_origin(self, owned_values):
+        """Owned-order values -> the rank/order the particles came from."""
+        if self.world == 1:
+            return owned_values
+        back = _alltoallv(list(owned_values.split(self._own_counts)), self.group)
+        flat = torch.cat(back)
+        out = torch.empty((self.n_in,) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
+        out[self._ret_index] = flat
+        return out
+
+    def _from_origin(self, values):
+        """Per-particle values given in the input order -> owned order (same routing as the positions)."""
+        if self.world == 1:
+            return values
+        v = values[self._ret_index]
+        return torch.cat(_alltoallv(list(v.split(self._ret_counts)), self.group))
+
+    def _boundary_distance(self):
+        lo, hi = (t.to(self.dev) for t in self.domains[self.rank])
+        d = torch.minimum(self.pos - lo, hi - self.pos)             # +inf along open / unsplit outer faces
+        if self.boxsize is not None:
+            full = (hi - lo) >= self.boxsize * (1 - 1e-12)          # domain spans the whole period: no face
+            d = torch.where(full, torch.full_like(d, float("inf")), d)
+        return d.min(dim=1).values
+
+    # -- smoothing lengths + halo construction ---------------------------------------------------------
+    def smooth(self, k, kernel_id=0):
+        """Smoothing lengths (and, as a by-product, the halo for all later passes with this k)."""
+        sm = self.tree1.knn_smooth(k, None, kernel_id) if self.n_own >= k else None
+        self._sm_stage1 = sm
+        if self.world == 1:
+            if sm is None:
+                raise ValueError("Number of smoothing particles exceeds number of particles in tree")
+            self._sm_own, self._k = sm, k
+            return sm
+        if sm is None:                                              # fewer than k owned particles: everything is boundary
+            r_ub = torch.full((self.n_own,), float("inf"), dtype=self.dt, device=self.dev)
+            sm = torch.zeros(self.n_own, dtype=self.dt, device=self.dev)
+        else:
+            r_ub = 2 * sm
+        flagged = r_ub * (1 + 1e-6) >= self._boundary_distance()
+        period = self.boxsize
+        # boundary queries -> the ranks whose domain their ball touches
+        fidx = torch.nonzero(flagged).squeeze(1)
+        fpos, frad = self.pos[fidx], r_ub[fidx] * (1 + 1e-6)      # cover rounding of r = 2h = sqrt(d2_k)
+        sends = []
+        for r in range(self.world):
+            if r == self.rank:
+                sends.append(torch.empty((0, 4), dtype=self.dt, device=self.dev))
+                continue
+            lo, hi = (t.to(self.dev) for t in self.domains[r])
+            touch = _box_gap2(fpos, lo, hi, period) <= frad * frad * (1 + 1e-6)
+            sends.append(torch.cat([fpos[touch], frad[touch, None]], dim=1))
+        balls = _alltoallv(sends, self.group)
+        # which of my particles do they need?
+        self._halo_send = []
+        for r in range(self.world):
+            b = balls[r]
+            if r == self.rank or b.shape[0] == 0:
+                self._halo_send.append(torch.empty(0, dtype=torch.int64, device=self.dev))
+                continue
+            rad = torch.where(torch.isfinite(b[:, 3]), b[:, 3], torch.full_like(b[:, 3], 1e30))
+            self._halo_send.append(torch.nonzero(self.tree1.mark_in_balls(b[:, :3].contiguous(), rad)).squeeze(1))
+        halo_pos = torch.cat(_alltoallv([self.pos[i] for i in self._halo_send], self.group))
+        halo_mass = torch.cat(_alltoallv([self.mass[i] for i in self._halo_send], self.group))
+        self.n_halo = int(halo_pos.shape[0])
+        self.stats = {"owned": self.n_own, "boundary_queries": int(fidx.numel()), "halo": self.n_halo}
+        # re-search the boundary queries on owned + halo
+        self.tree2 = self.backend.make_tree(torch.cat([self.pos, halo_pos]), torch.cat([self.mass, halo_mass]), self.boxsize)
+        self._own_mask2 = torch.cat([torch.ones(self.n_own, dtype=torch.bool, device=self.dev),
+                                     torch.zeros(self.n_halo, dtype=torch.bool, device=self.dev)])
+        if self.tree2.n < k:
+            raise ValueError("Number of smoothing particles exceeds number of particles in tree")
+        if fidx.numel() > 0:
+            mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
+            mask2[fidx] = True
+            sm2 = self.tree2.knn_smooth(k, mask2, kernel_id)
+            sm = sm.clone()
+            sm[fidx] = sm2[fidx]
+        self._fidx = fidx
+        self._sm_own, self._k = sm, k
+        return sm
+
+    def _halo_values(self, owned_values):
+        """Halo exchange #2: per-particle values of the halo particles, in tree2's halo order."""
+        return torch.cat(_alltoallv([owned_values[i] for i in self._halo_send], self.group))
+
+    def smooth_rho(self, k, kernel_id=0):
+        """(smooth, rho) aligned with the input particles."""
+        sm = self.smooth(k, kernel_id)
+        if self.world == 1:
+            rho = self.tree1.density(sm, k, kernel_id)
+        else:
+            # interior particles: their neighbours are all owned, so the owned-only tree is exact (and its
+            # density rode along the kNN pass when masses are uniform); boundary queries: owned + halo
+            if self._sm_stage1 is not None:
+                rho = self.tree1.density(self._sm_stage1, k, kernel_id)
+            else:
+                rho = torch.zeros(self.n_own, dtype=self.dt, device=self.dev)
+            if self._fidx.numel() > 0:
+                mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
+                mask2[self._fidx] = True
+                sm_all = torch.cat([sm, torch.ones(self.n_halo, dtype=self.dt, device=self.dev)])
+                rho2 = self.tree2.density(sm_all, k, kernel_id, mask2)
+                rho = rho.clone()
+                rho[self._fidx] = rho2[self._fidx]
+        self._rho_own = rho
+        return self._to_origin(sm), self._to_origin(rho)
+
+    def sph_op(self, op, qty, k=None, kernel_id=0):
+        """mean | disp | div | curl of `qty` (input order), after smooth_rho(k)."""
+        k = k or self._k
+        q_own = self._from_origin(qty)
+        if self.world == 1:
+            out = self.tree1.reduce(op, self._sm_own, self._rho_own, q_own, k, kernel_id)
+        else:
+            ones = torch.ones(self.n_halo, dtype=self.dt, device=self.dev)
+            sm_all = torch.cat([self._sm_own, ones])
+            rho_all = torch.cat([self._rho_own, self._halo_values(self._rho_own)])
+            q_all = torch.cat([q_own, self._halo_values(q_own)])
+            out = self.tree2.reduce(op, sm_all, rho_all, q_all, k, kernel_id, self._own_mask2)[: self.n_own]
+        if out.dim() == 2 and op in ("disp", "div"):
+            out = out[:, 0]
+        return self._to_origin(out)
+
+    def owned(self):
+        """(pos, mass, smooth, rho) of the particles this rank owns -- what it renders."""
+        return self.pos, self.mass, self._sm_own, self._rho_own

@@ -7,6 +7,8 @@ N x 3, ``mass`` N) in the requested dtype, with positions wrapped into
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 
@@ -96,3 +98,45 @@ def gaussian_blobs(n, seed=7, dtype=np.float64, n_blobs=5):
     vel = rng.normal(size=(n, 3)) + centres[which] * 3.0
     mass = rng.uniform(0.5, 1.5, n) / n
     return pos.astype(dtype), vel.astype(dtype), mass.astype(dtype)
+
+
+def zeldovich_box_device(n_side, seed=2, dtype=np.float64, device="cuda", rank=0, world=1, boxsize=1.0,
+                         sigma_cells=2.0):
+    """The ``zeldovich_box`` recipe evaluated with torch on ``device`` (C4/C5: the global field is too
+    large to generate with numpy on every rank).  Every rank evaluates the same global field (same
+    seed) and returns its Lagrangian slab ``rank`` of ``world`` -- a share of the particles that is
+    *not* a spatial partition, as a file chunk would be.  Returns torch tensors (pos, vel, mass)."""
+    import torch
+    tdt = torch.float64
+    n = n_side
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    k1 = torch.fft.fftfreq(n, d=1.0 / n, device=device, dtype=tdt)
+    kz1 = torch.fft.rfftfreq(n, d=1.0 / n, device=device, dtype=tdt)
+    k2 = (k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz1[None, None, :] ** 2)
+    k2[0, 0, 0] = 1.0
+    kcut = n / 8.0
+    amp = torch.where(k2 <= kcut * kcut, 1.0 / k2, torch.zeros_like(k2))
+    amp[0, 0, 0] = 0.0
+    del k2
+    phik = torch.complex(torch.randn(amp.shape, generator=g, device=device, dtype=tdt),
+                         torch.randn(amp.shape, generator=g, device=device, dtype=tdt)) * amp
+    del amp
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    comps, var = [], 0.0
+    for axis, kk in enumerate((k1[:, None, None], k1[None, :, None], kz1[None, None, :])):
+        comp = torch.fft.irfftn(1j * kk * phik, s=(n, n, n), dim=(0, 1, 2))
+        var += float(comp.var())
+        comps.append(comp[lo:hi].reshape(-1).clone())
+        del comp
+    del phik
+    psi = torch.stack(comps, dim=1)
+    psi *= sigma_cells / math.sqrt(var / 3.0)
+    gl = torch.arange(n, device=device, dtype=tdt) + 0.5
+    q = torch.stack(torch.meshgrid(gl[lo:hi], gl, gl, indexing="ij"), dim=-1).reshape(-1, 3)
+    pos = torch.remainder((q + psi) * (boxsize / n), boxsize)
+    vel = psi * 0.5 + 0.1 * torch.randn(psi.shape, generator=g, device=device, dtype=tdt)
+    out_dt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    pos = pos.to(out_dt)
+    pos[pos >= boxsize] = 0.0
+    mass = torch.full((pos.shape[0],), 1.0 / n ** 3, dtype=out_dt, device=device)
+    return pos.contiguous(), vel.to(out_dt).contiguous(), mass
