@@ -329,6 +329,125 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ours_distributed(args):
+    """N > 1: ONE global periodic box of about N x n_side^3 particles, spatially decomposed over the
+    ranks (pynbody_b200.distributed): coordinate-bisection domains, NCCL all-to-all of the particles,
+    need-based halo exchange, masked re-search of boundary queries.  Weak scaling: the per-GPU share
+    is fixed, the global box grows with N."""
+    import torch
+    import torch.distributed as dist
+    from pynbody_b200 import synth
+    from pynbody_b200.distributed import DistributedKDTree
+    from pynbody_b200.kdtree import kdmain
+
+    rank, world, local = (int(os.environ.get(v, "0")) for v in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    tsz = np.dtype(dtype).itemsize
+    side = int(round((world * args.n_side ** 3) ** (1.0 / 3.0)))
+    n_total = side ** 3
+    pos, vel, mass = synth.zeldovich_box_device(side, 2, dtype, "cuda", rank, world)
+    n_local = int(pos.shape[0])
+    h_pos = torch.empty(pos.shape, dtype=pos.dtype, pin_memory=True); h_pos.copy_(pos)
+    h_mass = torch.empty(mass.shape, dtype=mass.dtype, pin_memory=True); h_mass.copy_(mass)
+    h_sm = torch.empty(n_local, dtype=mass.dtype, pin_memory=True)
+    h_rho = torch.empty(n_local, dtype=mass.dtype, pin_memory=True)
+    last = {}
+
+    def step(p, m):
+        d = DistributedKDTree(p, m, boxsize=1.0)
+        sm, rho = d.smooth_rho(K_NEIGHBOURS, 1)
+        last["d"] = d
+        return sm, rho
+
+    def step_e2e():
+        p = h_pos.cuda(non_blocking=True)
+        m = h_mass.cuda(non_blocking=True)
+        sm, rho = step(p, m)
+        h_sm.copy_(sm, non_blocking=True)
+        h_rho.copy_(rho, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(pos, mass)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = kdmain.total_launches()
+    total_ms = timed(lambda: step(pos, mass), args.steps)
+    launches = kdmain.total_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    d = last["d"]
+    if args.verbose and rank == 0 and d.timings:
+        print("[dist phases ms] " + ", ".join(f"{k}={v:.1f}" for k, v in d.timings.items()), file=sys.stderr, flush=True)
+    st = torch.tensor([d.n_own, d.stats.get("boundary_queries", 0), d.stats.get("halo", 0)], device="cuda", dtype=torch.float64)
+    allst = [torch.empty_like(st) for _ in range(world)]
+    dist.all_gather(allst, st)
+
+    # C5-style image: every rank renders the particles it owns, frames are summed over NVLink
+    render = {}
+    if not args.no_render:
+        from pynbody_b200.distributed import reduce_image
+        from pynbody_b200.sph import _render, kernels
+        k2 = kernels.create_kernel(KERNEL).projection()
+        wrap = [-1.0, 0.0, 1.0]
+        res = args.render_res
+        opos, omass, osm, orho = d.owned()
+        def once():
+            img = _render.render_image(res, res, opos[:, 0], opos[:, 1], opos[:, 2], osm, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5,
+                                       orho, omass, orho, 0.0, float("inf"), float("-inf"), float("inf"), 0.0, k2, wrap, wrap)
+            return reduce_image(img)
+        once()
+        ms = timed(once, 2) / 2
+        render["image"] = {"resolution": res, "mode": "projected density, 3x3 periodic images, per-rank frames summed with an NCCL reduce",
+                           "ms": ms, "mpix_per_s": res * res / (ms * 1e-3) / 1e6}
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        knn_ms = kdmain.last_kernel_ms(0)
+        cfg = workload_config(args)
+        cfg["workload"] = (f"C4/C5-style: ONE global {n_total}-particle ({side}^3) clustered Zel'dovich-like periodic box "
+                           f"decomposed over {world} GPUs (~{n_total // world} particles per GPU), sim['rho'] = domain decomposition + "
+                           f"tree build + smooth + rho, k={K_NEIGHBOURS}, WendlandC2, {args.dtype}")
+        cfg["parallelism"] = (f"spatial domains x{world} (coordinate bisection), NCCL all-to-all particle routing + need-based halo "
+                              f"exchange + masked re-search; image = per-rank frames + NCCL reduce")
+        cfg["global_particles"] = n_total
+        cfg["per_rank_owned_boundary_halo"] = [[int(v) for v in s.tolist()] for s in allst]
+        line = {"metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": cfg,
+                "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": n_local * tsz * 4, "d2h_bytes_per_step": n_local * tsz * 2},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_knn (last launch on rank 0: masked re-search of boundary queries)",
+                             "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                             "peak_source": peak_src, "kernel_ms": knn_ms,
+                             "note": "per-kernel roofline is reported by the N=1 run; see DESIGN.md"},
+                "render": render}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,7 +469,10 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_ours(args)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            run_ours_distributed(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

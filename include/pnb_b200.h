@@ -76,7 +76,7 @@ int pnb_set_device(int device);
 /* ---- tree: kdmain.init + kdmain.build (kdmain.cpp:189-302; kd.cpp:98-238) --------------------
  * Uploads pos (N x 3) and mass (N), builds a balanced median-split kd-tree on the GPU and keeps
  * the particles resident in tree order as structure-of-arrays.  `leafsize` is the reference's
- * user-visible leaf size: it only shapes pnb_tree_node_count / pnb_tree_export_kdnodes; the
+ * user-visible leaf size: it only shapes pnb_tree_node_count / pnb_tree_export; the
  * device tree always uses 32-particle buckets (one warp lane per particle).
  * `boxsize` <= 0 means non-periodic (kdmain.cpp:360-361).  mass may be NULL. */
 pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stride1,
@@ -90,12 +90,15 @@ int64_t pnb_tree_num_particles(const pnb_tree *t);
 int pnb_tree_bounds(const pnb_tree *t, double *out6);
 /* kdmain.get_node_count (kd.cpp:98-111): 2 * nSplit for the user's leafsize */
 int64_t pnb_tree_node_count(const pnb_tree *t);
-/* particle_offsets (tree order -> file order), int64[N], host memory */
+/* device-tree order (tree position -> file index), int64[N], host memory.  This is the order of the
+ * 32-particle-bucket tree the kernels traverse; see pnb_tree_export for the reference-shaped tree. */
 int pnb_tree_order(pnb_tree *t, int64_t *out);
-/* reference-layout KDNode[node_count] records (kd.h:29-40, 80 bytes each), host memory.
- * Together with pnb_tree_order this is what KDTree.serialize() returns
- * (pynbody/kdtree/__init__.py:136-163). */
-int pnb_tree_export_kdnodes(pnb_tree *t, void *out, int64_t n_nodes);
+/* What KDTree.serialize() returns (pynbody/kdtree/__init__.py:136-163): reference-layout
+ * KDNode[node_count] records (kd.h:29-40, 80 bytes each) and the matching particle_offsets int64[N]
+ * (tree order -> file order) of a tree with the reference's shape for the user's leafsize (median
+ * splits m=(lo+hi)/2, kd.cpp:98-111,176-199), built on the GPU on demand.  Either output may be NULL.
+ * Host memory. */
+int pnb_tree_export(pnb_tree *t, void *kdnodes_out, int64_t n_nodes, int64_t *offsets_out);
 /* device-tree introspection used by the tests: number of 32-particle buckets, their start offsets
  * (int64[n_buckets + 1]) and tight bounds (double[n_buckets][6] = min xyz, max xyz), host memory */
 int64_t pnb_tree_num_buckets(const pnb_tree *t);
@@ -187,6 +190,8 @@ int64_t pnb_last_launch_count(int stage);
  * kernels on this thread: 0 = kNN (+fused density) kernel, 1 = gather/reduction kernel,
  * 2 = image/grid render kernel.  This is what bench.py's roofline block divides by. */
 double pnb_last_kernel_ms(int which);
+/* cumulative number of kernel launches issued by this thread through the library */
+int64_t pnb_total_launches(void);
 
 #ifdef __cplusplus
 }

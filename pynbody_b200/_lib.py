@@ -47,7 +47,7 @@ SIGNATURES = {
     "pnb_tree_bounds": (_i32, [_vp, _vp]),
     "pnb_tree_node_count": (_i64, [_vp]),
     "pnb_tree_order": (_i32, [_vp, _vp]),
-    "pnb_tree_export_kdnodes": (_i32, [_vp, _vp, _i64]),
+    "pnb_tree_export": (_i32, [_vp, _vp, _i64, _vp]),
     "pnb_tree_num_buckets": (_i64, [_vp]),
     "pnb_tree_buckets": (_i32, [_vp, _vp, _vp]),
     "pnb_set_array": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _i32]),
@@ -64,6 +64,7 @@ SIGNATURES = {
     "pnb_last_device_ms": (_dbl, [_i32]),
     "pnb_last_launch_count": (_i64, [_i32]),
     "pnb_last_kernel_ms": (_dbl, [_i32]),
+    "pnb_total_launches": (_i64, []),
 }
 
 _LIB = None

@@ -358,7 +358,7 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
             mass_dev.alloc(ts * n);
             fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
         }
-        build_tree(*t, cols, mass ? mass_dev.p : nullptr);
+        build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
         update_mass_uniformity(*t);
         timer.stop();
     });
@@ -415,10 +415,10 @@ int pnb_tree_buckets(pnb_tree *h, int64_t *start, double *bounds)
     });
 }
 
-int pnb_tree_export_kdnodes(pnb_tree *h, void *out, int64_t n_nodes)
+int pnb_tree_export(pnb_tree *h, void *kdnodes_out, int64_t n_nodes, int64_t *offsets_out)
 {
     Tree *t = reinterpret_cast<Tree *>(h);
-    return guarded([&] { export_kdnodes(*t, out, n_nodes); });
+    return guarded([&] { require_device(); export_reference_tree(*t, kdnodes_out, n_nodes, offsets_out); });
 }
 
 int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem)
@@ -562,6 +562,7 @@ int pnb_ball_query(pnb_tree *h, double cx, double cy, double cz, double r, doubl
 void pnb_release_cached_memory(void) { cache_trim(); }
 
 double pnb_last_device_ms(int stage) { return (stage >= 0 && stage < 3) ? g_stage_ms[stage] : 0.0; }
+int64_t pnb_total_launches(void) { return g_launches; }
 double pnb_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? g_kernel_ms[which] : 0.0; }
 int64_t pnb_last_launch_count(int stage) { return (stage >= 0 && stage < 3) ? g_stage_launches[stage] : 0; }
 

@@ -84,7 +84,19 @@ struct ArrRef {
 // ------------------------------------------------------------------------------------------------
 // the tree handle
 // ------------------------------------------------------------------------------------------------
+// how the implicit tree's nodes map to ranges of the particle permutation (tree_build.cu)
+struct TreeShape {
+    int64_t n = 0;
+    int levels = 0;     // buckets live at heap level `levels`
+    int packed = 1;     // 1: fixed-capacity buckets (device tree); 0: the reference's median ranges
+    int leafcap = 32;   // bucket capacity (packed) / leafsize (reference)
+};
+TreeShape packed_shape(int64_t n);
+TreeShape reference_shape(int64_t n, int leafsize);
+void shape_seg_of_node(const TreeShape &s, int level, int64_t j, int64_t &lo, int64_t &hi);
+
 struct Tree {
+    TreeShape shape;
     int dtype = PNB_F64;          // PNB_F32 / PNB_F64: dtype of pos/mass/smooth/rho ("T")
     int64_t n = 0;
     int user_leafsize = 16;
@@ -153,7 +165,7 @@ void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int nco
 
 // ---- stages --------------------------------------------------------------------------------------
 // cols: file-order coordinates as dense columns T[3][n]; mass_dev: T[n] in file order or null
-void build_tree(Tree &t, DevBuf &cols, const void *mass_dev);
+void build_tree(Tree &t, DevBuf &cols, const void *mass_dev, const TreeShape &shape, bool want_soa);
 
 struct KernelParams {
     int kernel_id;
@@ -172,7 +184,7 @@ bool run_gather(Tree &t, int propid, int k, double period, const KernelParams &k
                 const void *smooth_tree, const void *rho_tree, const void *qty_tree, int qdtype,
                 void *out_tree);
 // reference-layout KDNode records (kd.h:29-40) for the user's leafsize (export.cu)
-void export_kdnodes(Tree &t, void *out, int64_t n_nodes);
+void export_reference_tree(Tree &t, void *kdnodes_out, int64_t n_nodes, int64_t *offsets_out);
 void record_stage(int stage, double ms, int64_t launches);
 void set_kernel_ms(int which, double ms);
 // flags (uint8, TREE order, pre-zeroed) of the particles inside any of nq balls; centres are dense

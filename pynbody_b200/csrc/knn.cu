@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
             Box6<T> b = load_box(tv.box, cp);
             T sx, sy, sz;
             T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
-            bool pass = gap2 <= q.top * Ex<T>::slack();
+            bool pass = gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();   // (empty nodes: inverted bounds)
             if (__any_sync(FULL, pass)) {
                 if (cp < tv.nsplit) { cp = 2 * cp; continue; }
                 knn_visit_bucket<T, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, hd, hi, S, tile, lane);

@@ -1,20 +1,28 @@
-// tree_build.cu -- K1: balanced median-split kd-tree build on the GPU.
+// tree_build.cu -- K1: kd-tree build on the GPU.
 //
-// Replaces kdBuildTree / kdBuildNode / kdSelect / kdUpPass (pynbody/kdtree/kd.cpp:31-238).
-// Same tree shape as the reference (kd.cpp:98-111: all buckets at one depth, every node splits its
-// inclusive index range [lo,hi] at m=(lo+hi)/2 along the longest axis), but built breadth-first
-// with data-parallel passes instead of a recursive quickselect:
+// Replaces kdBuildTree / kdBuildNode / kdSelect / kdUpPass (pynbody/kdtree/kd.cpp:31-238).  The tree is
+// an implicit complete binary tree in heap order (root = 1, children 2i / 2i+1, all buckets at one
+// depth, kd.h:12-23) over a permutation of the particles; every node splits its particle range along
+// the longest axis of its tight bounds.  It is built breadth-first with data-parallel passes instead of
+// a recursive quickselect:
 //
 //   1. three radix sorts give, per axis, the list of particle ids ordered by that coordinate;
 //   2. per level, every node reads its tight bounds straight off the ends of its three list
 //      segments (no up-pass needed), picks its split axis, and the other two lists are
-//      stable-partitioned about the median rank with one global prefix sum;
+//      stable-partitioned about the split rank with one global prefix sum;
 //   3. after the last level the x-list *is* the tree order; particles are gathered once into
 //      tree-ordered structure-of-arrays x[], y[], z[], mass[] so that a 32-particle bucket is
 //      32 consecutive elements (one coalesced 128/256-byte line per coordinate).
 //
-// Unlike the reference (kd.cpp:168-174, split axis from the *inherited* box) the split axis is
-// taken from the tight box; neighbour sets do not depend on tree shape.
+// Two range shapes share the code:
+//   PACKED     (the device tree the kernels traverse) node (level, j) owns ranks
+//              [j*cap, min(n,(j+1)*cap)), cap = 32 << (levels-level): every bucket holds exactly 32
+//              particles (one per warp lane) except the last one; trailing buckets may be empty and
+//              carry inverted (+inf,-inf) bounds so no search ever opens them.
+//   REFERENCE  (only for KDTree.serialize(), export.cu) the reference's shape: inclusive range [lo,hi]
+//              split at m=(lo+hi)/2 (kd.cpp:176-199), leaf count from kdCountNodes (kd.cpp:98-111).
+// Unlike the reference (kd.cpp:168-174, split axis from the *inherited* box) the split axis is taken
+// from the tight box; neighbour sets do not depend on tree shape.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -24,18 +32,45 @@
 
 namespace pnb {
 
-// ---- index arithmetic of the implicit balanced tree (kd.cpp:176-199: m = (lo+hi)/2) --------------
-__host__ __device__ inline void seg_of_node(int64_t n, int level, int64_t j, int64_t &lo, int64_t &hi)
+// ---- index arithmetic of the implicit tree ----------------------------------------------------------
+// inclusive rank range [lo,hi] of node (level, j); empty nodes have hi < lo
+__host__ __device__ inline void seg_of_node(const TreeShape &s, int level, int64_t j, int64_t &lo, int64_t &hi)
 {
-    lo = 0; hi = n - 1;
+    if (s.packed) {
+        const int64_t cap = (int64_t)s.leafcap << (s.levels - level);
+        lo = j * cap;
+        hi = lo + cap - 1;
+        if (hi > s.n - 1) hi = s.n - 1;
+        if (lo > s.n) lo = s.n;
+        return;
+    }
+    lo = 0; hi = s.n - 1;
     for (int b = level - 1; b >= 0; --b) {
         int64_t m = (lo + hi) >> 1;
         if ((j >> b) & 1) lo = m + 1; else hi = m;
     }
 }
-__host__ __device__ inline void seg_of_pos(int64_t n, int level, int64_t p, int64_t &lo, int64_t &hi, int64_t &node)
+// last rank that goes to the lower child of a node owning [lo,hi]
+__host__ __device__ inline int64_t split_rank(const TreeShape &s, int level, int64_t lo, int64_t hi)
 {
-    lo = 0; hi = n - 1; node = 1;
+    if (s.packed) {
+        const int64_t m = lo + ((int64_t)s.leafcap << (s.levels - level - 1)) - 1;
+        return m < hi ? m : hi;
+    }
+    return (lo + hi) >> 1;
+}
+__host__ __device__ inline void seg_of_pos(const TreeShape &s, int level, int64_t p, int64_t &lo, int64_t &hi, int64_t &node)
+{
+    if (s.packed) {
+        const int64_t cap = (int64_t)s.leafcap << (s.levels - level);
+        const int64_t j = p / cap;
+        lo = j * cap;
+        hi = lo + cap - 1;
+        if (hi > s.n - 1) hi = s.n - 1;
+        node = ((int64_t)1 << level) + j;
+        return;
+    }
+    lo = 0; hi = s.n - 1; node = 1;
     for (int i = 0; i < level; ++i) {
         int64_t m = (lo + hi) >> 1;
         if (p <= m) { hi = m; node = 2 * node; } else { lo = m + 1; node = 2 * node + 1; }
@@ -63,49 +98,59 @@ __global__ void k_make_keys(const T *__restrict__ c, int64_t n, K *__restrict__ 
     ids[i] = (uint32_t)i;
 }
 
+template <typename T> __device__ inline T pos_inf();
+template <> __device__ inline float pos_inf<float>() { return __int_as_float(0x7f800000); }
+template <> __device__ inline double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000ll); }
+
 // one thread per node of `level`: tight bounds from the list ends, split axis, split value
 template <typename T>
-__global__ void k_node_bounds(int64_t n, int level, const uint32_t *__restrict__ L, const T *__restrict__ c,
+__global__ void k_node_bounds(TreeShape s, int level, const uint32_t *__restrict__ L, const T *__restrict__ c,
                               T *__restrict__ box, int8_t *__restrict__ dim_out, T *__restrict__ split_out, bool leaf,
                               int32_t *__restrict__ bucket_start)
 {
+    const int64_t n = s.n;
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t nn = (int64_t)1 << level;
     if (j >= nn) return;
     int64_t lo, hi;
-    seg_of_node(n, level, j, lo, hi);
+    seg_of_node(s, level, j, lo, hi);
     int64_t node = nn + j;
+    T *b = box + node * 6;
+    if (leaf) {
+        bucket_start[j] = (int32_t)lo;
+        if (j == nn - 1) bucket_start[nn] = (int32_t)n;
+    }
+    if (hi < lo) {                                   // empty: inverted bounds keep every search out
+        const T inf = pos_inf<T>();
+        b[0] = b[1] = b[2] = inf; b[3] = b[4] = b[5] = -inf;
+        if (!leaf) { dim_out[node] = 0; split_out[node] = 0; }
+        return;
+    }
     T mn[3], mx[3];
     for (int d = 0; d < 3; ++d) {
         mn[d] = c[d * n + L[d * n + lo]];
         mx[d] = c[d * n + L[d * n + hi]];
     }
-    T *b = box + node * 6;
     b[0] = mn[0]; b[1] = mn[1]; b[2] = mn[2]; b[3] = mx[0]; b[4] = mx[1]; b[5] = mx[2];
-    if (leaf) {
-        bucket_start[j] = (int32_t)lo;
-        if (j == nn - 1) bucket_start[nn] = (int32_t)n;
-        return;
-    }
+    if (leaf) return;
     int d = 0;
     for (int e = 1; e < 3; ++e)
         if (mx[e] - mn[e] > mx[d] - mn[d]) d = e;
     dim_out[node] = (int8_t)d;
-    int64_t m = (lo + hi) >> 1;
-    split_out[node] = c[d * n + L[d * n + m]];
+    split_out[node] = c[d * n + L[d * n + split_rank(s, level, lo, hi)]];
 }
 
-// one thread per list position: the particle at rank p of its node's split-axis list goes left iff p <= m
-__global__ void k_mark_sides(int64_t n, int level, const uint32_t *__restrict__ L, const int8_t *__restrict__ dim,
+// one thread per list position: the particle at rank p of its node's split-axis list goes to the
+// lower child iff p <= split rank
+__global__ void k_mark_sides(TreeShape s, int level, const uint32_t *__restrict__ L, const int8_t *__restrict__ dim,
                              uint8_t *__restrict__ side)
 {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= s.n) return;
     int64_t lo, hi, node;
-    seg_of_pos(n, level, p, lo, hi, node);
+    seg_of_pos(s, level, p, lo, hi, node);
     int d = dim[node];
-    int64_t m = (lo + hi) >> 1;
-    side[L[(int64_t)d * n + p]] = (uint8_t)(p > m);
+    side[L[(int64_t)d * s.n + p]] = (uint8_t)(p > split_rank(s, level, lo, hi));
 }
 
 struct LeftFlag {
@@ -114,17 +159,18 @@ struct LeftFlag {
     __host__ __device__ uint32_t operator()(int64_t i) const { return side[L[i]] ? 0u : 1u; }
 };
 
-// stable partition of all three lists about each node's median, using the global prefix sum S of
-// "goes left" flags over the concatenated lists
-__global__ void k_partition(int64_t n, int level, const uint32_t *__restrict__ L, const uint8_t *__restrict__ side,
+// stable partition of all three lists about each node's split rank, using the global prefix sum S of
+// "goes to the lower child" flags over the concatenated lists
+__global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__ L, const uint8_t *__restrict__ side,
                             const uint32_t *__restrict__ S, uint32_t *__restrict__ Lnew)
 {
+    const int64_t n = s.n;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= 3 * n) return;
     int64_t d = i / n, p = i - d * n;
     int64_t lo, hi, node;
-    seg_of_pos(n, level, p, lo, hi, node);
-    int64_t m = (lo + hi) >> 1;
+    seg_of_pos(s, level, p, lo, hi, node);
+    int64_t m = split_rank(s, level, lo, hi);
     uint32_t id = L[i];
     uint32_t left_before = S[i] - S[d * n + lo];     // modular arithmetic: exact because < 2^32
     int64_t dest = side[id] ? (m + 1) + (p - lo) - (int64_t)left_before : lo + (int64_t)left_before;
@@ -146,16 +192,13 @@ __global__ void k_gather_tree_order(int64_t n, const uint32_t *__restrict__ orde
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 template <typename T, typename K>
-static void build_typed(Tree &t, DevBuf &c, const T *mass)
+static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
 {
     const int64_t n = t.n;
+    const TreeShape shape = t.shape;
+    const int levels = shape.levels;
     cudaStream_t s = t.stream;
     const int BS = 256;
-
-    int levels = 0;
-    while (((n + ((int64_t)1 << levels) - 1) >> levels) > 32) ++levels;
-    t.levels = levels;
-    t.nsplit = (int64_t)1 << levels;
 
     DevBuf La(sizeof(uint32_t) * 3 * n), Lb(sizeof(uint32_t) * 3 * n);
     {
@@ -173,14 +216,14 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass)
                 La.as<uint32_t>() + d * n, n, 0, (int)sizeof(K) * 8, s)));
             g_launches += 4;   // CUB's histogram + onesweep passes (approximate count)
         }
-        PNB_CUDA(cudaStreamSynchronize(s));            // keys/tmp are freed on scope exit
+        PNB_CUDA(cudaStreamSynchronize(s));            // keys/tmp go back to the block cache on scope exit
     }
 
     t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
     t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
     DevBuf dim(sizeof(int8_t) * 2 * t.nsplit), split(sizeof(T) * 2 * t.nsplit);
     DevBuf side(sizeof(uint8_t) * n), S(sizeof(uint32_t) * 3 * n);
-    PNB_CUDA(cudaMemsetAsync(t.box.p, 0, t.box.bytes, s));
+    PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2 * t.nsplit, s));
 
     uint32_t *L = La.as<uint32_t>(), *Ln = Lb.as<uint32_t>();
     size_t scan_bytes = 0;
@@ -193,45 +236,69 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass)
 
     for (int level = 0; level < levels; ++level) {
         int64_t nn = (int64_t)1 << level;
-        PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, n, level, L, c.as<T>(), t.box.as<T>(),
+        PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
                    dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr);
-        PNB_LAUNCH(k_mark_sides, nblk(n, BS), BS, 0, s, n, level, L, dim.as<int8_t>(), side.as<uint8_t>());
+        PNB_LAUNCH(k_mark_sides, nblk(n, BS), BS, 0, s, shape, level, L, dim.as<int8_t>(), side.as<uint8_t>());
         LeftFlag f{L, side.as<uint8_t>()};
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
         PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
         g_launches += 2;
-        PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, n, level, L, side.as<uint8_t>(), S.as<uint32_t>(), Ln);
+        PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, shape, level, L, side.as<uint8_t>(), S.as<uint32_t>(), Ln);
         uint32_t *tmp = L; L = Ln; Ln = tmp;
     }
-    PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, n, levels, L, c.as<T>(), t.box.as<T>(),
+    PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
                dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>());
 
-    // tree-ordered structure of arrays
     t.order.alloc(sizeof(uint32_t) * n);
     PNB_CUDA(cudaMemcpyAsync(t.order.p, L, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
-    t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
-    if (mass) t.mass.alloc(sizeof(T) * n);
-    t.has_mass = mass != nullptr;
-    PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
-               t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
-
+    if (want_soa) {                                    // tree-ordered structure of arrays
+        t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
+        if (mass) t.mass.alloc(sizeof(T) * n);
+        t.has_mass = mass != nullptr;
+        PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
+                   t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
+    }
     T rb[6];
     PNB_CUDA(cudaMemcpyAsync(rb, t.box.as<T>() + 6, sizeof(rb), cudaMemcpyDeviceToHost, s));
     PNB_CUDA(cudaStreamSynchronize(s));
     for (int d = 0; d < 3; ++d) { t.root_min[d] = (double)rb[d]; t.root_max[d] = (double)rb[3 + d]; }
-    // split axes / values are only needed by the reference-layout export; keep them with the tree
     t.split_dim = std::move(dim);
     t.split_val = std::move(split);
 }
 
-void build_tree(Tree &t, DevBuf &cols, const void *mass_dev)
+// packed device tree: 32-particle buckets
+TreeShape packed_shape(int64_t n)
+{
+    TreeShape s;
+    s.n = n; s.packed = 1; s.leafcap = 32; s.levels = 0;
+    const int64_t nb = (n + 31) / 32;
+    while (((int64_t)1 << s.levels) < nb) ++s.levels;
+    return s;
+}
+// the reference's shape for a given leafsize (kd.cpp:98-111)
+TreeShape reference_shape(int64_t n, int leafsize)
+{
+    TreeShape s;
+    s.n = n; s.packed = 0; s.leafcap = leafsize; s.levels = 0;
+    int64_t m = n;
+    while (m > leafsize) { m >>= 1; ++s.levels; }
+    return s;
+}
+
+void build_tree(Tree &t, DevBuf &cols, const void *mass_dev, const TreeShape &shape, bool want_soa)
 {
     if (t.n < 1) throw Error(PNB_ERR_VALUE, "kd-tree needs at least one particle");
     if (t.n >= ((int64_t)1 << 31)) throw Error(PNB_ERR_VALUE, "at most 2^31-1 particles per device tree");
+    t.shape = shape;
+    t.levels = shape.levels;
+    t.nsplit = (int64_t)1 << shape.levels;
     if (t.dtype == PNB_F64)
-        build_typed<double, uint64_t>(t, cols, (const double *)mass_dev);
+        build_typed<double, uint64_t>(t, cols, (const double *)mass_dev, want_soa);
     else
-        build_typed<float, uint32_t>(t, cols, (const float *)mass_dev);
+        build_typed<float, uint32_t>(t, cols, (const float *)mass_dev, want_soa);
 }
+
+// host-side copy of the index arithmetic for export.cu
+void shape_seg_of_node(const TreeShape &s, int level, int64_t j, int64_t &lo, int64_t &hi) { seg_of_node(s, level, j, lo, hi); }
 
 }  // namespace pnb

@@ -27,6 +27,8 @@ local compute goes through a backend object -- ``GpuBackend`` (the C ABI) unless
 from __future__ import annotations
 
 import math
+import os
+import time
 
 import numpy as np
 import torch
@@ -229,7 +231,23 @@ class DistributedKDTree:
     and the halo is complete by construction.
     """
 
+    def _tick(self, name):
+        """Phase timing (PNB_DIST_PROFILE=1): synchronised wall-clock per phase in self.timings (ms)."""
+        if not self._profile:
+            return
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.timings[name] = self.timings.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
     def __init__(self, pos, mass, boxsize=None, group=None, backend=None):
+        self._profile = bool(os.environ.get("PNB_DIST_PROFILE"))
+        self.timings = {}
+        self.dev = pos.device
+        if self._profile and self.dev.type == "cuda":
+            torch.cuda.synchronize()
+        self._t_last = time.perf_counter()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -237,6 +255,7 @@ class DistributedKDTree:
         self.n_in = int(pos.shape[0])
         self.dev, self.dt = pos.device, pos.dtype
         self.domains, periodic = decompose(pos, boxsize, group)
+        self._tick("decompose")
         self.boxsize = float(boxsize) if periodic else None
         self.requested_boxsize = boxsize
         if self.world > 1:
@@ -253,8 +272,10 @@ class DistributedKDTree:
             self.mass = torch.cat(recv_mass)
         else:
             self.pos, self.mass = pos, mass
+        self._tick("route_particles")
         self.n_own = int(self.pos.shape[0])
         self.tree1 = self.backend.make_tree(self.pos, self.mass, self.boxsize)
+        self._tick("build_owned_tree")
         self.tree2 = None
         self._halo_send = None          # per destination rank: indices (into owned) of the particles it needs
         self._k = None
@@ -289,7 +310,9 @@ class DistributedKDTree:
     # -- smoothing lengths + halo construction ---------------------------------------------------------
     def smooth(self, k, kernel_id=0):
         """Smoothing lengths (and, as a by-product, the halo for all later passes with this k)."""
+        self._tick("idle")
         sm = self.tree1.knn_smooth(k, None, kernel_id) if self.n_own >= k else None
+        self._tick("knn_owned")
         self._sm_stage1 = sm
         if self.world == 1:
             if sm is None:
@@ -315,6 +338,7 @@ class DistributedKDTree:
             touch = _box_gap2(fpos, lo, hi, period) <= frad * frad * (1 + 1e-6)
             sends.append(torch.cat([fpos[touch], frad[touch, None]], dim=1))
         balls = _alltoallv(sends, self.group)
+        self._tick("select_and_send_boundary_queries")
         # which of my particles do they need?
         self._halo_send = []
         for r in range(self.world):
@@ -327,11 +351,13 @@ class DistributedKDTree:
         halo_pos = torch.cat(_alltoallv([self.pos[i] for i in self._halo_send], self.group))
         halo_mass = torch.cat(_alltoallv([self.mass[i] for i in self._halo_send], self.group))
         self.n_halo = int(halo_pos.shape[0])
+        self._tick("mark_and_exchange_halo")
         self.stats = {"owned": self.n_own, "boundary_queries": int(fidx.numel()), "halo": self.n_halo}
         # re-search the boundary queries on owned + halo
         self.tree2 = self.backend.make_tree(torch.cat([self.pos, halo_pos]), torch.cat([self.mass, halo_mass]), self.boxsize)
         self._own_mask2 = torch.cat([torch.ones(self.n_own, dtype=torch.bool, device=self.dev),
                                      torch.zeros(self.n_halo, dtype=torch.bool, device=self.dev)])
+        self._tick("build_halo_tree")
         if self.tree2.n < k:
             raise ValueError("Number of smoothing particles exceeds number of particles in tree")
         if fidx.numel() > 0:
@@ -340,6 +366,7 @@ class DistributedKDTree:
             sm2 = self.tree2.knn_smooth(k, mask2, kernel_id)
             sm = sm.clone()
             sm[fidx] = sm2[fidx]
+        self._tick("knn_boundary")
         self._fidx = fidx
         self._sm_own, self._k = sm, k
         return sm
@@ -368,7 +395,10 @@ class DistributedKDTree:
                 rho = rho.clone()
                 rho[self._fidx] = rho2[self._fidx]
         self._rho_own = rho
-        return self._to_origin(sm), self._to_origin(rho)
+        self._tick("density")
+        out = self._to_origin(sm), self._to_origin(rho)
+        self._tick("return_results")
+        return out
 
     def sph_op(self, op, qty, k=None, kernel_id=0):
         """mean | disp | div | curl of `qty` (input order), after smooth_rho(k)."""

@@ -51,23 +51,22 @@ class KDTree:
         self._pos = pos
         self.set_kernel(_config_kernel())
 
-    # -- reference-layout views, materialised on first access --------------------------------
+    # -- reference-layout views, materialised together on first access ------------------------
+    def _materialise(self):
+        if self._kdnodes is None or self._particle_offsets is None:
+            nodes = np.zeros(kdmain.get_node_count(self.kdtree), dtype=KDNode)
+            offsets = np.empty(self.kdtree.n, dtype=np.intp)
+            kdmain.export(self.kdtree, nodes, offsets)
+            self._kdnodes, self._particle_offsets = nodes, offsets
+
     @property
     def particle_offsets(self):
-        if self._particle_offsets is None:
-            from .. import _lib
-            out = np.empty(self.kdtree.n, dtype=np.intp)
-            _lib.check(_lib.lib().pnb_tree_order(self.kdtree.require_built(), out.ctypes.data))
-            self._particle_offsets = out
+        self._materialise()
         return self._particle_offsets
 
     @property
     def kdnodes(self):
-        if self._kdnodes is None:
-            from .. import _lib
-            out = np.zeros(kdmain.get_node_count(self.kdtree), dtype=KDNode)
-            _lib.check(_lib.lib().pnb_tree_export_kdnodes(self.kdtree.require_built(), out.ctypes.data, len(out)))
-            self._kdnodes = out
+        self._materialise()
         return self._kdnodes
 
     def _set_num_threads(self, num_threads):

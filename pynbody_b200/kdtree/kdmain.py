@@ -99,24 +99,30 @@ def _create_device_tree(kd):
 def build(kd, kdnodes, particle_offsets, num_threads=1):
     """build_or_import (kdmain.cpp:250-302) + kdBuildTree (kd.cpp:113-152) on the GPU.
 
-    Fills ``particle_offsets`` (tree order -> file order) and, when the requested leaf size is
-    representable by the device tree (>= 32 particles per leaf), the reference-layout ``kdnodes``.
-    Either may be ``None`` to skip the host copy.
+    Fills ``particle_offsets`` (tree order -> file order) and the reference-layout ``kdnodes``; either
+    may be ``None`` to skip the host copy (the device tree the kernels use is independent of them).
     """
     L = _lib.lib()
     _create_device_tree(kd)
     if particle_offsets is not None:
         if particle_offsets.dtype != np.intp or not particle_offsets.flags.c_contiguous or len(particle_offsets) != kd.n:
             raise ValueError("particle offsets must be a C-contiguous intp array of length N")
-        _lib.check(L.pnb_tree_order(kd.handle, particle_offsets.ctypes.data))
     if kdnodes is not None:
         if kdnodes.dtype.itemsize != KDNode.itemsize or not kdnodes.flags.c_contiguous:
             raise ValueError("kdnodes must be a C-contiguous KDNode array")
         if len(kdnodes) != get_node_count(kd):
             raise ValueError("kdnodes array has the wrong length")
-        rc = L.pnb_tree_export_kdnodes(kd.handle, kdnodes.ctypes.data, len(kdnodes))
-        if rc != _lib.OK and "leafsize" not in L.pnb_last_error().decode():
-            _lib.check(rc)
+    if kdnodes is not None or particle_offsets is not None:
+        export(kd, kdnodes, particle_offsets)
+
+
+def export(kd, kdnodes, particle_offsets):
+    """Fill reference-layout ``kdnodes`` / ``particle_offsets`` (either may be None) from a tree with the
+    reference's shape for ``kd.leafsize``, built on the GPU on demand (pnb_tree_export)."""
+    _lib.check(_lib.lib().pnb_tree_export(kd.require_built(),
+                                          None if kdnodes is None else kdnodes.ctypes.data,
+                                          0 if kdnodes is None else len(kdnodes),
+                                          None if particle_offsets is None else particle_offsets.ctypes.data))
 
 
 def import_prebuilt(kd, kdnodes, particle_offsets, _unused=0):
@@ -278,3 +284,8 @@ def last_launch_count(stage):
 def last_kernel_ms(which):
     """Duration (ms) of the last kNN (0) / gather (1) / render (2) kernel launch on this thread."""
     return _lib.lib().pnb_last_kernel_ms(int(which))
+
+
+def total_launches():
+    """Cumulative kernel launches issued through the library by this thread."""
+    return _lib.lib().pnb_total_launches()

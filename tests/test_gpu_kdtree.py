@@ -66,29 +66,86 @@ def test_library_reports_device():
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097, 100_003])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_tree_invariants(n, dtype):
-    """Buckets partition the particles, hold <= 32 each, and their bounds are tight."""
-    import ctypes as C
+    """Device tree: buckets partition the particles, hold exactly 32 each (the last one the remainder,
+    trailing ones nothing), and their bounds are tight."""
     from pynbody_b200 import _lib
     rng = np.random.default_rng(n)
     pos = rng.normal(size=(n, 3)).astype(dtype)
     kd = _tree(pos, np.ones(n, dtype), None)
-    order = kd.particle_offsets
-    assert np.array_equal(np.sort(order), np.arange(n))
     L = _lib.lib()
     h = kd.kdtree.handle
+    order = np.empty(n, np.int64)
+    _lib.check(L.pnb_tree_order(h, order.ctypes.data))
+    assert np.array_equal(np.sort(order), np.arange(n))
     nb = L.pnb_tree_num_buckets(h)
     start = np.empty(nb + 1, np.int64)
     bounds = np.empty((nb, 6))
     _lib.check(L.pnb_tree_buckets(h, start.ctypes.data, bounds.ctypes.data))
     assert start[0] == 0 and start[-1] == n
     counts = np.diff(start)
-    assert counts.max() <= 32 and counts.min() >= min(n, 1)
-    if nb > 1:
-        assert counts.max() - counts.min() <= 1          # balanced median splits (kd.cpp:176-199)
+    full = n // 32
+    assert np.all(counts[:full] == 32) and counts[full:].sum() == n - 32 * full and nb < 2 * max(1, -(-n // 32))
     for b in range(0, nb, max(1, nb // 50)):
         p = pos[order[start[b]:start[b + 1]]].astype(np.float64)
-        assert np.array_equal(bounds[b, :3], p.min(axis=0))
-        assert np.array_equal(bounds[b, 3:], p.max(axis=0))
+        if len(p):
+            assert np.array_equal(bounds[b, :3], p.min(axis=0))
+            assert np.array_equal(bounds[b, 3:], p.max(axis=0))
+        else:
+            assert np.all(bounds[b, :3] == np.inf) and np.all(bounds[b, 3:] == -np.inf)
+
+
+@pytest.mark.parametrize("n,leafsize,dtype", [(5000, 16, np.float64), (5000, 32, np.float32), (777, 8, np.float64),
+                                              (40, 64, np.float64)])
+def test_serialize_is_a_valid_reference_tree(n, leafsize, dtype):
+    """KDTree.serialize() (kdtree/__init__.py:136-163): reference-layout KDNode records + offsets.
+
+    Checked structurally, and by handing the serialized tree to the REFERENCE's own C++ code
+    (kdmain.import_prebuilt) and letting it smooth with it (the reference's test_kdtree_from_existing_kdtree,
+    tests/kdtree_test.py:284-294)."""
+    from oracle import ref
+    rng = np.random.default_rng(n)
+    pos = rng.normal(1.0, size=(n, 3)).astype(dtype)
+    mass = rng.uniform(size=n).astype(dtype)
+    kd = _tree(pos, mass, None, leafsize=leafsize)
+    leaf, boxsize, nodes, offsets, kernel_id = kd.serialize()
+    assert leaf == leafsize and boxsize is None and kernel_id == 0
+    assert np.array_equal(np.sort(offsets), np.arange(n))
+    nsplit = len(nodes) // 2
+    l = 1
+    m = n
+    while m > leafsize:
+        m >>= 1
+        l <<= 1
+    assert nsplit == l                                                       # kd.cpp:98-111
+    assert nodes["pLower"][1] == 0 and nodes["pUpper"][1] == n - 1
+    for i in range(1, nsplit):
+        lo, hi = nodes["pLower"][i], nodes["pUpper"][i]
+        mid = (lo + hi) // 2
+        assert (nodes["pLower"][2 * i], nodes["pUpper"][2 * i]) == (lo, mid)          # kd.cpp:176-199
+        assert (nodes["pLower"][2 * i + 1], nodes["pUpper"][2 * i + 1]) == (mid + 1, hi)
+        d = nodes["iDim"][i]
+        assert 0 <= d < 3
+        p = pos[offsets[lo:hi + 1]].astype(np.float64)
+        assert np.array_equal(nodes["bnd"]["fMin"][i], p.min(axis=0)) and np.array_equal(nodes["bnd"]["fMax"][i], p.max(axis=0))
+        assert p[:mid - lo + 1, d].max() <= nodes["fSplit"][i] <= p[mid - lo + 1:, d].min()
+    assert np.all(nodes["iDim"][nsplit:] == -1)
+    if ref.available():
+        theirs = ref.RefKDTree(pos, mass, leafsize, None, 1)
+        want = theirs.smooth(min(32, n))
+        kdc = ref.kdmain.init(pos, mass, leafsize)
+        ref.kdmain.import_prebuilt(kdc, nodes, offsets, 0)
+        sm = np.empty(n, dtype)
+        ref.kdmain.set_arrayref(kdc, 0, sm)
+        smx = ref.kdmain.nn_start(kdc, min(32, n), -1.0)
+        ref.kdmain.domain_decomposition(kdc, 1)
+        ref.kdmain.populate(kdc, smx, 1, 0, 0)
+        ref.kdmain.nn_stop(kdc, smx)
+        ref.kdmain.free(kdc)
+        assert np.array_equal(sm, want), "the reference must get its own answers from our serialized tree"
+    # and the round trip through our own deserialize
+    from pynbody_b200.kdtree import KDTree
+    kd2 = KDTree.deserialize(pos, mass, kd.serialize())
+    assert np.array_equal(_smooth(kd2, pos, min(32, n)), _smooth(kd, pos, min(32, n)))
 
 
 @pytest.mark.parametrize("name", list(cases.SMOOTH_CASES))
