@@ -12,25 +12,27 @@
 // own query; survivors (d2 < current k-th distance) are remembered in a 32-bit register mask and
 // then inserted into the lane's private bounded neighbour queue, all lanes inserting together.
 //
-// The queue (the reference's max-heap, pq.h) is a "grouped max-cache": the k distances live in
-// shared memory, lane-interleaved (entry e of lane l at [e*32+l]: conflict-free), split into 8 groups
-// of S = ceil(k/8) slots; the maximum of every group, its slot, and the overall maximum (the current
-// k-th distance) live in registers.  Replacing the current maximum is one store plus one rescan of a
-// single group: S independent shared-memory loads (one latency) instead of the log2(k) dependent
-// load/compare/store rounds of a binary heap sift-down -- the v1 profile (profiles/r1_knn_v1_*)
-// showed that sift-down as 45 % of all issue slots at 9 of 32 lanes active.
+// The queue (the reference's max-heap, pq.h) is a TOURNAMENT TREE per lane in shared memory,
+// lane-interleaved (element e of lane l at [e*32+l]: conflict-free): K2 = 2^ceil(log2 k) leaf slots
+// hold the distances, K2-1 one-byte internal nodes hold the leaf index of the larger child's winner;
+// the root's winner is the current k-th distance and is kept in registers.  Replacing the maximum
+// touches one root-to-leaf path whose addresses depend only on the leaf index, so all sibling loads
+// of the path are issued together (two shared-memory round trips in total) and the rest is a
+// register compare chain: ~65 instructions against ~140 for the grouped max-cache of v2 and ~160 for
+// the binary-heap sift-down of v1, whose log2(k) load->compare->store rounds are serially dependent
+// (profiles/r1_knn_v1_summary.txt, r1_knn_v2_summary.txt).
 #include "traverse.cuh"
 
 namespace pnb {
 
 constexpr int KNN_WARPS = 2;
-constexpr int NGROUP = 8;
+constexpr int MAXLOG = 10;              // k <= 1024
 
 template <typename T>
 struct KnnArgs {
     TreeView<T> tv;
     int k;
-    int S;                  // slots per group, ceil(k / NGROUP)
+    int LOG;                // log2(K2), K2 = leaf slots of the tournament tree
     T *smooth_t;            // [n] tree order
     T *rho_t;               // [n] tree order (FUSE_RHO: all particles have mass `uniform_mass`)
     double uniform_mass;
@@ -40,47 +42,53 @@ struct KnnArgs {
     T *nn_d2;               // [n][k]
 };
 
-template <typename T>
-struct TopK {
-    T gm[NGROUP];           // maximum of each group
-    unsigned long long gp;  // slot (within its group) of each group's maximum, 8 bits per group
-    T top;                  // overall maximum = k-th smallest d2 so far (+inf until k are held, pq.h:185-192)
+// per-lane view of the queue
+template <typename T, typename W_t>
+struct Queue {
+    T *hd;                  // leaves [K2], stride 32
+    W_t *W;                 // internal nodes [K2] (heap order, node 0 unused), stride 32: winner leaf index
+    int32_t *hi;            // neighbour ids [K2] (WITH_IDX)
+    int LOG, K2;
+    T top;                  // value of the root's winner = k-th smallest d2 so far (+inf until k are held)
+    int etop;               // its leaf
 };
 
-// replace the current maximum by (v, id)
-template <typename T, bool WITH_IDX>
-__device__ __forceinline__ void topk_replace_max(TopK<T> &q, T *hd, int32_t *hi, int S, T v, int32_t id)
+// replace the current maximum by (v, id) and replay its path to the root
+// LOGC >= 0: tree depth known at compile time (k <= 32 / 64 / 128: the path is fully unrolled without
+// predicates); LOGC < 0: depth read from the queue (any k <= 1024)
+template <typename T, typename W_t, int LOGC, bool WITH_IDX>
+__device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t id)
 {
-    int g = 0;
+    constexpr int NL = LOGC >= 0 ? LOGC : MAXLOG;
+    const int e = q.etop;
+    q.hd[e * 32] = v;
+    if (WITH_IDX) q.hi[e * 32] = id;
+    const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;      // heap index of the leaf
+    int si[NL > 0 ? NL : 1];
+    T sv[NL > 0 ? NL : 1];
+    // sibling winners along the path: addresses depend only on e, so all loads go out together
+    if (NL > 0) si[0] = e ^ 1;
 #pragma unroll
-    for (int i = NGROUP - 1; i >= 0; --i)
-        if (q.gm[i] == q.top) g = i;
-    const int s = (int)((q.gp >> (8 * g)) & 0xffull);
-    T *grp = hd + (size_t)g * S * 32;
-    grp[s * 32] = v;
-    if (WITH_IDX) hi[(g * S + s) * 32] = id;
-    // rescan the group: S independent loads
-    T m = grp[0];
-    int pos = 0;
-#pragma unroll 4
-    for (int t = 1; t < S; ++t) {
-        T val = grp[t * 32];
-        if (val > m) { m = val; pos = t; }
-    }
+    for (int l = 1; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((node >> l) ^ 1) * 32];
 #pragma unroll
-    for (int i = 0; i < NGROUP; ++i)
-        if (i == g) q.gm[i] = m;
-    q.gp = (q.gp & ~(0xffull << (8 * g))) | ((unsigned long long)pos << (8 * g));
-    T a0 = q.gm[0] > q.gm[1] ? q.gm[0] : q.gm[1], a1 = q.gm[2] > q.gm[3] ? q.gm[2] : q.gm[3];
-    T a2 = q.gm[4] > q.gm[5] ? q.gm[4] : q.gm[5], a3 = q.gm[6] > q.gm[7] ? q.gm[6] : q.gm[7];
-    a0 = a0 > a1 ? a0 : a1;
-    a2 = a2 > a3 ? a2 : a3;
-    q.top = a0 > a2 ? a0 : a2;
+    for (int l = 0; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) sv[l] = q.hd[si[l] * 32];
+    T cv = v;
+    int ce = e;
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) {
+            if (sv[l] > cv) { cv = sv[l]; ce = si[l]; }
+            q.W[(node >> (l + 1)) * 32] = (W_t)ce;
+        }
+    q.top = cv;
+    q.etop = ce;
 }
 
-template <typename T, bool WITH_IDX>
+template <typename T, typename W_t, int LOGC, bool WITH_IDX>
 __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t bucket, bool pass, T sx, T sy, T sz,
-                                                 TopK<T> &q, T *hd, int32_t *hi, int S, T *tile, int lane)
+                                                 Queue<T, W_t> &q, T *tile, int lane)
 {
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -106,31 +114,38 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (d2 < q.top) topk_replace_max<T, WITH_IDX>(q, hd, hi, S, d2, start + j);
+            if (d2 < q.top) queue_replace_max<T, W_t, LOGC, WITH_IDX>(q, d2, start + j);
         }
     }
 }
 
-template <typename T, bool WITH_IDX>
-__host__ __device__ inline size_t knn_smem_per_warp(int S)
+template <typename T, typename W_t, bool WITH_IDX>
+__host__ __device__ inline size_t knn_smem_per_warp(int K2)
 {
-    return (size_t)NGROUP * S * 32 * sizeof(T) + (WITH_IDX ? (size_t)NGROUP * S * 32 * 4 : 0) + 96 * sizeof(T);
+    size_t b = (size_t)K2 * 32 * sizeof(T) + (size_t)K2 * 32 * sizeof(W_t) + (WITH_IDX ? (size_t)K2 * 32 * 4 : 0)
+               + 96 * sizeof(T);
+    return (b + 127) & ~(size_t)127;
 }
 
-template <typename T, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
+template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const TreeView<T> &tv = a.tv;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t bucket = (int64_t)blockIdx.x * KNN_WARPS + wib;
     if (bucket >= tv.nsplit) return;                // whole warp exits together; no block barriers below
-    const int k = a.k, S = a.S, nslot = NGROUP * S;
+    const int k = a.k, LOG = LOGC >= 0 ? LOGC : a.LOG, K2 = 1 << LOG;
 
-    unsigned char *base = smem_raw + knn_smem_per_warp<T, WITH_IDX>(S) * wib;
-    T *hd = reinterpret_cast<T *>(base) + lane;
-    int32_t *hi = WITH_IDX ? reinterpret_cast<int32_t *>(base + (size_t)nslot * 32 * sizeof(T)) + lane : nullptr;
-    T *tile = reinterpret_cast<T *>(base + (size_t)nslot * 32 * sizeof(T) + (WITH_IDX ? (size_t)nslot * 32 * 4 : 0));
+    unsigned char *base = smem_raw + knn_smem_per_warp<T, W_t, WITH_IDX>(K2) * wib;
+    Queue<T, W_t> q;
+    q.LOG = LOG; q.K2 = K2;
+    q.hd = reinterpret_cast<T *>(base) + lane;
+    T *tile = reinterpret_cast<T *>(base + (size_t)K2 * 32 * sizeof(T));
+    unsigned char *after = base + (size_t)K2 * 32 * sizeof(T) + 96 * sizeof(T);
+    q.hi = nullptr;
+    if (WITH_IDX) { q.hi = reinterpret_cast<int32_t *>(after) + lane; after += (size_t)K2 * 32 * 4; }
+    q.W = reinterpret_cast<W_t *>(after) + lane;
 
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -139,20 +154,22 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     T qx = 0, qy = 0, qz = 0;
     if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
 
-    // slots [0,k) start at +inf (replaced first), padding slots [k, 8S) at -inf (never the maximum)
-    for (int e = 0; e < nslot; ++e) {
-        hd[e * 32] = e < k ? Ex<T>::inf() : -Ex<T>::inf();
-        if (WITH_IDX) hi[e * 32] = -1;
+    // leaves [0,k) start at +inf (replaced first), padding leaves [k,K2) at -inf (never a winner while a
+    // real leaf competes); every internal node starts with the leftmost leaf below it as winner
+    for (int e = 0; e < K2; ++e) {
+        q.hd[e * 32] = e < k ? Ex<T>::inf() : -Ex<T>::inf();
+        if (WITH_IDX) q.hi[e * 32] = -1;
     }
-    TopK<T> q;
-#pragma unroll
-    for (int g = 0; g < NGROUP; ++g) q.gm[g] = (g * S < k) ? Ex<T>::inf() : -Ex<T>::inf();
-    q.gp = 0;
+    for (int node = 1; node < K2; ++node) {
+        int lv = 31 - __clz(node);                  // depth of the node; its sub-tree spans K2 >> lv leaves
+        q.W[node * 32] = (W_t)((node - (1 << lv)) << (LOG - lv));
+    }
+    q.etop = 0;
     q.top = active ? Ex<T>::inf() : (T)-1;          // idle lanes never match
     const T L = tv.period;
 
     // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
-    knn_visit_bucket<T, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, hd, hi, S, tile, lane);
+    knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane);
 
     // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
     int64_t cell = tv.nsplit + bucket;
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
             bool pass = gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();   // (empty nodes: inverted bounds)
             if (__any_sync(FULL, pass)) {
                 if (cp < tv.nsplit) { cp = 2 * cp; continue; }
-                knn_visit_bucket<T, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, hd, hi, S, tile, lane);
+                knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane);
             }
             cp = next_node(cp);
             if (cp == stop) break;
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         const T m = (T)a.uniform_mass;
         T rho = 0;
         for (int e = 0; e < k; ++e) {
-            T q2 = hd[e * 32] * ih2;
+            T q2 = q.hd[e * 32] * ih2;
             T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)q2);
             w *= norm;
             rho += w * m;
@@ -198,8 +215,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     if (WITH_IDX && a.nn_idx) {
         const int64_t row = (int64_t)tv.order[p] * k;
         for (int e = 0; e < k; ++e) {
-            a.nn_idx[row + e] = (int64_t)tv.order[hi[e * 32]];
-            a.nn_d2[row + e] = hd[e * 32];
+            a.nn_idx[row + e] = (int64_t)tv.order[q.hi[e * 32]];
+            a.nn_d2[row + e] = q.hd[e * 32];
         }
     }
 }
@@ -213,24 +230,32 @@ KernelParams make_kernel_params(int kernel_id, int k)
     return kp;
 }
 
-template <typename T, bool WITH_IDX, bool FUSE_RHO>
+template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO>
 static void launch_knn(Tree &t, KnnArgs<T> &a)
 {
-    const size_t smem = knn_smem_per_warp<T, WITH_IDX>(a.S) * KNN_WARPS;
-    if (smem > 227 * 1024 || a.S > 255)
+    const size_t smem = knn_smem_per_warp<T, W_t, WITH_IDX>(1 << a.LOG) * KNN_WARPS;
+    if (smem > 227 * 1024)
         throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues");
     const unsigned grid = (unsigned)((t.nsplit + KNN_WARPS - 1) / KNN_WARPS);
     KernelTimer timer(0, t.stream);
     if (a.tv.periodic) {
-        auto kern = k_knn<T, WITH_IDX, FUSE_RHO, true>;
+        auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, true>;
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PNB_LAUNCH(kern, grid, KNN_WARPS * 32, smem, t.stream, a);
     } else {
-        auto kern = k_knn<T, WITH_IDX, FUSE_RHO, false>;
+        auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, false>;
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PNB_LAUNCH(kern, grid, KNN_WARPS * 32, smem, t.stream, a);
     }
     timer.stop();
+}
+
+template <typename T, typename W_t, int LOGC>
+static void dispatch_knn(Tree &t, KnnArgs<T> &a, bool with_idx, bool fuse_rho)
+{
+    if (with_idx) launch_knn<T, W_t, LOGC, true, false>(t, a);
+    else if (fuse_rho) launch_knn<T, W_t, LOGC, false, true>(t, a);
+    else launch_knn<T, W_t, LOGC, false, false>(t, a);
 }
 
 template <typename T>
@@ -242,7 +267,9 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     KnnArgs<T> a;
     a.tv = make_view<T>(t, period);
     a.k = k;
-    a.S = (k + NGROUP - 1) / NGROUP;
+    a.LOG = 0;
+    while ((1 << a.LOG) < k) ++a.LOG;
+    if (a.LOG > MAXLOG) throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large (at most 1024)");
     a.smooth_t = t.smooth_t.as<T>();
     a.rho_t = t.rho_t.as<T>();
     a.uniform_mass = t.uniform_mass;
@@ -250,9 +277,15 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     a.wendland_self = kp.wendland_self;
     a.nn_idx = nn_idx_dev;
     a.nn_d2 = (T *)nn_d2_dev;
-    if (nn_idx_dev) launch_knn<T, true, false>(t, a);
-    else if (fuse_rho) launch_knn<T, false, true>(t, a);
-    else launch_knn<T, false, false>(t, a);
+    const bool idx = nn_idx_dev != nullptr;
+    switch (a.LOG) {                                   // the usual neighbour counts get fully unrolled queues
+    case 5: dispatch_knn<T, uint8_t, 5>(t, a, idx, fuse_rho); break;
+    case 6: dispatch_knn<T, uint8_t, 6>(t, a, idx, fuse_rho); break;
+    case 7: dispatch_knn<T, uint8_t, 7>(t, a, idx, fuse_rho); break;
+    default:
+        if (a.LOG <= 8) dispatch_knn<T, uint8_t, -1>(t, a, idx, fuse_rho);
+        else dispatch_knn<T, uint16_t, -1>(t, a, idx, fuse_rho);
+    }
 }
 
 void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp, int64_t *nn_idx_dev, void *nn_d2_dev)
