@@ -17,18 +17,6 @@
 namespace pnb {
 
 template <typename T, bool PERIODIC>
-__device__ __forceinline__ T nearest_image_delta(T c, T x, T L)
-{
-    T d = Ex<T>::sub(c, x);
-    if (PERIODIC) {
-        T dp = Ex<T>::sub(Ex<T>::add(c, L), x), dm = Ex<T>::sub(Ex<T>::sub(c, L), x);
-        if (fabs(dp) < fabs(d)) d = dp;
-        if (fabs(dm) < fabs(d)) d = dm;
-    }
-    return d;
-}
-
-template <typename T, bool PERIODIC>
 __global__ void k_ball(TreeView<T> tv, T cx, T cy, T cz, T r2, uint32_t *__restrict__ out,
                        unsigned long long *__restrict__ counter, unsigned long long cap)
 {
@@ -43,10 +31,8 @@ __global__ void k_ball(TreeView<T> tv, T cx, T cy, T cz, T r2, uint32_t *__restr
     const int cnt = tv.bucket_start[bucket + 1] - start;
     bool in = false;
     if (lane < cnt) {
-        T dx = nearest_image_delta<T, PERIODIC>(cx, tv.x[start + lane], tv.period);
-        T dy = nearest_image_delta<T, PERIODIC>(cy, tv.y[start + lane], tv.period);
-        T dz = nearest_image_delta<T, PERIODIC>(cz, tv.z[start + lane], tv.period);
-        T d2 = Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
+        T d2 = PERIODIC ? dist2_nearest<T>(cx, cy, cz, tv.x[start + lane], tv.y[start + lane], tv.z[start + lane], tv.period)
+                        : dist2<T>(cx, cy, cz, tv.x[start + lane], tv.y[start + lane], tv.z[start + lane]);
         in = d2 <= r2;                                      // smooth.h:310
     }
     unsigned m = __ballot_sync(FULL, in);
@@ -128,8 +114,10 @@ __global__ void __launch_bounds__(128) k_mark_in_balls(TreeView<T> tv, const T *
             }
             __syncwarp();
             unsigned mask = 0;
+            const bool wide = PERIODIC && __any_sync(FULL, pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, tv.period));
             for (int j = 0; j < cnt; ++j) {
-                T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+                T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
+                            : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
                 mask |= (unsigned)(d2 <= r2) << j;
             }
             if (!pass) mask = 0;

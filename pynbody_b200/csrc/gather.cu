@@ -79,10 +79,19 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
             }
             __syncwarp();
             unsigned mask = 0;
+            // some lane's shift is not the nearest image for every particle of this cell: image per particle
+            const bool wide = PERIODIC && __any_sync(FULL, pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L));
+            if (!wide) {
 #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                T d2 = dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
-                mask |= (unsigned)(d2 <= ball2) << j;          // smooth.h:310 (non-strict)
+                for (int j = 0; j < cnt; ++j) {
+                    T d2 = dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
+                    mask |= (unsigned)(d2 <= ball2) << j;      // smooth.h:310 (non-strict)
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    T d2 = dist2_nearest<T>(qx, qy, qz, tile.x[j], tile.y[j], tile.z[j], L);
+                    mask |= (unsigned)(d2 <= ball2) << j;
+                }
             }
             if (!pass) mask = 0;
             if (PASS == 0) count += __popc(mask);
@@ -90,7 +99,8 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 if (mask) {
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const T d2 = dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
+                    const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile.x[j], tile.y[j], tile.z[j], L)
+                                      : dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
                     const double mj = (double)tile.m[j];
                     if (OP == OP_RHO) {
                         // rho_i += (W * norm) * m_j, accumulated in T by the caller's cast (smooth.h:640-645)

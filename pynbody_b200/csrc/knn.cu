@@ -88,7 +88,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t
 
 template <typename T, typename W_t, int LOGC, bool WITH_IDX>
 __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t bucket, bool pass, T sx, T sy, T sz,
-                                                 Queue<T, W_t> &q, T *tile, int lane)
+                                                 Queue<T, W_t> &q, T *tile, int lane, bool wide, T qx, T qy, T qz)
 {
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -102,10 +102,17 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
     // phase A: all candidates against this lane's query, branch-free
     unsigned mask = 0;
     const T top0 = q.top;
+    if (!wide) {
 #pragma unroll 4
-    for (int j = 0; j < cnt; ++j) {
-        T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-        mask |= (unsigned)(d2 < top0) << j;
+        for (int j = 0; j < cnt; ++j) {
+            T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+            mask |= (unsigned)(d2 < top0) << j;
+        }
+    } else {                                        // cell wider than half the period: image per particle
+        for (int j = 0; j < cnt; ++j) {
+            T d2 = dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period);
+            mask |= (unsigned)(d2 < top0) << j;
+        }
     }
     if (!pass) mask = 0;
     // phase B: all lanes insert their survivors together
@@ -113,7 +120,8 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
         if (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            const T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+            const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
+                              : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
             if (d2 < q.top) queue_replace_max<T, W_t, LOGC, WITH_IDX>(q, d2, start + j);
         }
     }
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TreeView<T> &tv = a.tv;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t bucket = (int64_t)blockIdx.x * KNN_WARPS + wib;
+    const int64_t bucket = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (bucket >= tv.nsplit) return;                // whole warp exits together; no block barriers below
     const int k = a.k, LOG = LOGC >= 0 ? LOGC : a.LOG, K2 = 1 << LOG;
 
@@ -169,7 +177,11 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     const T L = tv.period;
 
     // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
-    knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane);
+    {
+        const bool amb = active && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, tv.nsplit + bucket), qx, qy, qz, L);
+        knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane,
+                                                 PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+    }
 
     // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
     int64_t cell = tv.nsplit + bucket;
@@ -183,7 +195,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
             bool pass = gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();   // (empty nodes: inverted bounds)
             if (__any_sync(FULL, pass)) {
                 if (cp < tv.nsplit) { cp = 2 * cp; continue; }
-                knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane);
+                const bool amb = pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L);
+                knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
+                                                         PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
             }
             cp = next_node(cp);
             if (cp == stop) break;
@@ -233,19 +247,23 @@ KernelParams make_kernel_params(int kernel_id, int k)
 template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO>
 static void launch_knn(Tree &t, KnnArgs<T> &a)
 {
-    const size_t smem = knn_smem_per_warp<T, W_t, WITH_IDX>(1 << a.LOG) * KNN_WARPS;
+    // two warps per block unless one warp's queues already need more than half the shared memory
+    const size_t per_warp = knn_smem_per_warp<T, W_t, WITH_IDX>(1 << a.LOG);
+    const int warps = per_warp * KNN_WARPS <= 227 * 1024 ? KNN_WARPS : 1;
+    const size_t smem = per_warp * warps;
     if (smem > 227 * 1024)
-        throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues");
-    const unsigned grid = (unsigned)((t.nsplit + KNN_WARPS - 1) / KNN_WARPS);
+        throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues "
+                                   "(at most 512 for float64 positions, 1024 for float32)");
+    const unsigned grid = (unsigned)((t.nsplit + warps - 1) / warps);
     KernelTimer timer(0, t.stream);
     if (a.tv.periodic) {
         auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, true>;
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH(kern, grid, KNN_WARPS * 32, smem, t.stream, a);
+        PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
     } else {
         auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, false>;
         PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH(kern, grid, KNN_WARPS * 32, smem, t.stream, a);
+        PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
     }
     timer.stop();
 }

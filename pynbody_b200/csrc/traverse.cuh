@@ -39,6 +39,25 @@ __device__ __forceinline__ T dist2(T sx, T sy, T sz, T x, T y, T z)
     return Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
 }
 
+// Separation along one axis with the query image chosen PER PARTICLE: the nearest of q, fl(q+L), fl(q-L).
+// Same arithmetic as the per-cell shift wherever the cell is small against the box; used for cells that
+// span more than half the period (tiny particle sets) where no single shift serves the whole cell.
+template <typename T>
+__device__ __forceinline__ T nearest_image_delta(T q, T x, T L)
+{
+    T d = Ex<T>::sub(q, x);
+    T dp = Ex<T>::sub(Ex<T>::add(q, L), x), dm = Ex<T>::sub(Ex<T>::sub(q, L), x);
+    if (fabs(dp) < fabs(d)) d = dp;
+    if (fabs(dm) < fabs(d)) d = dm;
+    return d;
+}
+template <typename T>
+__device__ __forceinline__ T dist2_nearest(T qx, T qy, T qz, T x, T y, T z, T L)
+{
+    T dx = nearest_image_delta<T>(qx, x, L), dy = nearest_image_delta<T>(qy, y, L), dz = nearest_image_delta<T>(qz, z, L);
+    return Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
+}
+
 // read-only view of the device tree
 template <typename T>
 struct TreeView {
@@ -116,6 +135,18 @@ __device__ __forceinline__ T box_gap2(const Box6<T> &b, T qx, T qy, T qz, T L, T
     g += axis_gap2<T, PERIODIC>(qy, b.mn[1], b.mx[1], L, sy);
     g += axis_gap2<T, PERIODIC>(qz, b.mn[2], b.mx[2], L, sz);
     return g;
+}
+
+// The per-cell shift (sx,sy,sz) is the nearest image for EVERY particle of the cell iff no particle of the
+// cell is further than half a period from it along any axis.  Otherwise (tiny particle sets, or balls
+// approaching half the box) the image has to be chosen per particle.
+template <typename T, bool PERIODIC>
+__device__ __forceinline__ bool shift_is_ambiguous(const Box6<T> &b, T sx, T sy, T sz, T L)
+{
+    if (!PERIODIC) return false;
+    const T half = (T)0.5 * L;
+    return fmax(sx - b.mn[0], b.mx[0] - sx) > half || fmax(sy - b.mn[1], b.mx[1] - sy) > half
+           || fmax(sz - b.mn[2], b.mx[2] - sz) > half;
 }
 
 // in-order successor in the implicit tree when the sub-tree under `cp` is finished (kd.h:17-23)

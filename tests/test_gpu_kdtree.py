@@ -344,3 +344,68 @@ def test_device_resident_inputs():
     torch.cuda.synchronize()
     assert np.array_equal(sm.cpu().numpy(), sm_h)
     assert np.array_equal(rho.cpu().numpy(), rho_h)
+
+
+def _bruteforce_smooth(pos, k, L):
+    """Exact minimum-image kNN with the library's arithmetic: per axis the nearest of q, fl(q+L), fl(q-L);
+    d2 = (dx*dx + dy*dy) + dz*dz in the array dtype; h = 0.5*sqrt(d2_k)."""
+    dt = pos.dtype.type
+    q = pos[:, None, :]
+    x = pos[None, :, :]
+    d = q - x
+    if L is not None:
+        dp = (q + dt(L)) - x
+        dm = (q - dt(L)) - x
+        d = np.where(np.abs(dp) < np.abs(d), dp, d)
+        d = np.where(np.abs(dm) < np.abs(d), dm, d)
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    kth = np.sort(d2, axis=1)[:, k - 1]
+    return (dt(0.5) * np.sqrt(kth)).astype(pos.dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_small_and_ragged_cases(dtype):
+    """Ragged sizes around the bucket size, k from 1 to N, periodic and open, every reduction.
+
+    Open boxes: against the oracle.  Tiny periodic boxes: the reference's per-cell image choice makes its
+    answer depend on its own tree there, so the bar is the exact minimum-image
+    neighbour search (cells wider than half the box switch to a per-particle image)."""
+    from oracle import oracle
+    rng = np.random.default_rng(77)
+    for n in (2, 5, 31, 32, 33, 64, 65, 97, 300):
+        pos = rng.uniform(0.0, 1.0, (n, 3)).astype(dtype)
+        mass = rng.uniform(0.5, 1.5, n).astype(dtype)
+        vel = rng.normal(size=(n, 3)).astype(dtype)
+        for k in sorted({1, 2, min(n, 7), min(n, 40), n}):
+            kd = _tree(pos, mass, 1.0, 1)
+            assert np.array_equal(_smooth(kd, pos, k), _bruteforce_smooth(pos, k, 1.0)), (n, k, "periodic")
+            ref = oracle.OracleKDTree(pos, mass, 16, None, 1, 1)
+            kd = _tree(pos, mass, None, 1)
+            sm_ref = ref.smooth(k)
+            sm = _smooth(kd, pos, k)
+            assert np.array_equal(sm, sm_ref), (n, k, "open")
+            assert np.array_equal(sm, _bruteforce_smooth(pos, k, None))
+            if k < 2:
+                continue            # h = 0: densities are inf/nan in both implementations
+            rho_ref = ref.rho(k)
+            rho = _rho(kd, pos, mass, sm, k)
+            assert_close(rho, rho_ref, dtype, f"rho n={n} k={k}")
+            if k < 7:
+                continue            # a couple of neighbours sitting at the kernel edge: sums are rounding noise
+            kd.set_array_ref("rho", rho_ref)
+            assert_close(kd.sph_mean(vel, k), ref.qty_op("mean", vel, k), dtype, "mean")
+            assert_close(kd.sph_divergence(vel, k), ref.qty_op("div", vel, k), dtype, "div")
+
+
+def test_large_k():
+    """k well above the bucket size (generic-depth queue path) and the k limit."""
+    from oracle import oracle
+    pos, vel, mass = synth.uniform_box(20_000, 21, np.float64)
+    ref = oracle.OracleKDTree(pos, mass, 16, 1.0, None, 0)
+    kd = _tree(pos, mass, 1.0)
+    for k in (200, 400):
+        assert np.array_equal(_smooth(kd, pos, k), ref.smooth(k)), k
+    sm = np.empty(len(pos))
+    kd.set_array_ref("smooth", sm)
+    with pytest.raises(ValueError, match="too large"):
+        kd.populate("hsm", 5000)
