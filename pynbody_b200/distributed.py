@@ -114,22 +114,21 @@ class GpuBackend:
 # domain decomposition
 # ------------------------------------------------------------------------------------------------
 def _bisect(sample, lo, hi, ranks, out):
-    """Recursive coordinate bisection of box [lo,hi) among `ranks` using the coordinate sample."""
+    """Recursive coordinate bisection of box [lo,hi) among `ranks` using the coordinate sample
+    (numpy arrays on the host: a few hundred thousand points, selection not sorting)."""
     if len(ranks) == 1:
-        out[ranks[0]] = (lo.clone(), hi.clone())
+        out[ranks[0]] = (lo.copy(), hi.copy())
         return
     nleft = len(ranks) // 2
-    if sample.shape[0] > 0:
-        ext = sample.max(dim=0).values - sample.min(dim=0).values
+    ext = sample.max(axis=0) - sample.min(axis=0) if len(sample) else hi - lo
+    axis = int(np.argmax(ext))
+    if len(sample) > 1:
+        kth = min(len(sample) - 1, max(1, int(round(len(sample) * nleft / len(ranks)))))
+        q = np.partition(sample[:, axis], kth)[kth]
     else:
-        ext = hi - lo
-    axis = int(torch.argmax(ext))
-    if sample.shape[0] > 1:
-        q = torch.quantile(sample[:, axis].double(), nleft / len(ranks)).to(sample.dtype)
-    else:
-        q = (lo[axis] + hi[axis]) / 2 if torch.isfinite(lo[axis] + hi[axis]) else torch.zeros((), dtype=lo.dtype)
+        q = 0.5 * (lo[axis] + hi[axis]) if np.isfinite(lo[axis] + hi[axis]) else sample.dtype.type(0)
     left = sample[:, axis] < q
-    hi_l, lo_r = hi.clone(), lo.clone()
+    hi_l, lo_r = hi.copy(), lo.copy()
     hi_l[axis] = q
     lo_r[axis] = q
     _bisect(sample[left], lo, hi_l, ranks[:nleft], out)
@@ -161,17 +160,18 @@ def decompose(pos, boxsize, group=None, sample_per_rank=32768, seed=0):
         samp = torch.cat(allsamp)
         dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    samp = samp[~torch.isnan(samp[:, 0])].cpu()
-    mn, mx = mn.cpu(), mx.cpu()
+    samp = samp.cpu().numpy()
+    samp = samp[~np.isnan(samp[:, 0])]
+    mn, mx = mn.cpu().numpy(), mx.cpu().numpy()
     periodic = boxsize is not None and boxsize > 0 and bool(((mx - mn) <= boxsize).all())
     if periodic:
-        lo, hi = mn.clone(), mn + boxsize
+        lo, hi = mn.copy(), mn + samp.dtype.type(boxsize)
     else:
-        lo = torch.full((3,), float("-inf"), dtype=dt)
-        hi = torch.full((3,), float("inf"), dtype=dt)
+        lo = np.full(3, -np.inf, dtype=samp.dtype)
+        hi = np.full(3, np.inf, dtype=samp.dtype)
     out = [None] * world
     _bisect(samp, lo, hi, list(range(world)), out)
-    return out, periodic
+    return [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out], periodic
 
 
 def owner_of(pos, domains):
@@ -353,23 +353,38 @@ class DistributedKDTree:
         self.n_halo = int(halo_pos.shape[0])
         self._tick("mark_and_exchange_halo")
         self.stats = {"owned": self.n_own, "boundary_queries": int(fidx.numel()), "halo": self.n_halo}
-        # re-search the boundary queries on owned + halo
-        self.tree2 = self.backend.make_tree(torch.cat([self.pos, halo_pos]), torch.cat([self.mass, halo_mass]), self.boxsize)
-        self._own_mask2 = torch.cat([torch.ones(self.n_own, dtype=torch.bool, device=self.dev),
-                                     torch.zeros(self.n_halo, dtype=torch.bool, device=self.dev)])
-        self._tick("build_halo_tree")
-        if self.tree2.n < k:
-            raise ValueError("Number of smoothing particles exceeds number of particles in tree")
+        # re-search the boundary queries on (owned particles inside some boundary ball) + halo: everything a
+        # boundary query can reach, and nothing else -- the second tree is a few per cent of the first
+        self._near = torch.nonzero(self.tree1.mark_in_balls(fpos, frad)).squeeze(1) if fidx.numel() else fidx
+        self.n_near = int(self._near.shape[0])
+        self._f2 = torch.searchsorted(self._near, fidx)            # boundary queries' positions in tree2
+        self.stats["near"] = self.n_near
         if fidx.numel() > 0:
-            mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
-            mask2[fidx] = True
-            sm2 = self.tree2.knn_smooth(k, mask2, kernel_id)
+            self.tree2 = self.backend.make_tree(torch.cat([self.pos[self._near], halo_pos]),
+                                                torch.cat([self.mass[self._near], halo_mass]), self.boxsize)
+            self._tick("build_halo_tree")
+            if self.tree2.n < k:
+                raise ValueError("Number of smoothing particles exceeds number of particles in tree")
+            self._mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
+            self._mask2[self._f2] = True
+            sm2 = self.tree2.knn_smooth(k, self._mask2, kernel_id)
             sm = sm.clone()
-            sm[fidx] = sm2[fidx]
+            sm[fidx] = sm2[self._f2]
         self._tick("knn_boundary")
         self._fidx = fidx
+        self._interior = ~flagged
         self._sm_own, self._k = sm, k
         return sm
+
+    def _tree2_values(self, owned_values, halo_fill=None):
+        """Per-particle values in tree2's order: owned particles near the boundary, then the halo (halo
+        exchange #2 unless a constant fill is enough)."""
+        near = owned_values[self._near]
+        if halo_fill is not None:
+            halo = torch.full((self.n_halo,) + tuple(near.shape[1:]), halo_fill, dtype=near.dtype, device=self.dev)
+        else:
+            halo = self._halo_values(owned_values)
+        return torch.cat([near, halo])
 
     def _halo_values(self, owned_values):
         """Halo exchange #2: per-particle values of the halo particles, in tree2's halo order."""
@@ -388,12 +403,9 @@ class DistributedKDTree:
             else:
                 rho = torch.zeros(self.n_own, dtype=self.dt, device=self.dev)
             if self._fidx.numel() > 0:
-                mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
-                mask2[self._fidx] = True
-                sm_all = torch.cat([sm, torch.ones(self.n_halo, dtype=self.dt, device=self.dev)])
-                rho2 = self.tree2.density(sm_all, k, kernel_id, mask2)
+                rho2 = self.tree2.density(self._tree2_values(sm, 1.0), k, kernel_id, self._mask2)
                 rho = rho.clone()
-                rho[self._fidx] = rho2[self._fidx]
+                rho[self._fidx] = rho2[self._f2]
         self._rho_own = rho
         self._tick("density")
         out = self._to_origin(sm), self._to_origin(rho)
@@ -407,11 +419,13 @@ class DistributedKDTree:
         if self.world == 1:
             out = self.tree1.reduce(op, self._sm_own, self._rho_own, q_own, k, kernel_id)
         else:
-            ones = torch.ones(self.n_halo, dtype=self.dt, device=self.dev)
-            sm_all = torch.cat([self._sm_own, ones])
-            rho_all = torch.cat([self._rho_own, self._halo_values(self._rho_own)])
-            q_all = torch.cat([q_own, self._halo_values(q_own)])
-            out = self.tree2.reduce(op, sm_all, rho_all, q_all, k, kernel_id, self._own_mask2)[: self.n_own]
+            # interior queries see only owned particles; boundary queries run on tree2 with the halo's rho / qty
+            out = self.tree1.reduce(op, self._sm_own, self._rho_own, q_own, k, kernel_id, self._interior)
+            if self._fidx.numel() > 0:
+                out2 = self.tree2.reduce(op, self._tree2_values(self._sm_own, 1.0), self._tree2_values(self._rho_own),
+                                         self._tree2_values(q_own), k, kernel_id, self._mask2)
+                out = out.clone()
+                out[self._fidx] = out2[self._f2]
         if out.dim() == 2 and op in ("disp", "div"):
             out = out[:, 0]
         return self._to_origin(out)

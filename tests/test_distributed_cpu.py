@@ -101,7 +101,8 @@ def test_decompose_is_balanced_and_tiles_the_box():
     # bisection of a sample into 8 boxes: disjoint, covering, balanced
     from pynbody_b200.distributed import _bisect
     out = [None] * 8
-    _bisect(tp, torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64), list(range(8)), out)
+    _bisect(pos, np.zeros(3), np.ones(3), list(range(8)), out)
+    out = [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out]
     owner = owner_of(tp, out)
     counts = torch.bincount(owner, minlength=8)
     assert counts.sum() == len(pos) and counts.min() > 0.9 * len(pos) / 8 and counts.max() < 1.1 * len(pos) / 8
