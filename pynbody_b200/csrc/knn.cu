@@ -11,16 +11,22 @@
 // staged in shared memory (3 coalesced lines) and every lane measures all 32 candidates against its
 // own query; survivors (d2 < current k-th distance) are remembered in a 32-bit register mask and
 // then inserted into the lane's private bounded neighbour queue, all lanes inserting together.
+// The kernel is persistent: warps take buckets in tree order from a global counter.
 //
 // The queue (the reference's max-heap, pq.h) is a TOURNAMENT TREE per lane in shared memory,
 // lane-interleaved (element e of lane l at [e*32+l]: conflict-free): K2 = 2^ceil(log2 k) leaf slots
-// hold the distances, K2-1 one-byte internal nodes hold the leaf index of the larger child's winner;
-// the root's winner is the current k-th distance and is kept in registers.  Replacing the maximum
-// touches one root-to-leaf path whose addresses depend only on the leaf index, so all sibling loads
-// of the path are issued together (two shared-memory round trips in total) and the rest is a
-// register compare chain: ~65 instructions against ~140 for the grouped max-cache of v2 and ~160 for
-// the binary-heap sift-down of v1, whose log2(k) load->compare->store rounds are serially dependent
-// (profiles/r1_knn_v1_summary.txt, r1_knn_v2_summary.txt).
+// hold the keys, K2-1 one-byte internal nodes hold the leaf index of the larger child's winner; the
+// root's winner is the current k-th distance and is kept in registers.  Replacing the maximum touches
+// one root-to-leaf path whose addresses depend only on the leaf index, so all sibling loads of the path
+// are issued together (two shared-memory round trips) and the rest is a register compare chain
+// (profiles/r1_knn_v1_summary.txt, r1_knn_v2_summary.txt for the binary heap / grouped max-cache it
+// replaced).
+//
+// float64 positions: shared memory, not arithmetic, bounds the number of resident warps, and latency
+// hiding is what the kernel lives on.  The queue therefore keeps only the HIGH 32 bits of each d2 in
+// shared memory (non-negative doubles order like their bit patterns); the low words sit in an
+// L2-resident scratch array in global memory and are read only for the new maximum and to break ties
+// between equal high words.  Every ordering decision is still made on the exact 64-bit value.
 #include "traverse.cuh"
 
 namespace pnb {
@@ -40,24 +46,63 @@ struct KnnArgs {
     double wendland_self;
     int64_t *nn_idx;        // [n][k] file-order rows, or null
     T *nn_d2;               // [n][k]
+    unsigned long long *next_bucket;   // work counter
+    uint32_t *lo_scratch;   // [resident warps][K2][32] low words of the queued d2 (float64 only)
 };
+
+// key held in shared memory for a queued distance
+template <typename T> struct KeyOf { typedef T type; };
+template <> struct KeyOf<double> { typedef uint32_t type; };
 
 // per-lane view of the queue
 template <typename T, typename W_t>
 struct Queue {
-    T *hd;                  // leaves [K2], stride 32
+    typedef typename KeyOf<T>::type Key;
+    Key *hd;                // leaves [K2], stride 32
+    uint32_t *lo;           // low words [K2], stride 32, global memory (float64)
     W_t *W;                 // internal nodes [K2] (heap order, node 0 unused), stride 32: winner leaf index
     int32_t *hi;            // neighbour ids [K2] (WITH_IDX)
     int LOG, K2;
-    T top;                  // value of the root's winner = k-th smallest d2 so far (+inf until k are held)
-    int etop;               // its leaf
+    T top;                  // float: the root winner's value = k-th smallest d2 so far.  double: an UPPER BOUND of it
+                            // (exact high word, low word all ones) -- the exact low word is fetched only on demand
+    uint32_t top_hi, top_lo;  // double: exact high word; low word if lo_known
+    bool lo_known;
+    int etop;               // the root winner's leaf
 };
+
+// is d2 strictly below the current k-th distance?  (exact)
+template <typename W_t>
+__device__ __forceinline__ bool below_top(Queue<float, W_t> &q, float d2) { return d2 < q.top; }
+template <typename W_t>
+__device__ __forceinline__ bool below_top(Queue<double, W_t> &q, double d2)
+{
+    const uint32_t h = (uint32_t)__double2hiint(d2);
+    if (h != q.top_hi) return h < q.top_hi;         // non-negative doubles order like their bit patterns
+    if (!q.lo_known) { q.top_lo = q.lo[q.etop * 32]; q.lo_known = true; }   // equal high words: rare
+    return (uint32_t)__double2loint(d2) < q.top_lo;
+}
+template <typename W_t>
+__device__ __forceinline__ float top_exact(Queue<float, W_t> &q) { return q.top; }
+template <typename W_t>
+__device__ __forceinline__ double top_exact(Queue<double, W_t> &q)
+{
+    if (!q.lo_known) { q.top_lo = q.lo[q.etop * 32]; q.lo_known = true; }
+    return __hiloint2double((int)q.top_hi, (int)q.top_lo);
+}
+
+__device__ __forceinline__ float queue_value(const Queue<float, uint8_t> &q, int e) { return q.hd[e * 32]; }
+__device__ __forceinline__ float queue_value(const Queue<float, uint16_t> &q, int e) { return q.hd[e * 32]; }
+template <typename W_t>
+__device__ __forceinline__ double queue_value(const Queue<double, W_t> &q, int e)
+{
+    return __hiloint2double((int)q.hd[e * 32], (int)q.lo[e * 32]);
+}
 
 // replace the current maximum by (v, id) and replay its path to the root
 // LOGC >= 0: tree depth known at compile time (k <= 32 / 64 / 128: the path is fully unrolled without
 // predicates); LOGC < 0: depth read from the queue (any k <= 1024)
-template <typename T, typename W_t, int LOGC, bool WITH_IDX>
-__device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t id)
+template <typename W_t, int LOGC, bool WITH_IDX>
+__device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v, int32_t id)
 {
     constexpr int NL = LOGC >= 0 ? LOGC : MAXLOG;
     const int e = q.etop;
@@ -65,7 +110,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t
     if (WITH_IDX) q.hi[e * 32] = id;
     const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;      // heap index of the leaf
     int si[NL > 0 ? NL : 1];
-    T sv[NL > 0 ? NL : 1];
+    float sv[NL > 0 ? NL : 1];
     // sibling winners along the path: addresses depend only on e, so all loads go out together
     if (NL > 0) si[0] = e ^ 1;
 #pragma unroll
@@ -74,7 +119,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t
 #pragma unroll
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) sv[l] = q.hd[si[l] * 32];
-    T cv = v;
+    float cv = v;
     int ce = e;
 #pragma unroll
     for (int l = 0; l < NL; ++l)
@@ -83,6 +128,46 @@ __device__ __forceinline__ void queue_replace_max(Queue<T, W_t> &q, T v, int32_t
             q.W[(node >> (l + 1)) * 32] = (W_t)ce;
         }
     q.top = cv;
+    q.etop = ce;
+}
+
+template <typename W_t, int LOGC, bool WITH_IDX>
+__device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double v, int32_t id)
+{
+    constexpr int NL = LOGC >= 0 ? LOGC : MAXLOG;
+    const int e = q.etop;
+    const uint32_t vhi = (uint32_t)__double2hiint(v), vlo = (uint32_t)__double2loint(v);
+    q.hd[e * 32] = vhi;
+    q.lo[e * 32] = vlo;
+    if (WITH_IDX) q.hi[e * 32] = id;
+    const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;
+    int si[NL > 0 ? NL : 1];
+    uint32_t sk[NL > 0 ? NL : 1];
+    if (NL > 0) si[0] = e ^ 1;
+#pragma unroll
+    for (int l = 1; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((node >> l) ^ 1) * 32];
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) sk[l] = q.hd[si[l] * 32];
+    uint32_t ck = vhi, clo = vlo;
+    int ce = e;
+    bool clo_known = true;                          // low word of the current path winner is in a register
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) {
+            bool gt = sk[l] > ck;
+            if (sk[l] == ck) {                      // equal high words (rare): decide on the exact values
+                if (!clo_known) { clo = q.lo[ce * 32]; clo_known = true; }
+                gt = q.lo[si[l] * 32] > clo;
+            }
+            if (gt) { ck = sk[l]; ce = si[l]; clo_known = false; }
+            q.W[(node >> (l + 1)) * 32] = (W_t)ce;
+        }
+    q.top_hi = ck;
+    q.top_lo = clo;
+    q.lo_known = clo_known;
+    q.top = __hiloint2double((int)ck, -1);          // upper bound for pruning and the phase-A filter
     q.etop = ce;
 }
 
@@ -106,12 +191,12 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
 #pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
             T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            mask |= (unsigned)(d2 < top0) << j;
+            mask |= (unsigned)(sizeof(T) == 8 ? d2 <= top0 : d2 < top0) << j;     // (double: top0 is an upper bound)
         }
-    } else {                                        // cell wider than half the period: image per particle
+    } else {                                        // some lane's shift is ambiguous here: image per particle
         for (int j = 0; j < cnt; ++j) {
             T d2 = dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period);
-            mask |= (unsigned)(d2 < top0) << j;
+            mask |= (unsigned)(sizeof(T) == 8 ? d2 <= top0 : d2 < top0) << j;
         }
     }
     if (!pass) mask = 0;
@@ -122,7 +207,7 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             mask &= mask - 1;
             const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
                               : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (d2 < q.top) queue_replace_max<T, W_t, LOGC, WITH_IDX>(q, d2, start + j);
+            if (below_top(q, d2)) queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, start + j);
         }
     }
 }
@@ -130,108 +215,128 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
 template <typename T, typename W_t, bool WITH_IDX>
 __host__ __device__ inline size_t knn_smem_per_warp(int K2)
 {
-    size_t b = (size_t)K2 * 32 * sizeof(T) + (size_t)K2 * 32 * sizeof(W_t) + (WITH_IDX ? (size_t)K2 * 32 * 4 : 0)
-               + 96 * sizeof(T);
+    size_t b = (size_t)K2 * 32 * sizeof(typename KeyOf<T>::type) + (size_t)K2 * 32 * sizeof(W_t)
+               + (WITH_IDX ? (size_t)K2 * 32 * 4 : 0) + 96 * sizeof(T);
     return (b + 127) & ~(size_t)127;
 }
+
+// start-of-search state: k "real" leaves hold distinct huge keys in decreasing order (so the leftmost leaf
+// wins everywhere and no two keys tie), padding leaves [k,K2) hold the smallest key
+__device__ __forceinline__ float init_key(float, int e, int k) { return e < k ? 3.0e38f - 1.0e32f * (float)e : -1.0f; }
+__device__ __forceinline__ uint32_t init_key(double, int e, int k) { return e < k ? 0x7fe00000u - (uint32_t)e : 0u; }
+__device__ __forceinline__ float init_top(float) { return 3.0e38f; }
+__device__ __forceinline__ double init_top(double) { return __hiloint2double(0x7fe00000, 0); }
 
 template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename KeyOf<T>::type Key;
     const TreeView<T> &tv = a.tv;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t bucket = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (bucket >= tv.nsplit) return;                // whole warp exits together; no block barriers below
+    const int warps = blockDim.x >> 5;
     const int k = a.k, LOG = LOGC >= 0 ? LOGC : a.LOG, K2 = 1 << LOG;
 
     unsigned char *base = smem_raw + knn_smem_per_warp<T, W_t, WITH_IDX>(K2) * wib;
     Queue<T, W_t> q;
     q.LOG = LOG; q.K2 = K2;
-    q.hd = reinterpret_cast<T *>(base) + lane;
-    T *tile = reinterpret_cast<T *>(base + (size_t)K2 * 32 * sizeof(T));
-    unsigned char *after = base + (size_t)K2 * 32 * sizeof(T) + 96 * sizeof(T);
+    q.hd = reinterpret_cast<Key *>(base) + lane;
+    unsigned char *after = base + (size_t)K2 * 32 * sizeof(Key);
     q.hi = nullptr;
     if (WITH_IDX) { q.hi = reinterpret_cast<int32_t *>(after) + lane; after += (size_t)K2 * 32 * 4; }
     q.W = reinterpret_cast<W_t *>(after) + lane;
-
-    const int start = tv.bucket_start[bucket];
-    const int cnt = tv.bucket_start[bucket + 1] - start;
-    const bool active = lane < cnt && (!tv.query_mask || tv.query_mask[start + lane]);
-    if (!__any_sync(FULL, active)) return;          // no query of this bucket is selected
-    T qx = 0, qy = 0, qz = 0;
-    if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
-
-    // leaves [0,k) start at +inf (replaced first), padding leaves [k,K2) at -inf (never a winner while a
-    // real leaf competes); every internal node starts with the leftmost leaf below it as winner
-    for (int e = 0; e < K2; ++e) {
-        q.hd[e * 32] = e < k ? Ex<T>::inf() : -Ex<T>::inf();
-        if (WITH_IDX) q.hi[e * 32] = -1;
-    }
-    for (int node = 1; node < K2; ++node) {
-        int lv = 31 - __clz(node);                  // depth of the node; its sub-tree spans K2 >> lv leaves
-        q.W[node * 32] = (W_t)((node - (1 << lv)) << (LOG - lv));
-    }
-    q.etop = 0;
-    q.top = active ? Ex<T>::inf() : (T)-1;          // idle lanes never match
+    after += (size_t)K2 * 32 * sizeof(W_t);
+    T *tile = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(after) + 15) & ~(uintptr_t)15);
+    q.lo = a.lo_scratch ? a.lo_scratch + ((size_t)blockIdx.x * warps + wib) * (size_t)K2 * 32 + lane : nullptr;
     const T L = tv.period;
 
-    // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
-    {
-        const bool amb = active && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, tv.nsplit + bucket), qx, qy, qz, L);
-        knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane,
-                                                 PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
-    }
+    for (;;) {
+        unsigned long long b64 = 0;
+        if (lane == 0) b64 = atomicAdd(a.next_bucket, 1ull);
+        const int64_t bucket = (int64_t)__shfl_sync(FULL, b64, 0);
+        if (bucket >= tv.nsplit) return;
 
-    // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
-    int64_t cell = tv.nsplit + bucket;
-    while (cell != 1) {
-        int64_t cp = cell ^ 1;
-        const int64_t stop = next_node(cp);
-        for (;;) {
-            Box6<T> b = load_box(tv.box, cp);
-            T sx, sy, sz;
-            T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
-            bool pass = gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();   // (empty nodes: inverted bounds)
-            if (__any_sync(FULL, pass)) {
-                if (cp < tv.nsplit) { cp = 2 * cp; continue; }
-                const bool amb = pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L);
-                knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
-                                                         PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+        const int start = tv.bucket_start[bucket];
+        const int cnt = tv.bucket_start[bucket + 1] - start;
+        const bool active = lane < cnt && (!tv.query_mask || tv.query_mask[start + lane]);
+        if (!__any_sync(FULL, active)) continue;    // no query of this bucket is selected
+        T qx = 0, qy = 0, qz = 0;
+        if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
+
+        for (int e = 0; e < K2; ++e) {
+            q.hd[e * 32] = init_key(T(), e, k);
+            if (sizeof(T) == 8) q.lo[e * 32] = 0u;
+            if (WITH_IDX) q.hi[e * 32] = -1;
+        }
+        for (int node = 1; node < K2; ++node) {
+            int lv = 31 - __clz(node);              // depth of the node; its sub-tree spans K2 >> lv leaves
+            q.W[node * 32] = (W_t)((node - (1 << lv)) << (LOG - lv));
+        }
+        q.etop = 0;
+        q.top = init_top(T());                      // "+inf" until k are held (pq.h:185-192)
+        q.top_hi = 0x7fe00000u; q.top_lo = 0u; q.lo_known = true;
+        if (!active) { q.top = (T)-1; q.top_hi = 0u; }   // idle lanes never match
+
+        // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
+        {
+            const bool amb = active && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, tv.nsplit + bucket), qx, qy, qz, L);
+            knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane,
+                                                     PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+        }
+
+        // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
+        int64_t cell = tv.nsplit + bucket;
+        while (cell != 1) {
+            int64_t cp = cell ^ 1;
+            const int64_t stop = next_node(cp);
+            for (;;) {
+                Box6<T> b = load_box(tv.box, cp);
+                T sx, sy, sz;
+                T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
+                // (top * slack overflows to +inf while the queue still holds its initial huge keys; empty
+                // nodes have inverted bounds and an infinite gap)
+                bool pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
+                if (__any_sync(FULL, pass)) {
+                    if (cp < tv.nsplit) { cp = 2 * cp; continue; }
+                    const bool amb = pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L);
+                    knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
+                                                             PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+                }
+                cp = next_node(cp);
+                if (cp == stop) break;
             }
-            cp = next_node(cp);
-            if (cp == stop) break;
+            cell >>= 1;
         }
-        cell >>= 1;
-    }
 
-    if (!active) return;
-    const int64_t p = start + lane;
-    const T h = (T)0.5 * Ex<T>::sqrt(q.top);        // smooth.h:429
-    a.smooth_t[p] = h;
-
-    if (FUSE_RHO) {
-        // smDensity (smooth.h:626-647) over the queue: the gather set of radius 2h differs from the
-        // k nearest only by entries at q = 2 where both kernels vanish.  All masses are equal here.
-        const T ih = (T)(1.0 / (double)h);
-        const T ih2 = ih * ih;
-        const T norm = (T)(0.31830988618379067154 * (double)ih * (double)ih2);
-        const T m = (T)a.uniform_mass;
-        T rho = 0;
-        for (int e = 0; e < k; ++e) {
-            T q2 = q.hd[e * 32] * ih2;
-            T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)q2);
-            w *= norm;
-            rho += w * m;
+        if (active) {
+            const int64_t p = start + lane;
+            const T h = (T)0.5 * Ex<T>::sqrt(top_exact(q));    // smooth.h:429
+            a.smooth_t[p] = h;
+            if (FUSE_RHO) {
+                // smDensity (smooth.h:626-647) over the queue: the gather set of radius 2h differs from the
+                // k nearest only by entries at q = 2 where both kernels vanish.  All masses are equal here.
+                const T ih = (T)(1.0 / (double)h);
+                const T ih2 = ih * ih;
+                const T norm = (T)(0.31830988618379067154 * (double)ih * (double)ih2);
+                const T m = (T)a.uniform_mass;
+                T rho = 0;
+                for (int e = 0; e < k; ++e) {
+                    T q2 = queue_value(q, e) * ih2;
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)q2);
+                    w *= norm;
+                    rho += w * m;
+                }
+                a.rho_t[p] = rho;
+            }
+            if (WITH_IDX && a.nn_idx) {
+                const int64_t row = (int64_t)tv.order[p] * k;
+                for (int e = 0; e < k; ++e) {
+                    a.nn_idx[row + e] = (int64_t)tv.order[q.hi[e * 32]];
+                    a.nn_d2[row + e] = queue_value(q, e);
+                }
+            }
         }
-        a.rho_t[p] = rho;
-    }
-    if (WITH_IDX && a.nn_idx) {
-        const int64_t row = (int64_t)tv.order[p] * k;
-        for (int e = 0; e < k; ++e) {
-            a.nn_idx[row + e] = (int64_t)tv.order[q.hi[e * 32]];
-            a.nn_d2[row + e] = q.hd[e * 32];
-        }
+        __syncwarp();
     }
 }
 
@@ -244,28 +349,44 @@ KernelParams make_kernel_params(int kernel_id, int k)
     return kp;
 }
 
-template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO>
-static void launch_knn(Tree &t, KnnArgs<T> &a)
+template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
+static void launch_knn_p(Tree &t, KnnArgs<T> &a)
 {
+    auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, PERIODIC>;
+    const int K2 = 1 << a.LOG;
     // two warps per block unless one warp's queues already need more than half the shared memory
-    const size_t per_warp = knn_smem_per_warp<T, W_t, WITH_IDX>(1 << a.LOG);
+    const size_t per_warp = knn_smem_per_warp<T, W_t, WITH_IDX>(K2);
     const int warps = per_warp * KNN_WARPS <= 227 * 1024 ? KNN_WARPS : 1;
     const size_t smem = per_warp * warps;
     if (smem > 227 * 1024)
         throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues "
-                                   "(at most 512 for float64 positions, 1024 for float32)");
-    const unsigned grid = (unsigned)((t.nsplit + warps - 1) / warps);
-    KernelTimer timer(0, t.stream);
-    if (a.tv.periodic) {
-        auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, true>;
-        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
-    } else {
-        auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, false>;
-        PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
+                                   "(at most 1024)");
+    PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    PNB_CUDA(cudaGetDevice(&dev));
+    PNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (t.nsplit + warps - 1) / warps;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);    // persistent: one resident wave
+    DevBuf counter(sizeof(unsigned long long)), lo;
+    PNB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), t.stream));
+    a.next_bucket = counter.as<unsigned long long>();
+    a.lo_scratch = nullptr;
+    if (sizeof(T) == 8) {
+        lo.alloc(sizeof(uint32_t) * (size_t)grid * warps * K2 * 32);
+        a.lo_scratch = lo.as<uint32_t>();
     }
+    KernelTimer timer(0, t.stream);
+    PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
     timer.stop();
+}
+
+template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO>
+static void launch_knn(Tree &t, KnnArgs<T> &a)
+{
+    if (a.tv.periodic) launch_knn_p<T, W_t, LOGC, WITH_IDX, FUSE_RHO, true>(t, a);
+    else launch_knn_p<T, W_t, LOGC, WITH_IDX, FUSE_RHO, false>(t, a);
 }
 
 template <typename T, typename W_t, int LOGC>
