@@ -248,6 +248,12 @@ def run_ours(args):
     step(h_pos.numpy(), h_mass.numpy(), h_sm.numpy(), h_rho.numpy(), False)
     e2e_ms = timed(lambda: step(h_pos.numpy(), h_mass.numpy(), h_sm.numpy(), h_rho.numpy(), False), args.steps) / args.steps
     e2e_value = world * n / (e2e_ms * 1e-3)
+    # the same from ordinary (pageable) numpy arrays, as a pynbody user would hand them over
+    p_pos, p_mass = h_pos.numpy().copy(), h_mass.numpy().copy()
+    p_sm, p_rho = np.empty(n, p_mass.dtype), np.empty(n, p_mass.dtype)
+    step(p_pos, p_mass, p_sm, p_rho, False)
+    e2e_pageable_ms = timed(lambda: step(p_pos, p_mass, p_sm, p_rho, False), 2) / 2
+    del p_pos, p_mass, p_sm, p_rho
     h2d = n * tsz * (3 + 1) + n * tsz * 2        # pos + mass at build; smooth + mass re-read by populate('rho')
     d2h = n * tsz * 2                            # smooth, rho
 
@@ -306,7 +312,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "pageable_host_arrays_ms_per_step": e2e_pageable_ms},
         "gpu_launches": stats["launches"],
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_knn (kNN smoothing lengths + fused density)",
