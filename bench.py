@@ -366,6 +366,9 @@ def run_ours_distributed(args):
         d = DistributedKDTree(p, m, boxsize=1.0)
         sm, rho = d.smooth_rho(K_NEIGHBOURS, 1)
         last["d"] = d
+        if args.verbose and rank == 0:
+            print("[dist step] owned=%d knn ms/Mparticle by rank: %s" % (d.n_own, getattr(d, "knn_cost_by_rank", None)),
+                  file=sys.stderr, flush=True)
         return sm, rho
 
     def step_e2e():
@@ -406,8 +409,17 @@ def run_ours_distributed(args):
     step_e2e()
     e2e_ms = timed(step_e2e, args.steps) / args.steps
     d = last["d"]
+    if d.timings:                                   # PNB_DIST_PROFILE=1: phase table of every rank
+        names = list(d.timings)
+        mine = torch.tensor([d.timings[k] for k in names], device="cuda", dtype=torch.float64)
+        allt = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        if rank == 0:
+            for i, nm in enumerate(names):
+                print("[dist phase] %-36s %s" % (nm, " ".join("%7.1f" % float(t[i]) for t in allt)), file=sys.stderr, flush=True)
     if args.verbose and rank == 0 and d.timings:
         print("[dist phases ms] " + ", ".join(f"{k}={v:.1f}" for k, v in d.timings.items()), file=sys.stderr, flush=True)
+        print("[dist stats] " + json.dumps(d.stats), file=sys.stderr, flush=True)
     st = torch.tensor([d.n_own, d.stats.get("boundary_queries", 0), d.stats.get("halo", 0)], device="cuda", dtype=torch.float64)
     allst = [torch.empty_like(st) for _ in range(world)]
     dist.all_gather(allst, st)

@@ -62,10 +62,18 @@ struct DevBuf {
         return *this;
     }
     ~DevBuf() { release(); }
+    // Size classes: multiples of 512 B up to 1 MiB, then 8 geometric steps per octave (<= 12.5 % slack), so
+    // that work buffers of slightly different particle counts (multi-GPU domains, successive snapshots) land
+    // in the same class and are re-used instead of going back to cudaMalloc.
+    static size_t size_class(size_t b) {
+        if (b <= ((size_t)1 << 20)) return b == 0 ? 512 : (b + 511) & ~(size_t)511;
+        int lg = 63 - __builtin_clzll((unsigned long long)b);
+        const size_t step = (size_t)1 << (lg - 3);
+        return (b + step - 1) & ~(step - 1);
+    }
     void alloc(size_t b) {
         release();
-        cap = (b + 511) & ~(size_t)511;
-        if (cap == 0) cap = 512;
+        cap = size_class(b);
         p = cache_alloc(cap);
         bytes = b;
     }

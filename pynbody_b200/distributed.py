@@ -67,6 +67,10 @@ class GpuLocalTree:
         self.kd.populate("hsm", k)
         return sm
 
+    def last_knn_ms(self):
+        from .kdtree import kdmain
+        return kdmain.last_kernel_ms(0)
+
     def density(self, sm, k, kernel_id, mask=None):
         self.kd._kernel_id = int(kernel_id)
         self._mask(mask)
@@ -113,29 +117,62 @@ class GpuBackend:
 # ------------------------------------------------------------------------------------------------
 # domain decomposition
 # ------------------------------------------------------------------------------------------------
-def _bisect(sample, lo, hi, ranks, out):
-    """Recursive coordinate bisection of box [lo,hi) among `ranks` using the coordinate sample
-    (numpy arrays on the host: a few hundred thousand points, selection not sorting)."""
+def _bisect(sample, weight, lo, hi, ranks, out):
+    """Recursive coordinate bisection of box [lo,hi) among `ranks`: split planes at the weighted quantiles
+    of the coordinate sample (numpy arrays on the host; weight = estimated search cost per particle)."""
     if len(ranks) == 1:
         out[ranks[0]] = (lo.copy(), hi.copy())
         return
     nleft = len(ranks) // 2
     ext = sample.max(axis=0) - sample.min(axis=0) if len(sample) else hi - lo
     axis = int(np.argmax(ext))
-    if len(sample) > 1:
+    if len(sample) > 1 and weight is None:                  # equal weights: selection, not sorting
         kth = min(len(sample) - 1, max(1, int(round(len(sample) * nleft / len(ranks)))))
-        q = np.partition(sample[:, axis], kth)[kth]
+        q = np.partition(np.ascontiguousarray(sample[:, axis]), kth)[kth]
+    elif len(sample) > 1:
+        order = np.argsort(np.ascontiguousarray(sample[:, axis]))
+        cw = np.cumsum(weight[order])
+        i = int(np.searchsorted(cw, cw[-1] * nleft / len(ranks)))
+        q = sample[order[min(max(i, 1), len(sample) - 1)], axis]
     else:
         q = 0.5 * (lo[axis] + hi[axis]) if np.isfinite(lo[axis] + hi[axis]) else sample.dtype.type(0)
     left = sample[:, axis] < q
     hi_l, lo_r = hi.copy(), lo.copy()
     hi_l[axis] = q
     lo_r[axis] = q
-    _bisect(sample[left], lo, hi_l, ranks[:nleft], out)
-    _bisect(sample[~left], lo_r, hi, ranks[nleft:], out)
+    _bisect(sample[left], None if weight is None else weight[left], lo, hi_l, ranks[:nleft], out)
+    _bisect(sample[~left], None if weight is None else weight[~left], lo_r, hi, ranks[nleft:], out)
 
 
-def decompose(pos, boxsize, group=None, sample_per_rank=32768, seed=0):
+# Optional cost feedback (PNB_DIST_COST_FEEDBACK=1): after a smoothing pass the ranks share how long their
+# search took per particle and the next decomposition weights its coordinate sample with that
+# piecewise-constant cost field, as N-body codes do with the previous step's measured costs.  Off by
+# default: on the clustered boxes measured here the per-particle search cost of equal-count domains
+# agrees to ~2 % (4.28-4.39 ms per million particles at 4 GPUs), so there is nothing to gain, and split
+# planes that move from call to call defeat the re-use of work buffers.  Purely a performance hint: any
+# set of split planes gives the same results.
+_COST_FIELD = {}
+
+
+def record_costs(world, domains, cost_per_particle):
+    _COST_FIELD[world] = ([(l.numpy().copy(), h.numpy().copy()) for l, h in domains], np.asarray(cost_per_particle, float))
+
+
+def _sample_weights(world, samp):
+    if world not in _COST_FIELD or not len(samp) or not os.environ.get("PNB_DIST_COST_FEEDBACK"):
+        return None
+    w = np.ones(len(samp))
+    if True:
+        doms, cost = _COST_FIELD[world]
+        if np.all(np.isfinite(cost)) and cost.min() > 0:
+            cost = np.clip(cost / cost.mean(), 0.5, 2.0)
+            for (lo, hi), c in zip(doms, cost):
+                inside = np.all((samp >= lo) & (samp < hi), axis=1)
+                w[inside] = c
+    return w
+
+
+def decompose(pos, boxsize, group=None, sample_per_rank=8192, seed=0):
     """One cuboid domain (lo[3], hi[3]) per rank; identical on every rank.
 
     Periodic: domains tile [gmin, gmin + boxsize)^3.  Open: outer faces are +-inf.
@@ -170,7 +207,7 @@ def decompose(pos, boxsize, group=None, sample_per_rank=32768, seed=0):
         lo = np.full(3, -np.inf, dtype=samp.dtype)
         hi = np.full(3, np.inf, dtype=samp.dtype)
     out = [None] * world
-    _bisect(samp, lo, hi, list(range(world)), out)
+    _bisect(samp, _sample_weights(world, samp), lo, hi, list(range(world)), out)
     return [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out], periodic
 
 
@@ -314,6 +351,7 @@ class DistributedKDTree:
         sm = self.tree1.knn_smooth(k, None, kernel_id) if self.n_own >= k else None
         self._tick("knn_owned")
         self._sm_stage1 = sm
+        self._share_costs()
         if self.world == 1:
             if sm is None:
                 raise ValueError("Number of smoothing particles exceeds number of particles in tree")
@@ -385,6 +423,18 @@ class DistributedKDTree:
         else:
             halo = self._halo_values(owned_values)
         return torch.cat([near, halo])
+
+    def _share_costs(self):
+        """Tell every rank how expensive this rank's particles were to search (see _COST_FIELD)."""
+        ms = getattr(self.tree1, "last_knn_ms", lambda: None)()
+        if self.world == 1 or ms is None or not os.environ.get("PNB_DIST_COST_FEEDBACK"):
+            return
+        mine = torch.tensor([ms / max(self.n_own, 1)], dtype=torch.float64, device=self.dev)
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine, group=self.group)
+        costs = [float(c.item()) for c in allc]
+        self.knn_cost_by_rank = [round(c * 1e6, 2) for c in costs]      # ms per million particles
+        record_costs(self.world, self.domains, costs)
 
     def _halo_values(self, owned_values):
         """Halo exchange #2: per-particle values of the halo particles, in tree2's halo order."""

@@ -101,10 +101,20 @@ def test_decompose_is_balanced_and_tiles_the_box():
     # bisection of a sample into 8 boxes: disjoint, covering, balanced
     from pynbody_b200.distributed import _bisect
     out = [None] * 8
-    _bisect(pos, np.zeros(3), np.ones(3), list(range(8)), out)
+    _bisect(pos, None, np.zeros(3), np.ones(3), list(range(8)), out)
     out = [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out]
     owner = owner_of(tp, out)
     counts = torch.bincount(owner, minlength=8)
     assert counts.sum() == len(pos) and counts.min() > 0.9 * len(pos) / 8 and counts.max() < 1.1 * len(pos) / 8
     vol = sum(float(torch.prod(h - l)) for l, h in out)
     assert abs(vol - 1.0) < 1e-12
+    # cost feedback: particles in the lower half of the box are declared twice as expensive -> the domains
+    # there shrink so that every rank gets the same estimated work
+    w = np.where(pos[:, 2] < 0.5, 2.0, 1.0)
+    out2 = [None] * 8
+    _bisect(pos, w, np.zeros(3), np.ones(3), list(range(8)), out2)
+    out2 = [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out2]
+    owner2 = owner_of(tp, out2)
+    work = np.array([w[(owner2 == r).numpy()].sum() for r in range(8)])
+    assert work.min() > 0.9 * work.mean() and work.max() < 1.1 * work.mean()
+    assert abs(sum(float(torch.prod(h - l)) for l, h in out2) - 1.0) < 1e-12
