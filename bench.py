@@ -49,6 +49,15 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(dtype, n_side):
+    """DRAM bytes of one k_knn launch for this workload from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(f"{dtype}:{n_side}")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
 
@@ -317,7 +326,8 @@ def run_ours(args):
         "gpu_launches": stats["launches"],
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_knn (kNN smoothing lengths + fused density)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(args.dtype, args.n_side), "algorithmic_bytes_per_launch": alg_bytes,
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": 6 * tsz,
                      "kernel_ms": knn_kernel_ms,
                      "logical_gather_gbs": gather_bytes / (knn_kernel_ms * 1e-3) / 1e9,

@@ -177,6 +177,14 @@ int pnb_render_grid(int nx, int ny, int nz, const pnb_render_arrays *a,
                     const double *wrap_z, int n_wrap_z,
                     float *out, int out_mem);
 
+/* ---- _render.render_spherical_image_core (pynbody/sph/_render.pyx:51-179, sph/healpix.c) -----------
+ * Healpix (RING) image around the origin: projected column per solid angle (h_power == 2) or a thin
+ * shell at shell_radius sampled with the 3-D kernel (h_power == 3).  `a->sm` holds the smoothing
+ * lengths h.  out: float32[12 * nside * nside]. */
+int pnb_render_healpix(const pnb_render_arrays *a, int nside,
+                       const float *lut, int n_lut, int h_power, double max_d,
+                       double shell_radius, float *out, int out_mem);
+
 /* Return the device memory the library keeps cached for re-use (freed work buffers) to the driver. */
 void pnb_release_cached_memory(void);
 

@@ -415,3 +415,140 @@ void orc_to_3d_grid(int nx, int ny, int nz, int64_t n,
         }
     }
 }
+
+/* ========================================================================================
+ * Healpix renderer.  _render.pyx:51-179 (render_spherical_image_core) with the disc query of
+ * sph/healpix.c:24-204 (RING scheme).  Same operation order; libm sin/cos/acos/atan2/sqrt.
+ * ====================================================================================== */
+#define ORC_PI 3.14159265358979323846
+
+static size_t hp_ring_num_from_z(size_t nside, double z)                 /* healpix.c:24-43 */
+{
+    size_t nring = 4 * nside, iring;
+    double nd = (double)nside;
+    if (z > 2.0 / 3.0) iring = (size_t)(nd * sqrt(3.0 * (1.0 - z)) + 0.5);
+    else if (z >= -2.0 / 3.0) iring = (size_t)(nd * (2.0 - 1.5 * z) + 0.5);
+    else iring = (size_t)(nring - nd * sqrt(3.0 * (1.0 + z)) + 0.5);
+    if (iring < 1) iring = 1;
+    if (iring > nring) iring = nring;
+    return iring;
+}
+static double hp_z_from_ring_num(size_t nside, size_t iring)             /* healpix.c:46-64 */
+{
+    size_t nl4 = 4 * nside;
+    if (iring <= nside) { double t = iring; return 1.0 - (t * t) / (3.0 * nside * nside); }
+    if (iring <= 3 * nside) return (2 * (double)nside - (double)iring) / (1.5 * nside);
+    { double t = nl4 - iring; return -1.0 + (t * t) / (3.0 * nside * nside); }
+}
+static size_t hp_pixel_index(size_t nside, size_t iring, size_t iphi)    /* healpix.c:67-91 */
+{
+    size_t npix = 12 * nside * nside, ncap = 2 * nside * (nside + 1), nr;
+    if (iring <= nside) { nr = iring; return nr * (nr - 1) * 2 + iphi - 1; }
+    if (iring <= 3 * nside) return ncap + (iring - nside - 1) * 4 * nside + iphi - 1;
+    nr = 4 * nside - iring;
+    return npix - nr * (nr - 1) * 2 + iphi - 1 - 4 * nr;
+}
+static size_t hp_query_disc(size_t nside, double *vec0, double radius, size_t *listpix, double *distpix)
+{                                                                        /* healpix.c:94-204 */
+    double vecnorm = sqrt(vec0[0] * vec0[0] + vec0[1] * vec0[1] + vec0[2] * vec0[2]);
+    vec0[0] /= vecnorm; vec0[1] /= vecnorm; vec0[2] /= vecnorm;
+    double z0 = vec0[2], sin_theta0 = sqrt(1 - z0 * z0), phi0 = atan2(vec0[1], vec0[0]), theta0 = acos(z0);
+    double thetamin = theta0 - radius, thetamax = theta0 + radius;
+    if (thetamin < 0.0) thetamin = 0.0;
+    if (thetamax > ORC_PI) thetamax = ORC_PI;
+    double zmax = cos(thetamin), zmin = cos(thetamax);
+    size_t irmin = hp_ring_num_from_z(nside, zmax), irmax = hp_ring_num_from_z(nside, zmin), count = 0;
+    const double twopi = 2.0 * ORC_PI;
+    for (size_t iring = irmin; iring <= irmax; iring++) {
+        double z = hp_z_from_ring_num(nside, iring), sin_theta = sqrt(1.0 - z * z);
+        double cos_dphi = (cos(radius) - z * z0) / (sin_theta * sin_theta0), dphi;
+        if (cos_dphi >= 1.0) dphi = 0.0; else if (cos_dphi <= -1.0) dphi = ORC_PI; else dphi = acos(cos_dphi);
+        size_t ip_lo, ip_hi, n_in_ring, shift;
+        if (iring <= nside) { n_in_ring = 4 * iring; shift = 1; }
+        else if (iring <= 3 * nside) { n_in_ring = 4 * nside; shift = 2 - (iring - nside + 1) % 2; }
+        else { n_in_ring = 4 * (4 * nside - iring); shift = 1; }
+        if (dphi > 0.5 * ORC_PI) { ip_lo = 1; ip_hi = n_in_ring; }
+        else {
+            double phi_low = phi0 - dphi, phi_high = phi0 + dphi;
+            if (phi_low < 0.0) phi_low += twopi;
+            if (phi_high >= twopi) phi_high -= twopi;
+            double phi_factor = n_in_ring / twopi;
+            ip_lo = (size_t)(phi_low * phi_factor + 0.5 * shift);
+            ip_hi = (size_t)(phi_high * phi_factor + 0.5 * shift + 1);
+        }
+        if (ip_hi < ip_lo) ip_hi += n_in_ring;
+        if (ip_hi - ip_lo > n_in_ring) { ip_lo = 1; ip_hi = n_in_ring; }
+        for (size_t iphi = ip_lo; iphi <= ip_hi; iphi++) {
+            size_t ip = iphi;
+            if (ip > n_in_ring) ip -= n_in_ring;
+            size_t ipix = hp_pixel_index(nside, iring, ip);
+            double theta = acos(z), phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
+            if (phi >= twopi) phi -= twopi;
+            double vec[3] = { sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta) };
+            double dot = vec0[0] * vec[0] + vec0[1] * vec[1] + vec0[2] * vec[2];
+            if (dot > 1.0) dot = 1.0;
+            if (dot < -1.0) dot = -1.0;
+            double dist = acos(dot);
+            if (dist <= radius) { distpix[count] = dist; listpix[count++] = ipix; }
+        }
+    }
+    return count;
+}
+
+void orc_render_healpix(int64_t n, const void *rho, int rho_f64, const void *mass, int mass_f64,
+                        const void *qty, int qty_f64, const void *x, const void *y, const void *z, int64_t pos_stride,
+                        int pos_f64, const void *h, int h_f64, int nside, const float *lut, int ns, int h_power,
+                        double max_d, double shell_radius, float *out)
+{
+    arr_t ar = { rho, 1, rho_f64 }, am = { mass, 1, mass_f64 }, aq = { qty, 1, qty_f64 }, ah = { h, 1, h_f64 };
+    arr_t ax = { x, pos_stride, pos_f64 }, ay = { y, pos_stride, pos_f64 }, az = { z, pos_stride, pos_f64 };
+    size_t npix = (size_t)12 * nside * nside;
+    /* (a ring whose phi range wraps all the way round lists one pixel twice, healpix.c:166-171: leave room) */
+    size_t *index = (size_t *)malloc(sizeof(size_t) * (npix + 8 * (size_t)nside + 8));
+    double *angle = (double *)malloc(sizeof(double) * (npix + 8 * (size_t)nside + 8));
+    const int projected = h_power == 2;
+    const double max2 = max_d * max_d, shell_2 = shell_radius * shell_radius;
+    memset(out, 0, sizeof(float) * npix);
+    for (int64_t i = 0; i < n; ++i) {
+        double qty_i = ld(&aq, i);
+        if (qty_i != qty_i) continue;
+        double pos_i[3] = { ld(&ax, i), ld(&ay, i), ld(&az, i) };
+        double hi = ld(&ah, i);
+        double distance2 = pos_i[0] * pos_i[0] + pos_i[1] * pos_i[1] + pos_i[2] * pos_i[2];
+        /* smooth_2 = h[i]*h[i] is evaluated in the element type of h (_render.pyx:136) */
+        double smooth_2 = ah.f64 ? hi * hi : (double)(((const float *)h)[i] * ((const float *)h)[i]);
+        double distance = sqrt(distance2), kernel_max_2 = smooth_2 * max2;
+        double angular_size, two_rs_d = 0;
+        float h_to_kdim;
+        if (projected) {
+            angular_size = max_d * hi / distance;
+            h_to_kdim = (float)(smooth_2 / distance2);
+        } else {
+            two_rs_d = 2.0 * shell_radius * distance;
+            double cos_alpha = (shell_2 + distance2 - kernel_max_2) / two_rs_d;
+            if (cos_alpha >= 1.0) continue;
+            else if (cos_alpha <= -1.0) angular_size = ORC_PI;
+            else angular_size = acos(cos_alpha);
+            h_to_kdim = (float)(smooth_2 * hi);
+        }
+        size_t np_ = hp_query_disc((size_t)nside, pos_i, angular_size, index, angle);
+        for (size_t j = 0; j < np_; ++j) {
+            double d2;
+            if (projected) { double off = distance * angle[j]; d2 = off * off; }
+            else d2 = shell_2 + distance2 - two_rs_d * cos(angle[j]);
+            float kern = lut_lookup(d2, kernel_max_2, h_to_kdim, ns, lut);
+            /* im[...] += qty_i * kern * mass[i] / rho[i] with C's left-to-right promotion over the fused
+             * element types (_render.pyx:176): float until the first double operand appears */
+            int isd = aq.f64;
+            double vd = isd ? qty_i * (double)kern : 0.0;
+            float vf = isd ? 0.0f : (float)qty_i * kern;
+            if (isd || am.f64) { vd = (isd ? vd : (double)vf) * ld(&am, i); isd = 1; }
+            else vf = vf * ((const float *)mass)[i];
+            if (isd || ar.f64) { vd = (isd ? vd : (double)vf) / ld(&ar, i); isd = 1; }
+            else vf = vf / ((const float *)rho)[i];
+            if (isd) out[index[j]] = (float)((double)out[index[j]] + vd);
+            else out[index[j]] += vf;
+        }
+    }
+    free(index); free(angle);
+}

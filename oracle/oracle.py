@@ -194,3 +194,26 @@ def to_3d_grid(nx, ny, nz, x, y, z, sm, x1, x2, y1, y2, z1, z2, qty, mass, rho,
                          _p(lut), len(lut), int(kernel.h_power), float(kernel.max_d),
                          _p(wx), len(wx), _p(wy), len(wy), _p(wz), len(wz), _p(out))
     return out
+
+
+def render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell_radius=0.0):
+    """_render.render_spherical_image_core (pynbody/sph/_render.pyx:51-179) restated."""
+    if nside & (nside - 1):
+        raise ValueError("nside value must be a power of 2")
+    if kernel.h_power not in (2, 3):
+        raise ValueError("Only kernels of dimension 2 (projected) or 3 (thin shell) are supported for healpix maps")
+    if kernel.h_power == 3 and shell_radius <= 0.0:
+        raise ValueError("A positive shell_radius is required to render a 3D (thin shell) healpix map")
+    x, y, z, st, pf = _pos_cols(x, y, z)
+    rho, mass, qty, h = (_arr(a) for a in (rho, mass, qty, h))
+    lut = np.ascontiguousarray(kernel.get_samples(dtype=np.float32))
+    out = np.empty(12 * nside * nside, np.float32)
+    f = lambda a: int(a.dtype == np.float64)
+    L = lib()
+    L.orc_render_healpix.restype = None
+    L.orc_render_healpix.argtypes = [_i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
+                                     _vp, _i32, _i32, _dbl, _dbl, _vp]
+    L.orc_render_healpix(len(x), _p(rho), f(rho), _p(mass), f(mass), _p(qty), f(qty), _p(x), _p(y), _p(z), st, pf,
+                         _p(h), f(h), int(nside), _p(lut), len(lut), int(kernel.h_power), float(kernel.max_d),
+                         float(shell_radius), _p(out))
+    return out

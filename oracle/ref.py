@@ -241,3 +241,10 @@ def to_3d_grid(nx, ny, nz, x, y, z, sm, x1, x2, y1, y2, z1, z2, qty, mass, rho,
 
     _thread_map(work, list(range(num_threads)))
     return sum(res)
+
+
+def render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell_radius=0.0):
+    """The reference's healpix renderer (pynbody/sph/_render.pyx:51-179), as HealpixRenderer calls it
+    (pynbody/sph/renderers.py:720-766)."""
+    _load()
+    return _render.render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell_radius)

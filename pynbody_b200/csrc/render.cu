@@ -604,6 +604,198 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
     set_kernel_ms(2, kernel_ms);
 }
 
+// ================================================================================================
+// Healpix renderer.  Replaces _render.render_spherical_image_core (pynbody/sph/_render.pyx:51-179) and
+// its disc query query_disc_c (pynbody/sph/healpix.c:94-204, RING scheme).  Like the reference this is
+// a per-particle scatter over the pixels of the particle's angular disc -- the disc is found ring by
+// ring, exactly as healpix.c does it -- but one WARP takes one particle: the ring loop is warp-uniform
+// and the lanes share the pixels of a ring; contributions go to a double accumulator with atomicAdd.
+// ================================================================================================
+struct HpArgs {
+    const void *x, *y, *z, *h, *qty, *mass, *rho;
+    int pos_f64, h_f64, qty_f64, mass_f64, rho_f64;
+    int64_t n;
+    int nside, ns, projected;
+    double max_d, shell_radius;
+};
+
+__device__ __forceinline__ double ldv(const void *p, int f64, int64_t i)
+{
+    return f64 ? ((const double *)p)[i] : (double)((const float *)p)[i];
+}
+__device__ __forceinline__ size_t hp_ring_num_from_z(size_t nside, double z)            // healpix.c:24-43
+{
+    const size_t nring = 4 * nside;
+    size_t iring;
+    const double nd = (double)nside;
+    if (z > 2.0 / 3.0) iring = (size_t)(nd * sqrt(3.0 * (1.0 - z)) + 0.5);
+    else if (z >= -2.0 / 3.0) iring = (size_t)(nd * (2.0 - 1.5 * z) + 0.5);
+    else iring = (size_t)(nring - nd * sqrt(3.0 * (1.0 + z)) + 0.5);
+    if (iring < 1) iring = 1;
+    if (iring > nring) iring = nring;
+    return iring;
+}
+__device__ __forceinline__ double hp_z_from_ring_num(size_t nside, size_t iring)        // healpix.c:46-64
+{
+    const size_t nl4 = 4 * nside;
+    if (iring <= nside) { const double t = (double)iring; return 1.0 - (t * t) / (3.0 * nside * nside); }
+    if (iring <= 3 * nside) return (2 * (double)nside - (double)iring) / (1.5 * nside);
+    const double t = (double)(nl4 - iring);
+    return -1.0 + (t * t) / (3.0 * nside * nside);
+}
+__device__ __forceinline__ size_t hp_pixel_index(size_t nside, size_t iring, size_t iphi)   // healpix.c:67-91
+{
+    const size_t npix = 12 * nside * nside, ncap = 2 * nside * (nside + 1);
+    if (iring <= nside) return iring * (iring - 1) * 2 + iphi - 1;
+    if (iring <= 3 * nside) return ncap + (iring - nside - 1) * 4 * nside + iphi - 1;
+    const size_t nr = 4 * nside - iring;
+    return npix - nr * (nr - 1) * 2 + iphi - 1 - 4 * nr;
+}
+
+__global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *__restrict__ lut, double *__restrict__ acc)
+{
+    const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= a.n) return;
+    const double qty_i = ldv(a.qty, a.qty_f64, i);
+    if (qty_i != qty_i) return;                                                          // _render.pyx:128-129
+    double v0 = ldv(a.x, a.pos_f64, i), v1 = ldv(a.y, a.pos_f64, i), v2 = ldv(a.z, a.pos_f64, i);
+    const double hi = ldv(a.h, a.h_f64, i);
+    const double distance2 = v0 * v0 + v1 * v1 + v2 * v2;
+    const double distance = sqrt(distance2);
+    // h[i]*h[i] is evaluated in the element type of h (_render.pyx:136)
+    const double smooth_2 = a.h_f64 ? hi * hi : (double)(((const float *)a.h)[i] * ((const float *)a.h)[i]);
+    const double kernel_max_2 = smooth_2 * (a.max_d * a.max_d);
+    const double shell_2 = a.shell_radius * a.shell_radius;
+    double radius, two_rs_d = 0.0;
+    float h_to_kdim;
+    if (a.projected) {
+        radius = a.max_d * hi / distance;
+        h_to_kdim = (float)(smooth_2 / distance2);
+    } else {
+        two_rs_d = 2.0 * a.shell_radius * distance;
+        const double cos_alpha = (shell_2 + distance2 - kernel_max_2) / two_rs_d;
+        if (cos_alpha >= 1.0) return;
+        radius = cos_alpha <= -1.0 ? PI : acos(cos_alpha);
+        h_to_kdim = (float)(smooth_2 * hi);
+    }
+    // qty_i * kern * mass / rho with C's left-to-right promotion over the element types (_render.pyx:176)
+    const size_t nside = (size_t)a.nside;
+    const double vecnorm = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    v0 /= vecnorm; v1 /= vecnorm; v2 /= vecnorm;
+    const double z0 = v2, sin_theta0 = sqrt(1 - z0 * z0), phi0 = atan2(v1, v0), theta0 = acos(z0);
+    double thetamin = theta0 - radius, thetamax = theta0 + radius;
+    if (thetamin < 0.0) thetamin = 0.0;
+    if (thetamax > PI) thetamax = PI;
+    const size_t irmin = hp_ring_num_from_z(nside, cos(thetamin)), irmax = hp_ring_num_from_z(nside, cos(thetamax));
+    const double cos_radius = cos(radius);
+    for (size_t iring = irmin; iring <= irmax; ++iring) {
+        const double z = hp_z_from_ring_num(nside, iring), sin_theta = sqrt(1.0 - z * z);
+        const double cos_dphi = (cos_radius - z * z0) / (sin_theta * sin_theta0);
+        const double dphi = cos_dphi >= 1.0 ? 0.0 : (cos_dphi <= -1.0 ? PI : acos(cos_dphi));
+        size_t ip_lo, ip_hi, n_in_ring, shift;
+        if (iring <= nside) { n_in_ring = 4 * iring; shift = 1; }
+        else if (iring <= 3 * nside) { n_in_ring = 4 * nside; shift = 2 - (iring - nside + 1) % 2; }
+        else { n_in_ring = 4 * (4 * nside - iring); shift = 1; }
+        if (dphi > 0.5 * PI) { ip_lo = 1; ip_hi = n_in_ring; }
+        else {
+            double phi_low = phi0 - dphi, phi_high = phi0 + dphi;
+            if (phi_low < 0.0) phi_low += twopi;
+            if (phi_high >= twopi) phi_high -= twopi;
+            const double phi_factor = n_in_ring / twopi;
+            ip_lo = (size_t)(phi_low * phi_factor + 0.5 * shift);
+            ip_hi = (size_t)(phi_high * phi_factor + 0.5 * shift + 1);
+        }
+        if (ip_hi < ip_lo) ip_hi += n_in_ring;
+        if (ip_hi - ip_lo > n_in_ring) { ip_lo = 1; ip_hi = n_in_ring; }
+        const double theta = acos(z), st = sin(theta), ct = cos(theta);
+        for (size_t iphi = ip_lo + lane; iphi <= ip_hi; iphi += 32) {
+            size_t ip = iphi;
+            if (ip > n_in_ring) ip -= n_in_ring;
+            const size_t ipix = hp_pixel_index(nside, iring, ip);
+            double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
+            if (phi >= twopi) phi -= twopi;
+            double dot = v0 * (st * cos(phi)) + v1 * (st * sin(phi)) + v2 * ct;
+            if (dot > 1.0) dot = 1.0;
+            if (dot < -1.0) dot = -1.0;
+            const double dist = acos(dot);
+            if (!(dist <= radius)) continue;
+            double d2;
+            if (a.projected) { const double off = distance * dist; d2 = off * off; }
+            else d2 = shell_2 + distance2 - two_rs_d * cos(dist);
+            const double t = a.ns * (d2 / kernel_max_2);
+            const unsigned idx = (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
+            const float kern = idx < (unsigned)a.ns ? lut[idx] / h_to_kdim : 0.0f;
+            bool isd = a.qty_f64;
+            double vd = isd ? qty_i * (double)kern : 0.0;
+            float vf = isd ? 0.0f : (float)qty_i * kern;
+            if (isd || a.mass_f64) { vd = (isd ? vd : (double)vf) * ldv(a.mass, a.mass_f64, i); isd = true; }
+            else vf = vf * ((const float *)a.mass)[i];
+            if (isd || a.rho_f64) { vd = (isd ? vd : (double)vf) / ldv(a.rho, a.rho_f64, i); isd = true; }
+            else vf = vf / ((const float *)a.rho)[i];
+            atomicAdd(&acc[ipix], isd ? vd : (double)vf);
+        }
+    }
+}
+
+void render_healpix(const pnb_render_arrays *a, int nside, const float *lut, int n_lut, int h_power, double max_d,
+                    double shell_radius, float *out, int out_mem)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw Error(PNB_ERR_CUDA, "no CUDA device available: pnb_b200 has no CPU fallback");
+    }
+    check_arrays(a);
+    if (nside < 1 || (nside & (nside - 1))) throw Error(PNB_ERR_VALUE, "nside value must be a power of 2");
+    if (h_power != 2 && h_power != 3)
+        throw Error(PNB_ERR_VALUE, "Only kernels of dimension 2 (projected) or 3 (thin shell) are supported for healpix maps");
+    if (h_power == 3 && !(shell_radius > 0.0))
+        throw Error(PNB_ERR_VALUE, "A positive shell_radius is required to render a 3D (thin shell) healpix map");
+    if (!lut || n_lut < 1 || n_lut > 8192) throw Error(PNB_ERR_VALUE, "kernel table must hold 1..8192 samples");
+    if (!out) throw Error(PNB_ERR_VALUE, "output pointer is null");
+    cudaStream_t s = nullptr;
+    StageTimer stage(2, s);
+    const int64_t n = a->n, npix = (int64_t)12 * nside * nside;
+    DevBuf acc(sizeof(double) * npix), lut_dev(sizeof(float) * n_lut);
+    PNB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * npix, s));
+    PNB_CUDA(cudaMemcpyAsync(lut_dev.p, lut, sizeof(float) * n_lut, cudaMemcpyHostToDevice, s));
+    double kernel_ms = 0;
+    if (n > 0) {
+        const size_t ps = tsize(a->pos_dtype);
+        DevBuf dx(ps * n), dy(ps * n), dz(ps * n), dh(tsize(a->sm_dtype) * n), dq(tsize(a->qty_dtype) * n),
+            dm(tsize(a->mass_dtype) * n), dr(tsize(a->rho_dtype) * n);
+        fetch_columns(a->x, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dx.p, s);
+        fetch_columns(a->y, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dy.p, s);
+        fetch_columns(a->z, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dz.p, s);
+        fetch_columns(a->sm, a->sm_stride, 0, 1, a->sm_dtype, a->mem, n, dh.p, s);
+        fetch_columns(a->qty, a->qty_stride, 0, 1, a->qty_dtype, a->mem, n, dq.p, s);
+        fetch_columns(a->mass, a->mass_stride, 0, 1, a->mass_dtype, a->mem, n, dm.p, s);
+        fetch_columns(a->rho, a->rho_stride, 0, 1, a->rho_dtype, a->mem, n, dr.p, s);
+        HpArgs h;
+        h.x = dx.p; h.y = dy.p; h.z = dz.p; h.h = dh.p; h.qty = dq.p; h.mass = dm.p; h.rho = dr.p;
+        h.pos_f64 = a->pos_dtype; h.h_f64 = a->sm_dtype; h.qty_f64 = a->qty_dtype; h.mass_f64 = a->mass_dtype;
+        h.rho_f64 = a->rho_dtype; h.n = n; h.nside = nside; h.ns = n_lut; h.projected = h_power == 2;
+        h.max_d = max_d; h.shell_radius = shell_radius;
+        KernelTimer timer(2, s);
+        PNB_LAUNCH(k_render_healpix, nblk(n * 32, 256), 256, 0, s, h, lut_dev.as<float>(), acc.as<double>());
+        timer.stop();
+        kernel_ms = pnb_last_kernel_ms(2);
+    }
+    if (out_mem == PNB_DEVICE) {
+        PNB_LAUNCH(k_finalize, nblk(npix, 256), 256, 0, s, acc.as<double>(), npix, out);
+        PNB_CUDA(cudaStreamSynchronize(s));
+    } else {
+        DevBuf of(sizeof(float) * npix);
+        PNB_LAUNCH(k_finalize, nblk(npix, 256), 256, 0, s, acc.as<double>(), npix, of.as<float>());
+        PNB_CUDA(cudaMemcpyAsync(out, of.p, sizeof(float) * npix, cudaMemcpyDeviceToHost, s));
+        PNB_CUDA(cudaStreamSynchronize(s));
+    }
+    stage.stop();
+    set_kernel_ms(2, kernel_ms);
+}
+
 template <typename F>
 int guarded_render(F &&f)
 {
@@ -635,6 +827,12 @@ int pnb_render_image(int nx, int ny, const pnb_render_arrays *a, double x1, doub
         render(false, nx, ny, 1, a, x1, x2, y1, y2, 0.0, 1.0, z_camera, z0, smooth_lo, smooth_hi, z_lo, z_hi, min_smooth,
                lut, n_lut, h_power, max_d, wrap_x, n_wrap_x, wrap_y, n_wrap_y, nullptr, 0, out, out_mem);
     });
+}
+
+int pnb_render_healpix(const pnb_render_arrays *a, int nside, const float *lut, int n_lut, int h_power, double max_d,
+                       double shell_radius, float *out, int out_mem)
+{
+    return guarded_render([&] { render_healpix(a, nside, lut, n_lut, h_power, max_d, shell_radius, out, out_mem); });
 }
 
 int pnb_render_grid(int nx, int ny, int nz, const pnb_render_arrays *a, double x1, double x2, double y1, double y2,

@@ -134,6 +134,25 @@ def to_3d_grid(nx, ny, nz, x, y, z, sm, x1, x2, y1, y2, z1, z2, qty, mass, rho,
     return out
 
 
+def render_spherical_image_core(rho, mass, qtyar, x, y, z, h, nside, kernel, shell_radius=0.0):
+    """Healpix (RING) SPH image around the origin, float32 ``(12 * nside**2,)``
+    (pynbody/sph/_render.pyx:51-179): projected column per solid angle for a 2-D kernel, thin shell at
+    ``shell_radius`` for a 3-D kernel."""
+    nside = int(nside)
+    if nside & (nside - 1) != 0:
+        raise ValueError("nside value must be a power of 2")
+    if kernel.h_power not in (2, 3):
+        raise ValueError("Only kernels of dimension 2 (projected) or 3 (thin shell) are supported for healpix maps")
+    if kernel.h_power == 3 and shell_radius <= 0.0:
+        raise ValueError("A positive shell_radius is required to render a 3D (thin shell) healpix map")
+    ra, keep = _arrays(x, y, z, h, qtyar, mass, rho)
+    lut, h_power, max_d = _kernel_table(kernel)
+    out, outp = _output((12 * nside * nside,), ra.mem)
+    _lib.check(_lib.lib().pnb_render_healpix(C.byref(ra), nside, lut.ctypes.data, len(lut), h_power, max_d,
+                                             float(shell_radius), outp, ra.mem))
+    return out
+
+
 def last_render_ms():
     """(device ms of the whole last render call, ms spent in the tile render kernel launches)."""
     L = _lib.lib()
