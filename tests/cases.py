@@ -121,6 +121,47 @@ RENDER_CASES = {
 }
 
 
+@dataclass
+class HealpixCase:
+    lut: str
+    h_power: int
+    dtype: type
+    nside: int
+    shell_radius: float = 0.0
+    seed: int = 31
+    n: int = 4000
+    mixed: bool = False
+
+    def make(self):
+        """Particles in a thick shell around the origin (0.6 < r < 1.4) so that angular discs stay well
+        below a hemisphere (the reference's fixed-size pixel buffer overflows for near-full-sky discs)."""
+        rng = np.random.default_rng(self.seed)
+        n = self.n
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = rng.uniform(0.6, 1.4, n)
+        pos = (d * r[:, None]).astype(self.dtype)
+        h = rng.lognormal(np.log(0.05), 0.6, n).astype(self.dtype)
+        mass = (rng.uniform(0.5, 1.5, n) / n).astype(self.dtype)
+        rho = rng.uniform(0.5, 2.0, n).astype(np.float64 if self.mixed else self.dtype)
+        qty = rng.uniform(0.5, 2.0, n).astype(self.dtype)
+        qty[11] = np.nan                      # skipped (_render.pyx:128-129)
+        return dict(pos=pos, h=h, mass=mass, rho=rho, qty=qty)
+
+    def args(self, a, kern):
+        pos = a["pos"]
+        return (a["rho"], a["mass"], a["qty"], pos[:, 0], pos[:, 1], pos[:, 2], a["h"], self.nside, kern, self.shell_radius)
+
+
+HEALPIX_CASES = {
+    "proj_cubic_f64": HealpixCase("cubic2d", 2, np.float64, 16),
+    "proj_wendland_f32": HealpixCase("wendland2d", 2, np.float32, 32),
+    "proj_cubic_f32_mixed": HealpixCase("cubic2d", 2, np.float32, 8, mixed=True),
+    "shell_wendland_f64": HealpixCase("wendland3d", 3, np.float64, 16, shell_radius=1.0),
+    "shell_cubic_f32": HealpixCase("cubic3d", 3, np.float32, 32, shell_radius=0.9),
+}
+
+
 def load_luts():
     return dict(np.load(os.path.join(GOLDEN, "luts.npz")))
 

@@ -69,6 +69,13 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"render_{name}.npz"), image=img)
         print(name, img.shape, float(np.nansum(img)))
 
+    for name, case in cases.HEALPIX_CASES.items():
+        a = case.make()
+        kern = ref.LutKernel(luts[case.lut], case.h_power)
+        img = ref.render_spherical_image_core(*case.args(a, kern))
+        np.savez_compressed(os.path.join(HERE, f"healpix_{name}.npz"), image=img)
+        print(name, img.shape, float(np.nansum(img)))
+
 
 if __name__ == "__main__":
     main()

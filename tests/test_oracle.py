@@ -157,3 +157,16 @@ def test_particles_in_sphere_vs_bruteforce(npart, offset, radius, dtype):   # kd
     p[p < -0.5] += 1.0
     want = np.where(np.sqrt((p.astype(dtype) ** 2).sum(axis=1)) < radius)[0]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", list(cases.HEALPIX_CASES))
+def test_healpix_oracle_matches_reference_golden(name, luts):
+    """sph/_render.pyx:51-179 + sph/healpix.c restated: bit-exact against the reference-generated golden."""
+    case = cases.HEALPIX_CASES[name]
+    gold = cases.load_golden("healpix", name)["image"]
+    kern = ref.LutKernel(luts[case.lut], case.h_power)
+    img = oracle.render_spherical_image_core(*case.args(case.make(), kern))
+    assert img.dtype == np.float32 and img.shape == (12 * case.nside ** 2,)
+    assert np.array_equal(img, gold)
+    with pytest.raises(ValueError):
+        oracle.render_spherical_image_core(*case.args(case.make(), kern)[:7], 12, kern)      # nside not a power of 2
