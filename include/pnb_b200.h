@@ -185,18 +185,29 @@ int pnb_render_healpix(const pnb_render_arrays *a, int nside,
                        const float *lut, int n_lut, int h_power, double max_d,
                        double shell_radius, float *out, int out_mem);
 
+/* ---- filt.geometry_selection.selection (pynbody/filt/geometry_selection.pyx:31-103, .hpp:3-119) ----
+ * Tree-less sphere / cuboid selection over a C-contiguous [n][3] position array of `dtype`, in host or
+ * device memory.  params: (x0,y0,z0,r_max) for PNB_REGION_SPHERE, (x0,y0,z0,x1,y1,z1) for PNB_REGION_CUBE,
+ * each cast to `dtype` as the reference casts them; wrap > 0 selects the periodic variant (box size, cast
+ * to `dtype`).  out: uint8[n], 1 = inside (strict inequalities, arithmetic in `dtype`, bit-identical to
+ * the reference).  PNB_ERR_VALUE for a wrong parameter count or an unknown region. */
+#define PNB_REGION_SPHERE 0
+#define PNB_REGION_CUBE   1
+int pnb_select_region(const void *pos, int64_t n, int dtype, int mem, int region, const double *params,
+                      int n_params, double wrap, uint8_t *out, int out_mem);
+
 /* Return the device memory the library keeps cached for re-use (freed work buffers) to the driver. */
 void pnb_release_cached_memory(void);
 
 /* ---- timing hooks (bench.py) ------------------------------------------------------------------
  * Device time in milliseconds of the kernels launched by the last pnb_tree_create (stage 0),
- * pnb_populate / pnb_knn (stage 1) or render call (stage 2) on this thread, measured with CUDA
+ * pnb_populate / pnb_knn (stage 1), render call (stage 2) or pnb_select_region (stage 3) on this thread, measured with CUDA
  * events on the library's stream; also the number of kernel launches of that call. */
 double pnb_last_device_ms(int stage);
 int64_t pnb_last_launch_count(int stage);
 /* Duration (ms, CUDA events on the launching stream) of the last launch of one of the dominant
  * kernels on this thread: 0 = kNN (+fused density) kernel, 1 = gather/reduction kernel,
- * 2 = image/grid render kernel.  This is what bench.py's roofline block divides by. */
+ * 2 = image/grid render kernel, 3 = region selection kernel.  This is what bench.py's roofline block divides by. */
 double pnb_last_kernel_ms(int which);
 /* cumulative number of kernel launches issued by this thread through the library */
 int64_t pnb_total_launches(void);

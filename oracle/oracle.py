@@ -217,3 +217,49 @@ def render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell
                          _p(h), f(h), int(nside), _p(lut), len(lut), int(kernel.h_power), float(kernel.max_d),
                          float(shell_radius), _p(out))
     return out
+
+
+def selection(pos_ar, region, parameters, wrap):
+    """filt.geometry_selection.selection (pynbody/filt/geometry_selection.pyx:31-103) restated in numpy.
+
+    Element-wise numpy arithmetic in the array's own dtype performs exactly the reference's operations
+    (geometry_selection.hpp:11-28 offsets and wrap, :47-62 sphere, :64-77 cuboid), one IEEE operation
+    at a time, so the flags are bit-identical; pinned against the compiled reference module in
+    tests/test_oracle.py."""
+    if not isinstance(pos_ar, np.ndarray) or pos_ar.dtype not in (np.float32, np.float64) or pos_ar.ndim != 2:
+        raise TypeError("No matching signature found")
+    out = np.empty(len(pos_ar), np.uint8)
+    if len(pos_ar) == 0:
+        return out
+    if pos_ar.shape[1] != 3 or pos_ar.strides != (3 * pos_ar.itemsize, pos_ar.itemsize):
+        raise ValueError("Input array must be C-contiguous and have 3 columns")
+    T = pos_ar.dtype.type
+    wrap = T(wrap)
+    half = wrap / T(2)
+
+    def offsets(centre):
+        ds = []
+        for c in range(3):
+            d = pos_ar[:, c] - centre[c]
+            if wrap > 0:
+                d = np.where(d > half, d - wrap, d)
+                d = np.where(d < -half, d + wrap, d)
+            ds.append(d)
+        return ds
+
+    if region == "sphere":
+        if len(parameters) != 4:
+            raise ValueError("Sphere selection requires 4 parameters: (x0, y0, z0, r_max)")
+        x0, y0, z0, r = (T(p) for p in parameters)
+        dx, dy, dz = offsets((x0, y0, z0))
+        out[:] = (dx * dx + dy * dy) + dz * dz < r * r
+    elif region == "cube":
+        if len(parameters) != 6:
+            raise ValueError("Cube selection requires 6 parameters: (x0, y0, z0, x1, y1, z1)")
+        x0, y0, z0, x1, y1, z1 = (T(p) for p in parameters)
+        two = T(2)
+        dx, dy, dz = offsets(((x0 + x1) / two, (y0 + y1) / two, (z0 + z1) / two))
+        out[:] = (np.abs(dx) < (x1 - x0) / two) & (np.abs(dy) < (y1 - y0) / two) & (np.abs(dz) < (z1 - z0) / two)
+    else:
+        raise ValueError("Region must be either 'sphere' or 'cube'")
+    return out

@@ -248,3 +248,16 @@ def render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell
     (pynbody/sph/renderers.py:720-766)."""
     _load()
     return _render.render_spherical_image_core(rho, mass, qty, x, y, z, h, nside, kernel, shell_radius)
+
+
+def selection(pos_ar, region, parameters, wrap):
+    """The reference's compiled ``pynbody.filt.geometry_selection.selection``
+    (pynbody/filt/geometry_selection.pyx:31-103), built by oracle/Makefile into ``_ref/pnbref/filt``."""
+    if not os.path.isdir(os.path.join(_REF, "pnbref")):
+        raise ImportError("oracle/_ref/pnbref not built: run `make -C oracle ref` where /root/reference exists")
+    sys.path.insert(0, _REF)
+    try:
+        from pnbref.filt import geometry_selection  # type: ignore
+    finally:
+        sys.path.remove(_REF)
+    return geometry_selection.selection(pos_ar, region, parameters, wrap)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "pnb_render_grid": (_i32, [_i32, _i32, _i32, C.POINTER(RenderArrays)] + [_dbl] * 8
                         + [_vp, _i32, _i32, _dbl, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32]),
     "pnb_render_healpix": (_i32, [C.POINTER(RenderArrays), _i32, _vp, _i32, _i32, _dbl, _dbl, _vp, _i32]),
+    "pnb_select_region": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _dbl, _vp, _i32]),
     "pnb_release_cached_memory": (None, []),
     "pnb_last_device_ms": (_dbl, [_i32]),
     "pnb_last_launch_count": (_i64, [_i32]),

@@ -12,6 +12,7 @@ import os
 _defaults = {
     "number_of_threads": os.cpu_count() or 1,   # [general] number_of_threads=-1 -> cpu count (no-op on GPU)
     "image-default-resolution": 1000,
+    "image-default-nside": 64,
     "sph": {
         "smooth-particles": 32,
         "tree-leafsize": 16,

@@ -12,8 +12,8 @@ namespace pnb {
 
 static thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
-static thread_local double g_stage_ms[3] = {0, 0, 0};
-static thread_local int64_t g_stage_launches[3] = {0, 0, 0};
+static thread_local double g_stage_ms[4] = {0, 0, 0, 0};
+static thread_local int64_t g_stage_launches[4] = {0, 0, 0, 0};
 
 void set_last_error(const std::string &m) { g_error = m; }
 void record_stage(int stage, double ms, int64_t launches)
@@ -22,7 +22,7 @@ void record_stage(int stage, double ms, int64_t launches)
     g_stage_launches[stage] = launches;
 }
 
-static thread_local double g_kernel_ms[3] = {0, 0, 0};
+static thread_local double g_kernel_ms[4] = {0, 0, 0, 0};
 void set_kernel_ms(int which, double ms) { g_kernel_ms[which] = ms; }
 KernelTimer::KernelTimer(int w, cudaStream_t s) : which(w), stream(s)
 {
@@ -561,9 +561,9 @@ int pnb_ball_query(pnb_tree *h, double cx, double cy, double cz, double r, doubl
 
 void pnb_release_cached_memory(void) { cache_trim(); }
 
-double pnb_last_device_ms(int stage) { return (stage >= 0 && stage < 3) ? g_stage_ms[stage] : 0.0; }
+double pnb_last_device_ms(int stage) { return (stage >= 0 && stage < 4) ? g_stage_ms[stage] : 0.0; }
 int64_t pnb_total_launches(void) { return g_launches; }
-double pnb_last_kernel_ms(int which) { return (which >= 0 && which < 3) ? g_kernel_ms[which] : 0.0; }
-int64_t pnb_last_launch_count(int stage) { return (stage >= 0 && stage < 3) ? g_stage_launches[stage] : 0; }
+double pnb_last_kernel_ms(int which) { return (which >= 0 && which < 4) ? g_kernel_ms[which] : 0.0; }
+int64_t pnb_last_launch_count(int stage) { return (stage >= 0 && stage < 4) ? g_stage_launches[stage] : 0; }
 
 }  // extern "C"

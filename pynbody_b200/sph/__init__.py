@@ -119,42 +119,139 @@ def _columns(pos):
     return pos[:, 0], pos[:, 1], pos[:, 2]
 
 
+class RenderPipelineLogicError(RuntimeError):
+    """Inconsistent combination of projection / weighting / denoising (renderers.py:42-43)."""
+
+
+def _ones_like(a):
+    from .. import _lib
+    if _lib._is_torch(a):
+        import torch
+        return torch.ones_like(a)
+    return np.ones_like(np.asarray(a))
+
+
+def _divide(num, den):
+    from .. import _lib
+    if _lib._is_torch(num):
+        return num / den
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return num / den
+
+
+def _multipass(render_one, quantity, projected, weight, denoise):
+    """The two-pass decorators of the reference's render pipeline, in the order make_render_pipeline applies
+    them (renderers.py:985-992):
+
+    * ``weight`` (True = volume weighting, or an array): projected average
+      ``render(q * w, projected) / render(w, projected)`` -- ProjectionAverageImageRenderer (renderers.py:508-556);
+    * ``denoise``: ``render(q) / render(ones)`` for slices and grids -- DenoisedImageRenderer (renderers.py:488-506).
+
+    ``render_one(quantity, projected)`` performs one native render."""
+    if weight is not None and weight is not False:
+        if projected:
+            raise RenderPipelineLogicError("Cannot take a projected average of an already projected image.")
+        w = _ones_like(quantity) if weight is True else weight
+        if len(w) != len(quantity):
+            raise ValueError("Weighting array must have the same length as the snapshot")
+        if denoise:
+            raise RenderPipelineLogicError("Denoising not supported with projected images")
+        return _divide(render_one(quantity * w, True), render_one(w, True))
+    if denoise:
+        if projected:
+            raise RenderPipelineLogicError("Denoising not supported with projected images")
+        return _divide(render_one(quantity, False), render_one(_ones_like(quantity), False))
+    return render_one(quantity, projected)
+
+
 def render_image(pos, mass, rho, smooth, quantity=None, width=None, resolution=None, nx=None, ny=None, kernel=None,
                  projected=True, z_plane=0.0, z_camera=None, smooth_range=(0.0, np.inf), smooth_floor=0.0,
-                 restrict_depth=False, boxsize=None, geometry=None):
+                 restrict_depth=False, boxsize=None, geometry=None, weight=None, denoise=False):
     """SPH image of ``quantity`` (default: the density) -- ImageRenderer.render + _call_c_renderer
     (renderers.py:650-697).  ``projected=True`` integrates along z with the 2-D kernel; otherwise a slice at
-    ``z_plane``.  Always the exact renderer (the reference's ``approximate_fast=False``)."""
+    ``z_plane``.  ``weight`` / ``denoise`` add the reference's two-pass decorators (see :func:`_multipass`;
+    ``weight`` needs ``projected=False`` as its passes are projections themselves).  Always the exact renderer
+    (the reference's ``approximate_fast=False``)."""
     g = geometry or ImageGeometry(width if width is not None else 200.0, resolution)
     if geometry is None:
         g.set_pixels(nx, ny)
         g.z_plane, g.z_camera = z_plane, z_camera
         if restrict_depth:
             g.restrict_z_range()
-    k = kernels.create_kernel(kernel)
-    if projected:
-        k = k.projection()
-    q = rho if quantity is None else quantity
+    k3 = kernels.create_kernel(kernel)
+    k2 = None
     x, y, z = _columns(pos)
-    return _render.render_image(g.nx, g.ny, x, y, z, smooth, g.x1, g.x2, g.y1, g.y2, g.z_camera or 0.0, g.z_plane,
-                                q, mass, rho, smooth_range[0], smooth_range[1], g.z1, g.z2, smooth_floor, k,
-                                wrapping_repeat_array(g.x1, g.x2, boxsize), wrapping_repeat_array(g.y1, g.y2, boxsize))
+    wx, wy = wrapping_repeat_array(g.x1, g.x2, boxsize), wrapping_repeat_array(g.y1, g.y2, boxsize)
+
+    def one(q, proj):
+        nonlocal k2
+        if proj and k2 is None:
+            k2 = k3.projection()
+        return _render.render_image(g.nx, g.ny, x, y, z, smooth, g.x1, g.x2, g.y1, g.y2, g.z_camera or 0.0, g.z_plane,
+                                    q, mass, rho, smooth_range[0], smooth_range[1], g.z1, g.z2, smooth_floor,
+                                    k2 if proj else k3, wx, wy)
+
+    return _multipass(one, rho if quantity is None else quantity, projected, weight, denoise)
+
+
+def render_healpix(pos, mass, rho, smooth, quantity=None, nside=None, kernel=None, shell_distance=None, weight=None,
+                   denoise=False):
+    """Healpix (RING) SPH map around the origin -- HealpixRenderer (renderers.py:720-766).  By default the
+    line-of-sight projection per solid angle; with ``shell_distance`` the quantity sampled on a thin shell at
+    that radius with the 3-D kernel.  float32 ``(12 * nside**2,)``."""
+    if nside is None:
+        nside = config["image-default-nside"]
+    k3 = kernels.create_kernel(kernel)
+    k2 = None
+    x, y, z = _columns(pos)
+    is_shell = shell_distance is not None
+
+    def one(q, proj):
+        nonlocal k2
+        if proj and k2 is None:
+            k2 = k3.projection()
+        return _render.render_spherical_image_core(rho, mass, q, x, y, z, smooth, int(nside), k2 if proj else k3,
+                                                   float(shell_distance or 0.0))
+
+    # by default spherical images are projected onto the sky; a weighted map starts from an unprojected base
+    # and a thin shell is not a projection (renderers.py:946-960)
+    projected = not is_shell and not weight
+    return _multipass(one, rho if quantity is None else quantity, projected, weight, denoise)
 
 
 def render_3d_grid(pos, mass, rho, smooth, quantity=None, width=None, resolution=None, nx=None, ny=None, nz=None,
-                   kernel=None, smooth_range=(0.0, np.inf), boxsize=None, geometry=None):
+                   kernel=None, smooth_range=(0.0, np.inf), boxsize=None, geometry=None, denoise=False):
     """SPH interpolation onto a 3-D grid -- Grid3dRenderer (renderers.py:700-718): a cube of side ``width``
-    centred on the origin, float32 ``(nx, ny, nz)``."""
+    centred on the origin, float32 ``(nx, ny, nz)``; ``denoise`` divides by the grid of ones (renderers.py:488-506)."""
     g = geometry or ImageGeometry(width if width is not None else 200.0, resolution)
     if geometry is None:
         g.restrict_z_range()
         g.set_pixels(nx, ny, nz)
     k = kernels.create_kernel(kernel)
-    q = rho if quantity is None else quantity
     x, y, z = _columns(pos)
-    return _render.to_3d_grid(g.nx, g.ny, g.nz, x, y, z, smooth, g.x1, g.x2, g.y1, g.y2, g.z1, g.z2, q, mass, rho,
-                              smooth_range[0], smooth_range[1], k, wrapping_repeat_array(g.x1, g.x2, boxsize),
-                              wrapping_repeat_array(g.y1, g.y2, boxsize), wrapping_repeat_array(g.z1, g.z2, boxsize))
+    wraps = [wrapping_repeat_array(a, b, boxsize) for a, b in ((g.x1, g.x2), (g.y1, g.y2), (g.z1, g.z2))]
+
+    def one(q, proj):
+        return _render.to_3d_grid(g.nx, g.ny, g.nz, x, y, z, smooth, g.x1, g.x2, g.y1, g.y2, g.z1, g.z2, q, mass, rho,
+                                  smooth_range[0], smooth_range[1], k, *wraps)
+
+    return _multipass(one, rho if quantity is None else quantity, False, None, denoise)
+
+
+def render(pos, mass, rho, smooth, quantity=None, target="image", nside=None, shell_distance=None, **kwargs):
+    """Array-level counterpart of ``make_render_pipeline(...).render()`` (renderers.py:770-994): dispatch on
+    ``target`` ('image', 'volume' or 'healpix') with the reference's argument checks."""
+    if target not in ("image", "volume", "healpix"):
+        raise ValueError("Unknown render target; options are 'image', 'volume' or 'healpix'")
+    if nside is not None and target != "healpix":
+        raise ValueError("nside is only valid in combination with target='healpix'")
+    if shell_distance is not None and target != "healpix":
+        raise ValueError("shell_distance is only valid in combination with target='healpix'")
+    if target == "image":
+        return render_image(pos, mass, rho, smooth, quantity, **kwargs)
+    if target == "volume":
+        return render_3d_grid(pos, mass, rho, smooth, quantity, **kwargs)
+    return render_healpix(pos, mass, rho, smooth, quantity, nside=nside, shell_distance=shell_distance, **kwargs)
 
 
 to_3d_grid = render_3d_grid

@@ -162,6 +162,59 @@ HEALPIX_CASES = {
 }
 
 
+@dataclass
+class SelectCase:
+    """filt.geometry_selection.selection: region, parameters, wrap (<= 0: none), dtype."""
+    region: str
+    params: tuple
+    wrap: float
+    dtype: type
+    n: int = 20000
+    seed: int = 51
+    scale: float = 1.0          # positions uniform in [-scale/2, scale/2)^3
+
+    def make(self):
+        """Uniform positions plus points placed within a few ulps of the region's surface, where only
+        the reference's exact operation order gives the reference's answer."""
+        rng = np.random.default_rng(self.seed)
+        pos = rng.uniform(-0.5 * self.scale, 0.5 * self.scale, (self.n, 3))
+        m = self.n // 4
+        p = np.array(self.params, dtype=np.float64)
+        if self.region == "sphere":
+            d = rng.normal(size=(m, 3))
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            r = p[3] * (1.0 + rng.integers(-4, 5, m) * np.finfo(self.dtype).eps)
+            pos[:m] = p[:3] + d * r[:, None]
+        else:
+            lo, hi = p[:3], p[3:]
+            pts = rng.uniform(lo, hi, (m, 3))
+            ax = rng.integers(0, 3, m)
+            side = rng.integers(0, 2, m)
+            face = np.where(side == 0, lo[ax], hi[ax])
+            pts[np.arange(m), ax] = face * (1.0 + rng.integers(-4, 5, m) * np.finfo(self.dtype).eps)
+            pos[:m] = pts
+        if self.wrap > 0:       # fold into the box, some points exactly on +-wrap/2
+            pos = (pos + 0.5 * self.wrap) % self.wrap - 0.5 * self.wrap
+            pos[m:m + 8, 0] = 0.5 * self.wrap
+            pos[m + 8:m + 16, 1] = -0.5 * self.wrap
+        return np.ascontiguousarray(pos.astype(self.dtype))
+
+    def args(self, pos):
+        return (pos, self.region, self.params, self.dtype(self.wrap))
+
+
+SELECT_CASES = {
+    "sphere_f64": SelectCase("sphere", (0.1, -0.05, 0.02, 0.3), -1.0, np.float64),
+    "sphere_f32": SelectCase("sphere", (0.1, -0.05, 0.02, 0.3), -1.0, np.float32),
+    "sphere_wrap_f64": SelectCase("sphere", (0.45, -0.48, 0.4, 0.25), 1.0, np.float64),
+    "sphere_wrap_f32": SelectCase("sphere", (-0.49, 0.3, 0.5, 0.2), 1.0, np.float32),
+    "cube_f64": SelectCase("cube", (-0.2, -0.1, -0.3, 0.25, 0.3, 0.1), -1.0, np.float64),
+    "cube_f32": SelectCase("cube", (-0.2, -0.1, -0.3, 0.25, 0.3, 0.1), 0.0, np.float32),
+    "cube_wrap_f64": SelectCase("cube", (0.3, 0.35, -0.1, 0.7, 0.6, 0.2), 1.0, np.float64),
+    "cube_wrap_f32_big": SelectCase("cube", (20.0, -10.0, 30.0, 60.0, 25.0, 70.0), 100.0, np.float32, scale=100.0),
+}
+
+
 def load_luts():
     return dict(np.load(os.path.join(GOLDEN, "luts.npz")))
 

@@ -76,6 +76,11 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"healpix_{name}.npz"), image=img)
         print(name, img.shape, float(np.nansum(img)))
 
+    for name, case in cases.SELECT_CASES.items():
+        flags = ref.selection(*case.args(case.make()))
+        np.savez_compressed(os.path.join(HERE, f"select_{name}.npz"), flags=np.packbits(flags), count=int(flags.sum()))
+        print(name, flags.shape, int(flags.sum()))
+
 
 if __name__ == "__main__":
     main()

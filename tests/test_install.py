@@ -20,10 +20,16 @@ def fake_pynbody():
     rnd = types.ModuleType("fakenbody.sph._render")
     rnd.render_image = lambda *a: "cpu image"
     rnd.to_3d_grid = lambda *a: "cpu grid"
-    rnd.render_spherical_image_core = lambda *a: "healpix stays"
-    mods = {"fakenbody": root, "fakenbody.kdtree": kdt, "fakenbody.sph": sph, "fakenbody.sph._render": rnd}
+    rnd.render_spherical_image_core = lambda *a: "cpu healpix"
+    rnd.render_something_else = lambda *a: "stays"
+    filt = types.ModuleType("fakenbody.filt")
+    filt.__path__ = []
+    gsel = types.ModuleType("fakenbody.filt.geometry_selection")
+    gsel.selection = lambda *a: "cpu selection"
+    mods = {"fakenbody": root, "fakenbody.kdtree": kdt, "fakenbody.sph": sph, "fakenbody.sph._render": rnd,
+            "fakenbody.filt": filt, "fakenbody.filt.geometry_selection": gsel}
     sys.modules.update(mods)
-    root.kdtree, root.sph, sph._render = kdt, sph, rnd
+    root.kdtree, root.sph, sph._render, root.filt, filt.geometry_selection = kdt, sph, rnd, filt, gsel
     yield root
     for m in mods:
         sys.modules.pop(m, None)
@@ -38,7 +44,12 @@ def test_install_swaps_only_the_hot_path(fake_pynbody):
     assert fake_pynbody.kdtree.kdmain is kdmain and fake_pynbody.kdtree.KDTree is KDTree
     assert fake_pynbody.sph._render.render_image is _render.render_image
     assert fake_pynbody.sph._render.to_3d_grid is _render.to_3d_grid
-    assert fake_pynbody.sph._render.render_spherical_image_core() == "healpix stays"
+    assert fake_pynbody.sph._render.render_spherical_image_core is _render.render_spherical_image_core
+    assert fake_pynbody.sph._render.render_something_else() == "stays"
+    from pynbody_b200.filt import geometry_selection
+    assert fake_pynbody.filt.geometry_selection.selection is geometry_selection.selection
     assert fake_pynbody.config["sph"]["approximate-fast-images"] is False
     install.uninstall(fake_pynbody)
     assert (fake_pynbody.kdtree.kdmain, fake_pynbody.kdtree.KDTree, fake_pynbody.sph._render.render_image) == before
+    assert fake_pynbody.sph._render.render_spherical_image_core() == "cpu healpix"
+    assert fake_pynbody.filt.geometry_selection.selection() == "cpu selection"

@@ -170,3 +170,30 @@ def test_healpix_oracle_matches_reference_golden(name, luts):
     assert np.array_equal(img, gold)
     with pytest.raises(ValueError):
         oracle.render_spherical_image_core(*case.args(case.make(), kern)[:7], 12, kern)      # nside not a power of 2
+
+
+@pytest.mark.parametrize("name", list(cases.SELECT_CASES))
+def test_selection_oracle_matches_reference_golden(name):
+    """filt/geometry_selection.pyx:31-103 restated: flags bit-identical to the compiled reference's, on
+    inputs that include points within a few ulps of the surface and exactly on the wrap boundary."""
+    case = cases.SELECT_CASES[name]
+    gold = cases.load_golden("select", name)
+    flags = oracle.selection(*case.args(case.make()))
+    assert flags.dtype == np.uint8 and flags.shape == (case.n,)
+    assert int(flags.sum()) == int(gold["count"])
+    assert np.array_equal(np.packbits(flags), gold["flags"])
+    if ref.available():
+        assert np.array_equal(flags, ref.selection(*case.args(case.make())))
+
+
+def test_selection_oracle_errors_and_empty():
+    pos = np.zeros((4, 3))
+    with pytest.raises(ValueError, match="4 parameters"):
+        oracle.selection(pos, "sphere", (0, 0, 0), -1.0)
+    with pytest.raises(ValueError, match="6 parameters"):
+        oracle.selection(pos, "cube", (0, 0, 0, 1), -1.0)
+    with pytest.raises(ValueError, match="sphere' or 'cube"):
+        oracle.selection(pos, "disc", (0, 0, 0, 1), -1.0)
+    with pytest.raises(ValueError, match="C-contiguous"):
+        oracle.selection(np.zeros((4, 6))[:, ::2], "sphere", (0, 0, 0, 1), -1.0)
+    assert oracle.selection(np.zeros((0, 3)), "sphere", (0, 0, 0, 1), -1.0).shape == (0,)

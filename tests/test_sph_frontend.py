@@ -68,3 +68,75 @@ def test_frontend_smooth_rho_equal_oracle():
     assert np.array_equal(sm, ref.smooth(32))
     np.testing.assert_allclose(r, ref.rho(32), rtol=1e-5)
     assert np.array_equal(sph.smooth(pos, mass, boxsize=1.0), ref.smooth(32))     # config default: 32 neighbours
+
+
+def test_multipass_argument_checks():
+    """The reference's pipeline logic errors (renderers.py:488-521, 939-944) -- raised before any native call."""
+    n = 8
+    pos, one = np.zeros((n, 3)), np.ones(n)
+    with pytest.raises(sph.RenderPipelineLogicError, match="already projected"):
+        sph.render_image(pos, one, one, one, one, width=1.0, resolution=4, projected=True, weight=True)
+    with pytest.raises(sph.RenderPipelineLogicError, match="Denoising not supported"):
+        sph.render_image(pos, one, one, one, one, width=1.0, resolution=4, projected=True, denoise=True)
+    with pytest.raises(sph.RenderPipelineLogicError, match="Denoising not supported"):
+        sph.render_image(pos, one, one, one, one, width=1.0, resolution=4, projected=False, weight=True, denoise=True)
+    with pytest.raises(ValueError, match="same length"):
+        sph.render_image(pos, one, one, one, one, width=1.0, resolution=4, projected=False, weight=np.ones(3))
+    with pytest.raises(ValueError, match="nside is only valid"):
+        sph.render(pos, one, one, one, target="image", nside=8)
+    with pytest.raises(ValueError, match="shell_distance is only valid"):
+        sph.render(pos, one, one, one, target="volume", shell_distance=1.0)
+    with pytest.raises(ValueError, match="Unknown render target"):
+        sph.render(pos, one, one, one, target="cube")
+
+
+@pytest.mark.gpu
+def test_weighted_denoised_and_healpix_pipelines():
+    """ProjectionAverageImageRenderer / DenoisedImageRenderer / HealpixRenderer compositions
+    (renderers.py:488-556, 720-766) against the same compositions of oracle renders."""
+    from oracle import oracle
+    from pynbody_b200.sph import kernels
+    rng = np.random.default_rng(4)
+    n = 20000
+    pos = rng.uniform(-0.5, 0.5, (n, 3))
+    sm = rng.lognormal(np.log(0.03), 0.4, n)
+    mass = np.full(n, 1.0 / n)
+    rho = rng.uniform(0.5, 2.0, n)
+    temp = rng.uniform(1.0, 2.0, n)
+    k3 = kernels.CubicSplineKernel()
+    k2 = k3.projection()
+    x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+
+    def ora(q, kern, z0=0.0):
+        return oracle.render_image(64, 64, x, y, z, sm, -0.5, 0.5, -0.5, 0.5, 0.0, z0, q, mass, rho, 0.0, np.inf, -np.inf,
+                                   np.inf, 0.0, kern, [0.0], [0.0])
+
+    # rho-weighted projected average of temp
+    img = sph.render_image(pos, mass, rho, sm, temp, width=1.0, resolution=64, kernel=k3, projected=False, weight=rho)
+    want = ora(temp * rho, k2) / ora(rho, k2)
+    np.testing.assert_allclose(img, want, rtol=2e-4)
+    assert 1.0 < np.nanmin(img) and np.nanmax(img) < 2.0
+    # volume-weighted
+    img = sph.render(pos, mass, rho, sm, temp, target="image", width=1.0, resolution=64, kernel=k3, projected=False, weight=True)
+    np.testing.assert_allclose(img, ora(temp, k2) / ora(np.ones(n), k2), rtol=2e-4)
+    # denoised slice
+    img = sph.render_image(pos, mass, rho, sm, temp, width=1.0, resolution=64, kernel=k3, projected=False, z_plane=0.05,
+                           denoise=True)
+    np.testing.assert_allclose(img, ora(temp, k3, 0.05) / ora(np.ones(n), k3, 0.05), rtol=2e-4)
+    # denoised grid
+    grid = sph.render(pos, mass, rho, sm, temp, target="volume", width=1.0, resolution=16, kernel=k3, denoise=True)
+    g = lambda q: oracle.to_3d_grid(16, 16, 16, x, y, z, sm, -0.5, 0.5, -0.5, 0.5, -0.5, 0.5, q, mass, rho, 0.0, np.inf, k3,
+                                    [0.0], [0.0], [0.0])
+    np.testing.assert_allclose(grid, g(temp) / g(np.ones(n)), rtol=2e-4)
+    # healpix: particles on a thick shell, projection and thin shell
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    hp_pos = d * rng.uniform(0.7, 1.3, n)[:, None]
+    hx, hy, hz = hp_pos[:, 0], hp_pos[:, 1], hp_pos[:, 2]
+    got = sph.render(hp_pos, mass, rho, sm, temp, target="healpix", nside=16, kernel=k3)
+    want = oracle.render_spherical_image_core(rho, mass, temp, hx, hy, hz, sm, 16, k2)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6 * want.max())
+    got = sph.render_healpix(hp_pos, mass, rho, sm, temp, nside=16, kernel=k3, shell_distance=1.0)
+    want = oracle.render_spherical_image_core(rho, mass, temp, hx, hy, hz, sm, 16, k3, 1.0)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6 * want.max())
+    assert sph.render_healpix(hp_pos, mass, rho, sm, nside=None, kernel=k3).shape == (12 * 64 * 64,)
