@@ -30,6 +30,12 @@
 #include "traverse.cuh"
 
 namespace pnb {
+#ifdef KNN_STATS
+__device__ unsigned long long g_stats[8];
+#define STAT(i, v) do { if (lane == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define STAT(i, v)
+#endif
 
 constexpr int KNN_WARPS = 2;
 constexpr int MAXLOG = 10;              // k <= 1024
@@ -141,7 +147,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
     q.lo[e * 32] = vlo;
     if (WITH_IDX) q.hi[e * 32] = id;
     const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;
-    int si[NL > 0 ? NL : 1];
+    int si[NL > 0 ? NL : 1], win[NL > 0 ? NL : 1];
     uint32_t sk[NL > 0 ? NL : 1];
     if (NL > 0) si[0] = e ^ 1;
 #pragma unroll
@@ -150,20 +156,39 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
 #pragma unroll
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) sk[l] = q.hd[si[l] * 32];
-    uint32_t ck = vhi, clo = vlo;
+    // the path is replayed on the high words alone, without branches; equal high words anywhere on the
+    // path (rare) send the lane through the exact replay below
+    uint32_t ck = vhi;
     int ce = e;
-    bool clo_known = true;                          // low word of the current path winner is in a register
+    bool tie = false;
 #pragma unroll
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) {
-            bool gt = sk[l] > ck;
-            if (sk[l] == ck) {                      // equal high words (rare): decide on the exact values
-                if (!clo_known) { clo = q.lo[ce * 32]; clo_known = true; }
-                gt = q.lo[si[l] * 32] > clo;
-            }
-            if (gt) { ck = sk[l]; ce = si[l]; clo_known = false; }
-            q.W[(node >> (l + 1)) * 32] = (W_t)ce;
+            const bool gt = sk[l] > ck;
+            tie |= sk[l] == ck;
+            ck = gt ? sk[l] : ck;
+            ce = gt ? si[l] : ce;
+            win[l] = ce;
         }
+    uint32_t clo = vlo;
+    bool clo_known = ce == e;                       // low word of the path winner is in a register
+    if (tie) {
+        ck = vhi; clo = vlo; ce = e; clo_known = true;
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+            if (LOGC >= 0 || l < q.LOG) {
+                bool gt = sk[l] > ck;
+                if (sk[l] == ck) {                  // decide on the exact 64-bit values
+                    if (!clo_known) { clo = q.lo[ce * 32]; clo_known = true; }
+                    gt = q.lo[si[l] * 32] > clo;
+                }
+                if (gt) { ck = sk[l]; ce = si[l]; clo_known = false; }
+                win[l] = ce;
+            }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+        if (LOGC >= 0 || l < q.LOG) q.W[(node >> (l + 1)) * 32] = (W_t)win[l];
     q.top_hi = ck;
     q.top_lo = clo;
     q.lo_known = clo_known;
@@ -171,9 +196,59 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
     q.etop = ce;
 }
 
+// ---- start of a search: the first k candidates go straight into the leaves, then the tree is built once ----
+__device__ __forceinline__ void leaf_store(Queue<float, uint8_t> &q, int e, float d2) { q.hd[e * 32] = d2; }
+__device__ __forceinline__ void leaf_store(Queue<float, uint16_t> &q, int e, float d2) { q.hd[e * 32] = d2; }
+template <typename W_t>
+__device__ __forceinline__ void leaf_store(Queue<double, W_t> &q, int e, double d2)
+{
+    q.hd[e * 32] = (uint32_t)__double2hiint(d2);
+    q.lo[e * 32] = (uint32_t)__double2loint(d2);
+}
+// does leaf a hold a larger value than leaf b?  (exact)
+__device__ __forceinline__ bool leaf_greater(const Queue<float, uint8_t> &q, int a, int b) { return q.hd[a * 32] > q.hd[b * 32]; }
+__device__ __forceinline__ bool leaf_greater(const Queue<float, uint16_t> &q, int a, int b) { return q.hd[a * 32] > q.hd[b * 32]; }
+template <typename W_t>
+__device__ __forceinline__ bool leaf_greater(const Queue<double, W_t> &q, int a, int b)
+{
+    const uint32_t ka = q.hd[a * 32], kb = q.hd[b * 32];
+    if (ka != kb) return ka > kb;
+    return q.lo[a * 32] > q.lo[b * 32];
+}
+__device__ __forceinline__ void set_top_from_leaf(Queue<float, uint8_t> &q, int e) { q.top = q.hd[e * 32]; q.etop = e; }
+__device__ __forceinline__ void set_top_from_leaf(Queue<float, uint16_t> &q, int e) { q.top = q.hd[e * 32]; q.etop = e; }
+template <typename W_t>
+__device__ __forceinline__ void set_top_from_leaf(Queue<double, W_t> &q, int e)
+{
+    q.top_hi = q.hd[e * 32];
+    q.lo_known = false;
+    q.top = __hiloint2double((int)q.top_hi, -1);
+    q.etop = e;
+}
+
+// play every match of the tournament once (K2 - 1 comparisons); leaves [k, K2) hold the smallest key
+template <typename T, typename W_t, int LOGC>
+__device__ __forceinline__ void queue_build(Queue<T, W_t> &q)
+{
+    const int K2 = LOGC >= 0 ? (1 << LOGC) : q.K2;
+    if (K2 == 1) { set_top_from_leaf(q, 0); return; }
+#pragma unroll 4
+    for (int node = K2 - 1; node >= K2 / 2; --node) {      // parents of leaves
+        const int a = 2 * node - K2, b = a + 1;
+        q.W[node * 32] = (W_t)(leaf_greater(q, b, a) ? b : a);
+    }
+#pragma unroll 4
+    for (int node = K2 / 2 - 1; node >= 1; --node) {
+        const int a = (int)q.W[2 * node * 32], b = (int)q.W[(2 * node + 1) * 32];
+        q.W[node * 32] = (W_t)(leaf_greater(q, b, a) ? b : a);
+    }
+    set_top_from_leaf(q, (int)q.W[32]);
+}
+
 template <typename T, typename W_t, int LOGC, bool WITH_IDX>
 __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t bucket, bool pass, T sx, T sy, T sz,
-                                                 Queue<T, W_t> &q, T *tile, int lane, bool wide, T qx, T qy, T qz)
+                                                 Queue<T, W_t> &q, T *tile, int lane, bool wide, T qx, T qy, T qz,
+                                                 int &filled, int k, bool active)
 {
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -184,6 +259,25 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
         tile[64 + lane] = tv.z[start + lane];
     }
     __syncwarp();
+    unsigned done = 0;                              // candidates consumed by the fill below
+    if (filled >= 0) {
+        // the queue is not full yet (warp-uniform: nothing is pruned while the k-th distance is infinite, so
+        // every lane has seen the same candidates): store the distances into the next leaves
+        const int take = min(cnt, k - filled);
+        for (int j = 0; j < take; ++j) {
+            const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
+                              : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
+            leaf_store(q, filled + j, d2);
+            if (WITH_IDX) q.hi[(filled + j) * 32] = start + j;
+        }
+        filled += take;
+        if (filled < k) return;
+        queue_build<T, W_t, LOGC>(q);
+        filled = -1;
+        if (!active) { q.top = (T)-1; q.top_hi = 0u; q.top_lo = 0u; q.lo_known = true; }   // idle lanes never match
+        if (take == cnt) return;
+        done = (1u << take) - 1u;
+    }
     // phase A: all candidates against this lane's query, branch-free
     unsigned mask = 0;
     const T top0 = q.top;
@@ -199,16 +293,33 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             mask |= (unsigned)(sizeof(T) == 8 ? d2 <= top0 : d2 < top0) << j;
         }
     }
+    mask &= ~done;
     if (!pass) mask = 0;
+#ifdef KNN_STATS
+    {
+        unsigned tot = __popc(mask);
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+        STAT(0, 1);            // buckets visited
+        STAT(1, tot);          // survivors (lane sum)
+    }
+#endif
     // phase B: all lanes insert their survivors together
     while (__any_sync(FULL, mask != 0)) {
+        STAT(2, 1);            // rounds
+        bool ins = false;
         if (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
                               : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (below_top(q, d2)) queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, start + j);
+            if (below_top(q, d2)) { queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, start + j); ins = true; }
         }
+#ifdef KNN_STATS
+        unsigned b = __ballot_sync(FULL, ins);
+        STAT(3, __popc(b));    // inserts (lane sum)
+        STAT(4, b != 0);       // rounds with at least one insert
+#endif
+        (void)ins;
     }
 }
 
@@ -220,10 +331,9 @@ __host__ __device__ inline size_t knn_smem_per_warp(int K2)
     return (b + 127) & ~(size_t)127;
 }
 
-// start-of-search state: k "real" leaves hold distinct huge keys in decreasing order (so the leftmost leaf
-// wins everywhere and no two keys tie), padding leaves [k,K2) hold the smallest key
-__device__ __forceinline__ float init_key(float, int e, int k) { return e < k ? 3.0e38f - 1.0e32f * (float)e : -1.0f; }
-__device__ __forceinline__ uint32_t init_key(double, int e, int k) { return e < k ? 0x7fe00000u - (uint32_t)e : 0u; }
+// padding leaves [k, K2) hold the smallest key; until k candidates have been seen the k-th distance is "+inf"
+__device__ __forceinline__ float init_key(float, int, int) { return -1.0f; }
+__device__ __forceinline__ uint32_t init_key(double, int, int) { return 0u; }
 __device__ __forceinline__ float init_top(float) { return 3.0e38f; }
 __device__ __forceinline__ double init_top(double) { return __hiloint2double(0x7fe00000, 0); }
 
@@ -246,7 +356,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     if (WITH_IDX) { q.hi = reinterpret_cast<int32_t *>(after) + lane; after += (size_t)K2 * 32 * 4; }
     q.W = reinterpret_cast<W_t *>(after) + lane;
     after += (size_t)K2 * 32 * sizeof(W_t);
-    T *tile = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(after) + 15) & ~(uintptr_t)15);
+    T *tile = reinterpret_cast<T *>(after);       // 16-byte aligned: every array above is a multiple of 32 bytes
     q.lo = a.lo_scratch ? a.lo_scratch + ((size_t)blockIdx.x * warps + wib) * (size_t)K2 * 32 + lane : nullptr;
     const T L = tv.period;
 
@@ -263,25 +373,21 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         T qx = 0, qy = 0, qz = 0;
         if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
 
-        for (int e = 0; e < K2; ++e) {
+        for (int e = k; e < K2; ++e) {              // padding leaves hold the smallest key and never win
             q.hd[e * 32] = init_key(T(), e, k);
             if (sizeof(T) == 8) q.lo[e * 32] = 0u;
             if (WITH_IDX) q.hi[e * 32] = -1;
         }
-        for (int node = 1; node < K2; ++node) {
-            int lv = 31 - __clz(node);              // depth of the node; its sub-tree spans K2 >> lv leaves
-            q.W[node * 32] = (W_t)((node - (1 << lv)) << (LOG - lv));
-        }
+        int filled = 0;                             // leaves filled so far; -1 once the tournament has been built
         q.etop = 0;
         q.top = init_top(T());                      // "+inf" until k are held (pq.h:185-192)
         q.top_hi = 0x7fe00000u; q.top_lo = 0u; q.lo_known = true;
-        if (!active) { q.top = (T)-1; q.top_hi = 0u; }   // idle lanes never match
 
         // own bucket first (smooth.h:200-208): the query lies inside its bounds, so no shift applies
         {
             const bool amb = active && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, tv.nsplit + bucket), qx, qy, qz, L);
             knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, bucket, active, qx, qy, qz, q, tile, lane,
-                                                     PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+                                                     PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
         }
 
         // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
@@ -291,6 +397,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
             const int64_t stop = next_node(cp);
             for (;;) {
                 Box6<T> b = load_box(tv.box, cp);
+                STAT(5, 1);    // nodes tested
                 T sx, sy, sz;
                 T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
                 // (top * slack overflows to +inf while the queue still holds its initial huge keys; empty
@@ -300,7 +407,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                     if (cp < tv.nsplit) { cp = 2 * cp; continue; }
                     const bool amb = pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L);
                     knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
-                                                             PERIODIC && __any_sync(FULL, amb), qx, qy, qz);
+                                                             PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
                 }
                 cp = next_node(cp);
                 if (cp == stop) break;
@@ -377,9 +484,20 @@ static void launch_knn_p(Tree &t, KnnArgs<T> &a)
         lo.alloc(sizeof(uint32_t) * (size_t)grid * warps * K2 * 32);
         a.lo_scratch = lo.as<uint32_t>();
     }
+#ifdef KNN_STATS
+    unsigned long long zero[8] = {0};
+    PNB_CUDA(cudaMemcpyToSymbol(g_stats, zero, sizeof(zero)));
+#endif
     KernelTimer timer(0, t.stream);
     PNB_LAUNCH(kern, grid, warps * 32, smem, t.stream, a);
     timer.stop();
+#ifdef KNN_STATS
+    unsigned long long st[8];
+    PNB_CUDA(cudaMemcpyFromSymbol(st, g_stats, sizeof(st)));
+    const double nb = (double)t.nsplit;
+    fprintf(stderr, "[knn stats] per home bucket: visited %.1f  survivors/lane %.1f  rounds %.1f  inserts/lane %.1f  "
+            "rounds_with_insert %.1f  nodes %.1f\n", st[0] / nb, st[1] / nb / 32, st[2] / nb, st[3] / nb / 32, st[4] / nb, st[5] / nb);
+#endif
 }
 
 template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO>
