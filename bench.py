@@ -49,11 +49,12 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(dtype, n_side):
-    """DRAM bytes of one k_knn launch for this workload from the committed ncu capture (profiles/), or None."""
+def load_traffic(dtype, n_side, what=None):
+    """DRAM bytes of one k_knn launch for this workload from the committed ncu capture (profiles/), or None;
+    ``what`` selects another figure of the same capture (issue_active_pct, warp_inst_per_particle)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(f"{dtype}:{n_side}")
+            return json.load(f).get(f"{dtype}:{n_side}" + (f":{what}" if what else ""))
     except Exception:
         return None
 
@@ -332,8 +333,11 @@ def run_ours(args):
                      "kernel_ms": knn_kernel_ms,
                      "logical_gather_gbs": gather_bytes / (knn_kernel_ms * 1e-3) / 1e9,
                      "neighbour_interactions_per_s": n * K_NEIGHBOURS / (knn_kernel_ms * 1e-3),
-                     "note": "irregular tree search: bound by on-chip queue updates and L2 latency, not by HBM bytes "
-                             "(SURVEY.md 8d); traffic from ncu is in profiles/"},
+                     "ncu_issue_active_pct": load_traffic(args.dtype, args.n_side, "issue_active_pct"),
+                     "ncu_warp_inst_per_particle": load_traffic(args.dtype, args.n_side, "warp_inst_per_particle"),
+                     "note": "irregular tree search: bound by instruction issue (on-chip neighbour-queue updates), not by "
+                             "HBM bytes (SURVEY.md 8d); traffic and issue-slot utilisation from the committed ncu capture "
+                             "profiles/r1_knn_v6_summary.txt"},
         "stages_ms": {"build": float(np.mean(stats["build_ms"])), "smooth_incl_fused_rho": float(np.mean(stats["knn_ms"])),
                       "knn_kernel": knn_kernel_ms, "rho_readback": float(np.mean(stats["rho_ms"])), **extra},
         "render": render,

@@ -114,14 +114,14 @@ __device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v,
     const int e = q.etop;
     q.hd[e * 32] = v;
     if (WITH_IDX) q.hi[e * 32] = id;
-    const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;      // heap index of the leaf
+    const int K2c = LOGC >= 0 ? (1 << LOGC) : q.K2;              // heap index of leaf e is K2c + e
     int si[NL > 0 ? NL : 1];
     float sv[NL > 0 ? NL : 1];
     // sibling winners along the path: addresses depend only on e, so all loads go out together
     if (NL > 0) si[0] = e ^ 1;
 #pragma unroll
     for (int l = 1; l < NL; ++l)
-        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((node >> l) ^ 1) * 32];
+        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((K2c >> l) + ((e >> l) ^ 1)) * 32];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) sv[l] = q.hd[si[l] * 32];
@@ -131,7 +131,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v,
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) {
             if (sv[l] > cv) { cv = sv[l]; ce = si[l]; }
-            q.W[(node >> (l + 1)) * 32] = (W_t)ce;
+            q.W[((K2c >> (l + 1)) + (e >> (l + 1))) * 32] = (W_t)ce;
         }
     q.top = cv;
     q.etop = ce;
@@ -146,13 +146,13 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
     q.hd[e * 32] = vhi;
     q.lo[e * 32] = vlo;
     if (WITH_IDX) q.hi[e * 32] = id;
-    const int node = (LOGC >= 0 ? (1 << LOGC) : q.K2) + e;
+    const int K2c = LOGC >= 0 ? (1 << LOGC) : q.K2;
     int si[NL > 0 ? NL : 1], win[NL > 0 ? NL : 1];
     uint32_t sk[NL > 0 ? NL : 1];
     if (NL > 0) si[0] = e ^ 1;
 #pragma unroll
     for (int l = 1; l < NL; ++l)
-        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((node >> l) ^ 1) * 32];
+        if (LOGC >= 0 || l < q.LOG) si[l] = (int)q.W[((K2c >> l) + ((e >> l) ^ 1)) * 32];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
         if (LOGC >= 0 || l < q.LOG) sk[l] = q.hd[si[l] * 32];
@@ -188,7 +188,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
     }
 #pragma unroll
     for (int l = 0; l < NL; ++l)
-        if (LOGC >= 0 || l < q.LOG) q.W[(node >> (l + 1)) * 32] = (W_t)win[l];
+        if (LOGC >= 0 || l < q.LOG) q.W[((K2c >> (l + 1)) + (e >> (l + 1))) * 32] = (W_t)win[l];
     q.top_hi = ck;
     q.top_lo = clo;
     q.lo_known = clo_known;
