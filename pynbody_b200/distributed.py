@@ -118,30 +118,40 @@ class GpuBackend:
 # domain decomposition
 # ------------------------------------------------------------------------------------------------
 def _bisect(sample, weight, lo, hi, ranks, out):
-    """Recursive coordinate bisection of box [lo,hi) among `ranks`: split planes at the weighted quantiles
-    of the coordinate sample (numpy arrays on the host; weight = estimated search cost per particle)."""
+    """Recursive coordinate bisection of box [lo,hi) among `ranks`: split planes at the (weighted) quantiles
+    of the coordinate sample.  ``sample`` is a [3][m] tensor (one contiguous row per axis) that stays on the
+    device it was gathered on -- only the chosen axis and plane of each node come back to the host;
+    ``weight`` = estimated search cost per sample point, or None.  lo / hi are host tensors."""
     if len(ranks) == 1:
-        out[ranks[0]] = (lo.copy(), hi.copy())
+        out[ranks[0]] = (lo.clone(), hi.clone())
         return
     nleft = len(ranks) // 2
-    ext = sample.max(axis=0) - sample.min(axis=0) if len(sample) else hi - lo
-    axis = int(np.argmax(ext))
-    if len(sample) > 1 and weight is None:                  # equal weights: selection, not sorting
-        kth = min(len(sample) - 1, max(1, int(round(len(sample) * nleft / len(ranks)))))
-        q = np.partition(np.ascontiguousarray(sample[:, axis]), kth)[kth]
-    elif len(sample) > 1:
-        order = np.argsort(np.ascontiguousarray(sample[:, axis]))
-        cw = np.cumsum(weight[order])
-        i = int(np.searchsorted(cw, cw[-1] * nleft / len(ranks)))
-        q = sample[order[min(max(i, 1), len(sample) - 1)], axis]
+    m = int(sample.shape[1])
+    if m > 1:
+        ext = (sample.max(dim=1).values - sample.min(dim=1).values).tolist()
+        axis = max(range(3), key=lambda a: ext[a])
+        col = sample[axis]
+        if weight is None:                                  # equal weights: selection, not sorting
+            kth = min(m - 1, max(1, int(round(m * nleft / len(ranks)))))
+            q = torch.kthvalue(col, kth + 1).values
+        else:
+            order = torch.argsort(col)
+            cw = torch.cumsum(weight[order], 0)
+            i = int(torch.searchsorted(cw, cw[-1] * nleft / len(ranks)))
+            q = col[order[min(max(i, 1), m - 1)]]
+        left = col < q
+        q = q.to(lo.device, lo.dtype)
     else:
-        q = 0.5 * (lo[axis] + hi[axis]) if np.isfinite(lo[axis] + hi[axis]) else sample.dtype.type(0)
-    left = sample[:, axis] < q
-    hi_l, lo_r = hi.copy(), lo.copy()
+        ext = (hi - lo).tolist()
+        axis = max(range(3), key=lambda a: ext[a])
+        mid = 0.5 * (lo[axis] + hi[axis])
+        q = mid if bool(torch.isfinite(mid)) else torch.zeros((), dtype=lo.dtype)
+        left = sample[axis] < q.to(sample.device, sample.dtype)
+    hi_l, lo_r = hi.clone(), lo.clone()
     hi_l[axis] = q
     lo_r[axis] = q
-    _bisect(sample[left], None if weight is None else weight[left], lo, hi_l, ranks[:nleft], out)
-    _bisect(sample[~left], None if weight is None else weight[~left], lo_r, hi, ranks[nleft:], out)
+    _bisect(sample[:, left], None if weight is None else weight[left], lo, hi_l, ranks[:nleft], out)
+    _bisect(sample[:, ~left], None if weight is None else weight[~left], lo_r, hi, ranks[nleft:], out)
 
 
 # Optional cost feedback (PNB_DIST_COST_FEEDBACK=1): after a smoothing pass the ranks share how long their
@@ -159,16 +169,18 @@ def record_costs(world, domains, cost_per_particle):
 
 
 def _sample_weights(world, samp):
-    if world not in _COST_FIELD or not len(samp) or not os.environ.get("PNB_DIST_COST_FEEDBACK"):
+    """samp: [3][m] tensor; returns a weight per sample point or None."""
+    if world not in _COST_FIELD or not samp.shape[1] or not os.environ.get("PNB_DIST_COST_FEEDBACK"):
         return None
-    w = np.ones(len(samp))
-    if True:
-        doms, cost = _COST_FIELD[world]
-        if np.all(np.isfinite(cost)) and cost.min() > 0:
-            cost = np.clip(cost / cost.mean(), 0.5, 2.0)
-            for (lo, hi), c in zip(doms, cost):
-                inside = np.all((samp >= lo) & (samp < hi), axis=1)
-                w[inside] = c
+    w = torch.ones(samp.shape[1], dtype=torch.float64, device=samp.device)
+    doms, cost = _COST_FIELD[world]
+    if np.all(np.isfinite(cost)) and cost.min() > 0:
+        cost = np.clip(cost / cost.mean(), 0.5, 2.0)
+        for (lo, hi), c in zip(doms, cost):
+            lo_t = torch.as_tensor(lo, device=samp.device, dtype=samp.dtype)[:, None]
+            hi_t = torch.as_tensor(hi, device=samp.device, dtype=samp.dtype)[:, None]
+            inside = ((samp >= lo_t) & (samp < hi_t)).all(dim=0)
+            w[inside] = float(c)
     return w
 
 
@@ -197,18 +209,17 @@ def decompose(pos, boxsize, group=None, sample_per_rank=8192, seed=0):
         samp = torch.cat(allsamp)
         dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    samp = samp.cpu().numpy()
-    samp = samp[~np.isnan(samp[:, 0])]
-    mn, mx = mn.cpu().numpy(), mx.cpu().numpy()
+    samp = samp[~torch.isnan(samp[:, 0])].t().contiguous()          # [3][m]: one contiguous row per axis
+    mn, mx = mn.cpu(), mx.cpu()
     periodic = boxsize is not None and boxsize > 0 and bool(((mx - mn) <= boxsize).all())
     if periodic:
-        lo, hi = mn.copy(), mn + samp.dtype.type(boxsize)
+        lo, hi = mn.clone(), mn + torch.tensor(boxsize, dtype=dt)
     else:
-        lo = np.full(3, -np.inf, dtype=samp.dtype)
-        hi = np.full(3, np.inf, dtype=samp.dtype)
+        lo = torch.full((3,), float("-inf"), dtype=dt)
+        hi = torch.full((3,), float("inf"), dtype=dt)
     out = [None] * world
     _bisect(samp, _sample_weights(world, samp), lo, hi, list(range(world)), out)
-    return [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out], periodic
+    return out, periodic
 
 
 def owner_of(pos, domains):
@@ -297,7 +308,9 @@ class DistributedKDTree:
         self.requested_boxsize = boxsize
         if self.world > 1:
             owner = owner_of(pos, self.domains)
-            order = torch.argsort(owner, stable=True)
+            # one-byte keys: the stable radix sort needs a single pass instead of eight
+            key = owner.to(torch.uint8) if self.world <= 255 else owner
+            order = torch.sort(key, stable=True).indices
             counts = torch.bincount(owner, minlength=self.world).tolist()
             src_idx = order                                         # original local index of each sent particle
             self._ret_counts = counts                               # what I sent to each rank (returns come back so)

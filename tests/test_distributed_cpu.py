@@ -101,8 +101,9 @@ def test_decompose_is_balanced_and_tiles_the_box():
     # bisection of a sample into 8 boxes: disjoint, covering, balanced
     from pynbody_b200.distributed import _bisect
     out = [None] * 8
-    _bisect(pos, None, np.zeros(3), np.ones(3), list(range(8)), out)
-    out = [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out]
+    cols = tp.t().contiguous()                           # [3][m]
+    zero, one = torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)
+    _bisect(cols, None, zero, one, list(range(8)), out)
     owner = owner_of(tp, out)
     counts = torch.bincount(owner, minlength=8)
     assert counts.sum() == len(pos) and counts.min() > 0.9 * len(pos) / 8 and counts.max() < 1.1 * len(pos) / 8
@@ -112,8 +113,7 @@ def test_decompose_is_balanced_and_tiles_the_box():
     # there shrink so that every rank gets the same estimated work
     w = np.where(pos[:, 2] < 0.5, 2.0, 1.0)
     out2 = [None] * 8
-    _bisect(pos, w, np.zeros(3), np.ones(3), list(range(8)), out2)
-    out2 = [(torch.from_numpy(l), torch.from_numpy(h)) for l, h in out2]
+    _bisect(cols, torch.from_numpy(w), zero, one, list(range(8)), out2)
     owner2 = owner_of(tp, out2)
     work = np.array([w[(owner2 == r).numpy()].sum() for r in range(8)])
     assert work.min() > 0.9 * work.mean() and work.max() < 1.1 * work.mean()
