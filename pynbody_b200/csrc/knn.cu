@@ -278,14 +278,23 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
         if (take == cnt) return;
         done = (1u << take) - 1u;
     }
-    // phase A: all candidates against this lane's query, branch-free
+    // phase A, transposed: lane j holds candidate j; the queries the bucket is in reach of (typically a third
+    // of the lanes) are taken in turn, their shifted position and k-th distance broadcast by shuffle, and the
+    // 32 verdicts of one query come back as one ballot -- half the instructions of testing all 32 x 32 pairs
     unsigned mask = 0;
     const T top0 = q.top;
     if (!wide) {
-#pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            T d2 = dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            mask |= (unsigned)(sizeof(T) == 8 ? d2 <= top0 : d2 < top0) << j;     // (double: top0 is an upper bound)
+        const T cx = lane < cnt ? tile[lane] : (T)0, cy = lane < cnt ? tile[32 + lane] : (T)0,
+                cz = lane < cnt ? tile[64 + lane] : (T)0;
+        unsigned todo = __ballot_sync(FULL, pass);
+        while (todo) {
+            const int i = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const T ux = __shfl_sync(FULL, sx, i), uy = __shfl_sync(FULL, sy, i), uz = __shfl_sync(FULL, sz, i);
+            const T ut = __shfl_sync(FULL, top0, i);
+            const T d2 = dist2<T>(ux, uy, uz, cx, cy, cz);
+            const unsigned row = __ballot_sync(FULL, lane < cnt && (sizeof(T) == 8 ? d2 <= ut : d2 < ut));   // (double: an upper bound)
+            if (lane == i) mask = row;
         }
     } else {                                        // some lane's shift is ambiguous here: image per particle
         for (int j = 0; j < cnt; ++j) {
