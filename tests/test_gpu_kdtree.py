@@ -409,3 +409,76 @@ def test_large_k():
     kd.set_array_ref("smooth", sm)
     with pytest.raises(ValueError, match="too large"):
         kd.populate("hsm", 5000)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_full_size_box_properties(dtype):
+    """BASELINE.json's headline workload at full size (256^3 = 16 777 216 particles, clustered periodic box,
+    k = 64, float64, device-resident), checked through size-independent properties:
+
+    * exactness on a sample: for 256 random particles the k-th smallest minimum-image distance over ALL
+      particles (torch shortlist, then the reference's operation order in numpy) gives h bit for bit;
+    * permutation invariance: the same particles in a shuffled order give the same h bit for bit and the
+      same density to rounding (the tree, the buckets and the visit order all change);
+    * the fused density equals the density of the general gather pass (forced by non-uniform masses that are
+      equal to rounding) to 1e-12.
+    """
+    import torch
+    k, L = 64, 1.0
+    pos, _, mass = synth.zeldovich_box_device(256, 2, np.float64)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    pos, mass = pos.to(tdt).contiguous(), mass.to(tdt).contiguous()
+    rtol = 1e-12 if dtype == np.float64 else 2e-5
+    n = pos.shape[0]
+    assert n == 1 << 24
+
+    def run(p, m):
+        kd = _tree(p, m, L)
+        kd.set_kernel("WendlandC2Kernel")
+        sm = torch.empty(n, dtype=tdt, device="cuda")
+        rho = torch.empty_like(sm)
+        kd.set_array_ref("smooth", sm)
+        kd.populate("hsm", k)
+        kd.set_array_ref("mass", m)
+        kd.set_array_ref("rho", rho)
+        kd.populate("rho", k)
+        torch.cuda.synchronize()
+        return sm, rho
+
+    sm, rho = run(pos, mass)
+    assert bool(torch.isfinite(sm).all()) and bool((sm > 0).all()) and bool((rho > 0).all())
+
+    # exactness on a sample
+    g = torch.Generator(device="cpu").manual_seed(11)
+    sample = torch.randint(0, n, (256,), generator=g)
+    for i in sample.tolist():
+        d = pos - pos[i]
+        d = d - torch.round(d / L) * L                         # shortlist only: exact values follow below
+        cand = torch.topk((d * d).sum(dim=1), k + 64, largest=False).indices
+        q, x = pos[i].cpu().numpy(), pos[cand].cpu().numpy()     # (the shortlist contains the query itself)
+        dd = _bruteforce_d2(q, x, L)
+        want = dtype(0.5) * np.sqrt(np.sort(dd)[k - 1])
+        assert float(sm[i]) == float(want), (i, float(sm[i]), float(want))
+
+    # permutation invariance
+    perm = torch.randperm(n, generator=torch.Generator(device="cuda").manual_seed(5), device="cuda")
+    sm_p, rho_p = run(pos[perm].contiguous(), mass[perm].contiguous())
+    assert bool((sm_p == sm[perm]).all())
+    assert float(((rho_p - rho[perm]).abs() / rho[perm]).max()) < rtol
+
+    # fused density vs the general gather pass
+    m2 = mass.clone()
+    m2[::2] = torch.nextafter(m2[::2], torch.full_like(m2[::2], 2.0))     # masses no longer identical
+    _, rho_g = run(pos, m2)
+    assert float(((rho_g - rho).abs() / rho).max()) < rtol
+
+
+def _bruteforce_d2(q, x, L):
+    """d2 of query q[3] to particles x[m,3] with the library's arithmetic (nearest of q, fl(q+L), fl(q-L) per axis)."""
+    dt = x.dtype.type
+    d = q[None, :] - x
+    dp = (q[None, :] + dt(L)) - x
+    dm = (q[None, :] - dt(L)) - x
+    d = np.where(np.abs(dp) < np.abs(d), dp, d)
+    d = np.where(np.abs(dm) < np.abs(d), dm, d)
+    return (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
