@@ -40,19 +40,31 @@ template <int OP> struct OpTraits {
     static constexpr bool grad = (OP == OP_DIV || OP == OP_CURL);
 };
 
-// shared-memory tile of one candidate bucket: x,y,z,mass,rho (T) then up to 3 quantity columns (Q)
+// shared-memory working set of one warp
 template <typename T, typename Q>
 struct Tile {
-    T x[32], y[32], z[32], m[32], rho[32];
-    Q q[3][32];
+    T x[32], y[32], z[32], m[32], rho[32];      // candidate bucket: coordinates, mass, density
+    Q q[3][32];                                 // ... and up to 3 quantity columns
+    T sx[32], sy[32], sz[32];                   // per query lane: its position shifted for this bucket
+    double c[8][32];                            // per query lane: ih2, norm, qx, qy, qz, e0, e1, e2 (e = own quantity / mean)
+    double acc[3][32];                          // per query lane: running sums
+    uint16_t pairs[1024];                       // accepted (query lane << 5 | candidate) pairs of the current bucket
 };
 
+// One sweep of the tree for the warp's 32 queries.  Per candidate bucket:
+//   1. lane j holds candidate j; the queries in reach are taken in turn (position and ball radius broadcast by
+//      shuffle), the 32 verdicts of one query come back as a ballot and the accepted pairs are appended to a list
+//      in shared memory;
+//   2. the list is worked off 32 pairs at a time -- every lane evaluates one (query, candidate) interaction, so
+//      all lanes are busy whatever the geometry (taking each lane's own candidates in turn kept ~8 of 32 busy);
+//      the list is ordered by query, so the terms of one query sit in adjacent lanes and are summed by a
+//      segmented shuffle reduction whose head lane adds the sum to the query's accumulator.
 template <typename T, typename Q, int OP, bool PERIODIC, int PASS>
 __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, Q> &tile, int lane, bool active,
-                                             T qx, T qy, T qz, T ball2, T ih2, double norm, const double *qi,
-                                             const double *mean, double *acc, int &count)
+                                             T qx, T qy, T qz, T ball2, int &count)
 {
     using OT = OpTraits<OP>;
+    constexpr int NC = (OT::two_pass && PASS == 1) ? 1 : (OP == OP_RHO || OP == OP_DIV ? 1 : OT::qcols);
     const TreeView<T> &tv = a.tv;
     const T L = tv.period;
     int64_t cp = 1;
@@ -67,9 +79,11 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
             const int start = tv.bucket_start[bucket];
             const int cnt = tv.bucket_start[bucket + 1] - start;
             __syncwarp();
+            T cx = 0, cy = 0, cz = 0;
             if (lane < cnt) {
                 const int64_t j = start + lane;
-                tile.x[lane] = tv.x[j]; tile.y[lane] = tv.y[j]; tile.z[lane] = tv.z[j];
+                cx = tv.x[j]; cy = tv.y[j]; cz = tv.z[j];
+                tile.x[lane] = cx; tile.y[lane] = cy; tile.z[lane] = cz;
                 tile.m[lane] = tv.mass[j];
                 if (OP != OP_RHO) {
                     tile.rho[lane] = a.rho_t[j];
@@ -77,70 +91,104 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                     for (int c = 0; c < OT::qcols; ++c) tile.q[c][lane] = a.qty_t[(int64_t)c * tv.n + j];
                 }
             }
-            __syncwarp();
-            unsigned mask = 0;
+            tile.sx[lane] = sx; tile.sy[lane] = sy; tile.sz[lane] = sz;
             // some lane's shift is not the nearest image for every particle of this cell: image per particle
             const bool wide = PERIODIC && __any_sync(FULL, pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L));
-            if (!wide) {
-#pragma unroll 4
-                for (int j = 0; j < cnt; ++j) {
-                    T d2 = dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
-                    mask |= (unsigned)(d2 <= ball2) << j;      // smooth.h:310 (non-strict)
+            // 1. accepted pairs, query by query
+            int npairs = 0;
+            unsigned todo = __ballot_sync(FULL, pass);
+            while (todo) {
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const T ub = __shfl_sync(FULL, ball2, i);
+                T d2;
+                if (!wide) {
+                    const T ux = __shfl_sync(FULL, sx, i), uy = __shfl_sync(FULL, sy, i), uz = __shfl_sync(FULL, sz, i);
+                    d2 = dist2<T>(ux, uy, uz, cx, cy, cz);
+                } else {
+                    const T ux = __shfl_sync(FULL, qx, i), uy = __shfl_sync(FULL, qy, i), uz = __shfl_sync(FULL, qz, i);
+                    d2 = dist2_nearest<T>(ux, uy, uz, cx, cy, cz, L);
                 }
-            } else {
-                for (int j = 0; j < cnt; ++j) {
-                    T d2 = dist2_nearest<T>(qx, qy, qz, tile.x[j], tile.y[j], tile.z[j], L);
-                    mask |= (unsigned)(d2 <= ball2) << j;
-                }
+                const bool in = lane < cnt && d2 <= ub;                         // smooth.h:310 (non-strict)
+                const unsigned row = __ballot_sync(FULL, in);
+                if (in) tile.pairs[npairs + __popc(row & ((1u << lane) - 1u))] = (uint16_t)(i << 5 | lane);
+                if (PASS == 0 && lane == i) count += __popc(row);
+                npairs += __popc(row);
             }
-            if (!pass) mask = 0;
-            if (PASS == 0) count += __popc(mask);
-            while (__any_sync(FULL, mask != 0)) {
-                if (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile.x[j], tile.y[j], tile.z[j], L)
-                                      : dist2<T>(sx, sy, sz, tile.x[j], tile.y[j], tile.z[j]);
-                    const double mj = (double)tile.m[j];
-                    if (OP == OP_RHO) {
-                        // rho_i += (W * norm) * m_j, accumulated in T by the caller's cast (smooth.h:640-645)
-                        T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
-                        w *= (T)norm;
-                        acc[0] = (double)((T)acc[0] + w * tile.m[j]);
-                    } else if (!OT::grad) {
-                        T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
-                        w *= (T)norm;
-                        const double wm = (double)w * mj / (double)tile.rho[j];
-                        if (!OT::two_pass || PASS == 0) {
+            __syncwarp();
+            // 2. one interaction per lane
+            for (int base = 0; base < npairs; base += 32) {
+                const bool valid = base + lane < npairs;
+                const unsigned code = valid ? tile.pairs[base + lane] : 0u;
+                const int i = valid ? (int)(code >> 5) : 32 + lane, j = (int)(code & 31u);
+                const int ii = i & 31;
+                const T px = tile.x[j], py = tile.y[j], pz = tile.z[j];
+                const T d2 = wide ? dist2_nearest<T>((T)tile.c[2][ii], (T)tile.c[3][ii], (T)tile.c[4][ii], px, py, pz, L)
+                                  : dist2<T>(tile.sx[ii], tile.sy[ii], tile.sz[ii], px, py, pz);
+                const T ih2 = (T)tile.c[0][ii];
+                const T norm = (T)tile.c[1][ii];
+                const double mj = (double)tile.m[j];
+                double v[NC];
+                if (OP == OP_RHO) {
+                    // rho_i += (W * norm) * m_j, each term rounded as the reference rounds it (smooth.h:640-645)
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
+                    w *= norm;
+                    v[0] = (double)(w * tile.m[j]);
+                } else if (!OT::grad) {
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
+                    w *= norm;
+                    const double wm = (double)w * mj / (double)tile.rho[j];
+                    if (!OT::two_pass || PASS == 0) {
 #pragma unroll
-                            for (int c = 0; c < OT::qcols; ++c) acc[c] = (double)((Q)acc[c] + (Q)(wm * (double)tile.q[c][j]));
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < OT::qcols; ++c) {
-                                Q tq = (Q)mean[c] - tile.q[c][j];
-                                acc[0] = (double)((Q)acc[0] + (Q)(wm * (double)tq * (double)tq));
-                            }
-                        }
+                        for (int c = 0; c < OT::qcols; ++c) v[c] = (double)(Q)(wm * (double)tile.q[c][j]);
                     } else {
-                        // raw UNWRAPPED separation (smooth.h:736-738, :791-793), wrapped r2 in the kernel
-                        const T dx = qx - tile.x[j], dy = qy - tile.y[j], dz = qz - tile.z[j];
-                        T g = (T)kern_g(a.kernel_id, (double)(d2 * ih2), (double)d2);
-                        g *= (T)norm;
-                        const T dq0 = (T)((double)tile.q[0][j] - qi[0]);
-                        const T dq1 = (T)((double)tile.q[1][j] - qi[1]);
-                        const T dq2 = (T)((double)tile.q[2][j] - qi[2]);
-                        const double gm = (double)g * mj / (double)tile.rho[j];
-                        if (OP == OP_DIV) {
-                            const T dv = dx * dq0 + dy * dq1 + dz * dq2;
-                            acc[0] = (double)((Q)acc[0] + (Q)((double)g * (double)dv * mj / (double)tile.rho[j]));
-                        } else {
-                            const T c0 = dy * dq2 - dz * dq1, c1 = dz * dq0 - dx * dq2, c2 = dx * dq1 - dy * dq0;
-                            acc[0] = (double)((Q)acc[0] + (Q)(gm * (double)c0));
-                            acc[1] = (double)((Q)acc[1] + (Q)(gm * (double)c1));
-                            acc[2] = (double)((Q)acc[2] + (Q)(gm * (double)c2));
+                        v[0] = 0;
+#pragma unroll
+                        for (int c = 0; c < OT::qcols; ++c) {
+                            Q tq = (Q)tile.c[5 + c][ii] - tile.q[c][j];
+                            v[0] += (double)(Q)(wm * (double)tq * (double)tq);
                         }
                     }
+                } else {
+                    // raw UNWRAPPED separation (smooth.h:736-738, :791-793), wrapped r2 in the kernel
+                    const T dx = (T)tile.c[2][ii] - px, dy = (T)tile.c[3][ii] - py, dz = (T)tile.c[4][ii] - pz;
+                    T g = (T)kern_g(a.kernel_id, (double)(d2 * ih2), (double)d2);
+                    g *= norm;
+                    const T dq0 = (T)((double)tile.q[0][j] - tile.c[5][ii]);
+                    const T dq1 = (T)((double)tile.q[1][j] - tile.c[6][ii]);
+                    const T dq2 = (T)((double)tile.q[2][j] - tile.c[7][ii]);
+                    const double gm = (double)g * mj / (double)tile.rho[j];
+                    if (OP == OP_DIV) {
+                        const T dv = dx * dq0 + dy * dq1 + dz * dq2;
+                        v[0] = (double)(Q)((double)g * (double)dv * mj / (double)tile.rho[j]);
+                    } else {
+                        const T c0 = dy * dq2 - dz * dq1, c1 = dz * dq0 - dx * dq2, c2 = dx * dq1 - dy * dq0;
+                        v[0] = (double)(Q)(gm * (double)c0);
+                        if (NC > 1) v[1 % NC] = (double)(Q)(gm * (double)c1);
+                        if (NC > 2) v[2 % NC] = (double)(Q)(gm * (double)c2);
+                    }
                 }
+                if (!valid) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) v[c] = 0;
+                }
+                // segmented sum over the lanes that hold the same query
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const int ki = __shfl_down_sync(FULL, i, s);
+                    const bool same = lane + s < 32 && ki == i;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const double o = __shfl_down_sync(FULL, v[c], s);
+                        if (same) v[c] += o;
+                    }
+                }
+                const int prev = __shfl_up_sync(FULL, i, 1);
+                if (valid && (lane == 0 || prev != i)) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) tile.acc[c][i] += v[c];
+                }
+                __syncwarp();
             }
         }
         cp = next_node(cp);
@@ -152,12 +200,12 @@ template <typename T, typename Q, int OP, bool PERIODIC>
 __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather(GatherArgs<T, Q> a)
 {
     using OT = OpTraits<OP>;
-    __shared__ Tile<T, Q> tiles[GATHER_WARPS];
+    extern __shared__ __align__(16) unsigned char gather_smem[];
     const TreeView<T> &tv = a.tv;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t bucket = (int64_t)blockIdx.x * GATHER_WARPS + wib;
     if (bucket >= tv.nsplit) return;
-    Tile<T, Q> &tile = tiles[wib];
+    Tile<T, Q> &tile = reinterpret_cast<Tile<T, Q> *>(gather_smem)[wib];
 
     const int start = tv.bucket_start[bucket];
     const int cnt = tv.bucket_start[bucket + 1] - start;
@@ -178,22 +226,26 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather(GatherArgs<T, Q> a
     // 1/(pi h^3) for values, 1/(pi h^4) for gradients (smooth.h:634-636, :724-726)
     const double norm = OT::grad ? (double)(T)(0.31830988618379067154 * (double)ih2 * (double)ih2)
                                  : (double)(T)(0.31830988618379067154 * (double)ih * (double)ih2);
-    double acc[3] = {0, 0, 0}, mean[3] = {0, 0, 0};
+    tile.c[0][lane] = (double)ih2; tile.c[1][lane] = norm;
+    tile.c[2][lane] = (double)qx; tile.c[3][lane] = (double)qy; tile.c[4][lane] = (double)qz;
+    for (int c = 0; c < 3; ++c) { tile.c[5 + c][lane] = qi[c]; tile.acc[c][lane] = 0; }
     int count = 0;
-    gather_sweep<T, Q, OP, PERIODIC, 0>(a, tile, lane, active, qx, qy, qz, ball2, ih2, norm, qi, mean, acc, count);
+    gather_sweep<T, Q, OP, PERIODIC, 0>(a, tile, lane, active, qx, qy, qz, ball2, count);
     if (OT::two_pass) {
-        for (int c = 0; c < 3; ++c) { mean[c] = acc[c]; acc[c] = 0; }
-        gather_sweep<T, Q, OP, PERIODIC, 1>(a, tile, lane, active, qx, qy, qz, ball2, ih2, norm, qi, mean, acc, count);
+        __syncwarp();
+        for (int c = 0; c < 3; ++c) { tile.c[5 + c][lane] = tile.acc[c][lane]; tile.acc[c][lane] = 0; }   // the means
+        gather_sweep<T, Q, OP, PERIODIC, 1>(a, tile, lane, active, qx, qy, qz, ball2, count);
     }
+    __syncwarp();
     if (!active) return;
     if (count > a.k + RESMOOTH_SAFE) atomicOr(a.overflow, 1);      // smooth.h:253-267
     if (OP == OP_RHO) {
-        reinterpret_cast<T *>(a.out_t)[p] = (T)acc[0];
+        reinterpret_cast<T *>(a.out_t)[p] = (T)tile.acc[0][lane];
     } else if (OT::two_pass) {
-        reinterpret_cast<Q *>(a.out_t)[p] = (Q)sqrt(acc[0]);         // smooth.h:866, :917
+        reinterpret_cast<Q *>(a.out_t)[p] = (Q)sqrt(tile.acc[0][lane]);         // smooth.h:866, :917
     } else {
 #pragma unroll
-        for (int c = 0; c < OT::ocols; ++c) reinterpret_cast<Q *>(a.out_t)[(int64_t)c * tv.n + p] = (Q)acc[c];
+        for (int c = 0; c < OT::ocols; ++c) reinterpret_cast<Q *>(a.out_t)[(int64_t)c * tv.n + p] = (Q)tile.acc[c][lane];
     }
 }
 
@@ -201,9 +253,14 @@ template <typename T, typename Q, int OP>
 static void launch_gather(Tree &t, GatherArgs<T, Q> &a)
 {
     const unsigned grid = (unsigned)((t.nsplit + GATHER_WARPS - 1) / GATHER_WARPS);
+    const size_t smem = sizeof(Tile<T, Q>) * GATHER_WARPS;
+    auto kp = k_gather<T, Q, OP, true>;
+    auto ko = k_gather<T, Q, OP, false>;
+    PNB_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PNB_CUDA(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer timer(1, t.stream);
-    if (a.tv.periodic) PNB_LAUNCH((k_gather<T, Q, OP, true>), grid, GATHER_WARPS * 32, 0, t.stream, a);
-    else PNB_LAUNCH((k_gather<T, Q, OP, false>), grid, GATHER_WARPS * 32, 0, t.stream, a);
+    if (a.tv.periodic) PNB_LAUNCH(kp, grid, GATHER_WARPS * 32, smem, t.stream, a);
+    else PNB_LAUNCH(ko, grid, GATHER_WARPS * 32, smem, t.stream, a);
     timer.stop();
 }
 
