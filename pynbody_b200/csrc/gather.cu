@@ -43,7 +43,8 @@ template <int OP> struct OpTraits {
 // shared-memory working set of one warp
 template <typename T, typename Q>
 struct Tile {
-    T x[32], y[32], z[32], m[32], rho[32];      // candidate bucket: coordinates, mass, density
+    T x[32], y[32], z[32], m[32];               // candidate bucket: coordinates, mass
+    double mr[32];                              // ... mass / density (one division per candidate, not per pair)
     Q q[3][32];                                 // ... and up to 3 quantity columns
     T sx[32], sy[32], sz[32];                   // per query lane: its position shifted for this bucket
     double c[8][32];                            // per query lane: ih2, norm, qx, qy, qz, e0, e1, e2 (e = own quantity / mean)
@@ -86,7 +87,7 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 tile.x[lane] = cx; tile.y[lane] = cy; tile.z[lane] = cz;
                 tile.m[lane] = tv.mass[j];
                 if (OP != OP_RHO) {
-                    tile.rho[lane] = a.rho_t[j];
+                    tile.mr[lane] = (double)tile.m[lane] / (double)a.rho_t[j];
 #pragma unroll
                     for (int c = 0; c < OT::qcols; ++c) tile.q[c][lane] = a.qty_t[(int64_t)c * tv.n + j];
                 }
@@ -127,7 +128,6 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                                   : dist2<T>(tile.sx[ii], tile.sy[ii], tile.sz[ii], px, py, pz);
                 const T ih2 = (T)tile.c[0][ii];
                 const T norm = (T)tile.c[1][ii];
-                const double mj = (double)tile.m[j];
                 double v[NC];
                 if (OP == OP_RHO) {
                     // rho_i += (W * norm) * m_j, each term rounded as the reference rounds it (smooth.h:640-645)
@@ -137,7 +137,7 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 } else if (!OT::grad) {
                     T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
                     w *= norm;
-                    const double wm = (double)w * mj / (double)tile.rho[j];
+                    const double wm = (double)w * tile.mr[j];
                     if (!OT::two_pass || PASS == 0) {
 #pragma unroll
                         for (int c = 0; c < OT::qcols; ++c) v[c] = (double)(Q)(wm * (double)tile.q[c][j]);
@@ -157,10 +157,10 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                     const T dq0 = (T)((double)tile.q[0][j] - tile.c[5][ii]);
                     const T dq1 = (T)((double)tile.q[1][j] - tile.c[6][ii]);
                     const T dq2 = (T)((double)tile.q[2][j] - tile.c[7][ii]);
-                    const double gm = (double)g * mj / (double)tile.rho[j];
+                    const double gm = (double)g * tile.mr[j];
                     if (OP == OP_DIV) {
                         const T dv = dx * dq0 + dy * dq1 + dz * dq2;
-                        v[0] = (double)(Q)((double)g * (double)dv * mj / (double)tile.rho[j]);
+                        v[0] = (double)(Q)(gm * (double)dv);
                     } else {
                         const T c0 = dy * dq2 - dz * dq1, c1 = dz * dq0 - dx * dq2, c2 = dx * dq1 - dy * dq0;
                         v[0] = (double)(Q)(gm * (double)c0);
