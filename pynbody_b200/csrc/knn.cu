@@ -8,10 +8,13 @@
 // particle i of that bucket.  The warp walks the tree ONCE for all 32 queries -- own bucket first,
 // then the sibling sub-trees bottom-up exactly in the reference's search order (smooth.h:209-241) --
 // with a per-lane periodic box test (kd.h:68-154) combined by a warp vote.  A candidate bucket is
-// staged in shared memory (3 coalesced lines) and every lane measures all 32 candidates against its
-// own query; survivors (d2 < current k-th distance) are remembered in a 32-bit register mask and
-// then inserted into the lane's private bounded neighbour queue, all lanes inserting together.
+// staged in shared memory (3 coalesced lines).  The first k candidates of a search go straight into
+// the queue's leaves.  After that the bucket is tested with lane = candidate: the queries in reach of
+// it are taken in turn, their (shifted) position and k-th distance broadcast by shuffle, and the 32
+// verdicts of one query come back as one ballot; the survivors (d2 < current k-th distance) of each
+// query are then inserted into its lane's private neighbour queue, all lanes inserting together.
 // The kernel is persistent: warps take buckets in tree order from a global counter.
+// (-DKNN_STATS builds a variant that counts buckets, survivors, insert rounds and node tests.)
 //
 // The queue (the reference's max-heap, pq.h) is a TOURNAMENT TREE per lane in shared memory,
 // lane-interleaved (element e of lane l at [e*32+l]: conflict-free): K2 = 2^ceil(log2 k) leaf slots
@@ -341,8 +344,8 @@ __host__ __device__ inline size_t knn_smem_per_warp(int K2)
 }
 
 // padding leaves [k, K2) hold the smallest key; until k candidates have been seen the k-th distance is "+inf"
-__device__ __forceinline__ float init_key(float, int, int) { return -1.0f; }
-__device__ __forceinline__ uint32_t init_key(double, int, int) { return 0u; }
+__device__ __forceinline__ float padding_key(float) { return -1.0f; }
+__device__ __forceinline__ uint32_t padding_key(double) { return 0u; }
 __device__ __forceinline__ float init_top(float) { return 3.0e38f; }
 __device__ __forceinline__ double init_top(double) { return __hiloint2double(0x7fe00000, 0); }
 
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
 
         for (int e = k; e < K2; ++e) {              // padding leaves hold the smallest key and never win
-            q.hd[e * 32] = init_key(T(), e, k);
+            q.hd[e * 32] = padding_key(T());
             if (sizeof(T) == 8) q.lo[e * 32] = 0u;
             if (WITH_IDX) q.hi[e * 32] = -1;
         }
