@@ -315,11 +315,12 @@ class DistributedKDTree:
             src_idx = order                                         # original local index of each sent particle
             self._ret_counts = counts                               # what I sent to each rank (returns come back so)
             self._ret_index = src_idx
-            pos_s, mass_s = pos[order], mass[order]
-            self.pos = torch.cat(_alltoallv(list(pos_s.split(counts)), group))
-            recv_mass = _alltoallv(list(mass_s.split(counts)), group)
-            self._own_counts = [int(t.shape[0]) for t in recv_mass]  # owned particles grouped by source rank
-            self.mass = torch.cat(recv_mass)
+            # positions and masses travel together: one exchange of [n][4] rows
+            packed = torch.cat([pos[order], mass[order, None].to(pos.dtype)], dim=1)
+            recv = _alltoallv(list(packed.split(counts)), group)
+            self._own_counts = [int(t.shape[0]) for t in recv]      # owned particles grouped by source rank
+            recv = torch.cat(recv)
+            self.pos, self.mass = recv[:, :3].contiguous(), recv[:, 3].contiguous()
         else:
             self.pos, self.mass = pos, mass
         self._tick("route_particles")
@@ -399,8 +400,9 @@ class DistributedKDTree:
                 continue
             rad = torch.where(torch.isfinite(b[:, 3]), b[:, 3], torch.full_like(b[:, 3], 1e30))
             self._halo_send.append(torch.nonzero(self.tree1.mark_in_balls(b[:, :3].contiguous(), rad)).squeeze(1))
-        halo_pos = torch.cat(_alltoallv([self.pos[i] for i in self._halo_send], self.group))
-        halo_mass = torch.cat(_alltoallv([self.mass[i] for i in self._halo_send], self.group))
+        halo = torch.cat(_alltoallv([torch.cat([self.pos[i], self.mass[i, None].to(self.dt)], dim=1) for i in self._halo_send],
+                                    self.group))
+        halo_pos, halo_mass = halo[:, :3], halo[:, 3]
         self.n_halo = int(halo_pos.shape[0])
         self._tick("mark_and_exchange_halo")
         self.stats = {"owned": self.n_own, "boundary_queries": int(fidx.numel()), "halo": self.n_halo}
