@@ -619,6 +619,11 @@ struct HpArgs {
     double max_d, shell_radius;
 };
 
+struct HpRing {                 // one ring of a particle's disc (healpix.c:120-200)
+    double st, ct;              // sin / cos of the ring's colatitude
+    unsigned ip_lo, n_in_ring, shift, iring;
+};
+
 __device__ __forceinline__ double ldv(const void *p, int f64, int64_t i)
 {
     return f64 ? ((const double *)p)[i] : (double)((const float *)p)[i];
@@ -690,33 +695,68 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
     if (thetamax > PI) thetamax = PI;
     const size_t irmin = hp_ring_num_from_z(nside, cos(thetamin)), irmax = hp_ring_num_from_z(nside, cos(thetamax));
     const double cos_radius = cos(radius);
-    for (size_t iring = irmin; iring <= irmax; ++iring) {
-        const double z = hp_z_from_ring_num(nside, iring), sin_theta = sqrt(1.0 - z * z);
-        const double cos_dphi = (cos_radius - z * z0) / (sin_theta * sin_theta0);
-        const double dphi = cos_dphi >= 1.0 ? 0.0 : (cos_dphi <= -1.0 ? PI : acos(cos_dphi));
-        size_t ip_lo, ip_hi, n_in_ring, shift;
-        if (iring <= nside) { n_in_ring = 4 * iring; shift = 1; }
-        else if (iring <= 3 * nside) { n_in_ring = 4 * nside; shift = 2 - (iring - nside + 1) % 2; }
-        else { n_in_ring = 4 * (4 * nside - iring); shift = 1; }
-        if (dphi > 0.5 * PI) { ip_lo = 1; ip_hi = n_in_ring; }
-        else {
-            double phi_low = phi0 - dphi, phi_high = phi0 + dphi;
-            if (phi_low < 0.0) phi_low += twopi;
-            if (phi_high >= twopi) phi_high -= twopi;
-            const double phi_factor = n_in_ring / twopi;
-            ip_lo = (size_t)(phi_low * phi_factor + 0.5 * shift);
-            ip_hi = (size_t)(phi_high * phi_factor + 0.5 * shift + 1);
+    // The disc is found ring by ring as healpix.c does it, 32 rings at a time with one ring per lane; the
+    // pixels of those rings are then numbered consecutively and dealt out to the lanes, so that all lanes
+    // are busy whatever the width of a ring (a disc of the usual size has ~12 pixels per ring).
+    __shared__ HpRing rings[8][32];
+    HpRing *wr = rings[threadIdx.x >> 5];
+    for (size_t rb = irmin; rb <= irmax; rb += 32) {
+        const size_t iring = rb + lane;
+        int count = 0;
+        if (iring <= irmax) {
+            const double z = hp_z_from_ring_num(nside, iring), sin_theta = sqrt(1.0 - z * z);
+            const double cos_dphi = (cos_radius - z * z0) / (sin_theta * sin_theta0);
+            const double dphi = cos_dphi >= 1.0 ? 0.0 : (cos_dphi <= -1.0 ? PI : acos(cos_dphi));
+            size_t ip_lo, ip_hi, n_in_ring, shift;
+            if (iring <= nside) { n_in_ring = 4 * iring; shift = 1; }
+            else if (iring <= 3 * nside) { n_in_ring = 4 * nside; shift = 2 - (iring - nside + 1) % 2; }
+            else { n_in_ring = 4 * (4 * nside - iring); shift = 1; }
+            if (dphi > 0.5 * PI) { ip_lo = 1; ip_hi = n_in_ring; }
+            else {
+                double phi_low = phi0 - dphi, phi_high = phi0 + dphi;
+                if (phi_low < 0.0) phi_low += twopi;
+                if (phi_high >= twopi) phi_high -= twopi;
+                const double phi_factor = n_in_ring / twopi;
+                ip_lo = (size_t)(phi_low * phi_factor + 0.5 * shift);
+                ip_hi = (size_t)(phi_high * phi_factor + 0.5 * shift + 1);
+            }
+            if (ip_hi < ip_lo) ip_hi += n_in_ring;
+            if (ip_hi - ip_lo > n_in_ring) { ip_lo = 1; ip_hi = n_in_ring; }
+            const double theta = acos(z);
+            sincos(theta, &wr[lane].st, &wr[lane].ct);
+            wr[lane].ip_lo = (unsigned)ip_lo; wr[lane].n_in_ring = (unsigned)n_in_ring;
+            wr[lane].shift = (unsigned)shift; wr[lane].iring = (unsigned)iring;
+            count = (int)(ip_hi - ip_lo + 1);
         }
-        if (ip_hi < ip_lo) ip_hi += n_in_ring;
-        if (ip_hi - ip_lo > n_in_ring) { ip_lo = 1; ip_hi = n_in_ring; }
-        const double theta = acos(z), st = sin(theta), ct = cos(theta);
-        for (size_t iphi = ip_lo + lane; iphi <= ip_hi; iphi += 32) {
-            size_t ip = iphi;
+        int incl = count;                               // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int excl = incl - count;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (int fb = 0; fb < total; fb += 32) {        // (warp-uniform trip count: the shuffles need every lane)
+            const int f = fb + lane;
+            int r = 0;                                  // the ring that holds pixel number f: largest r with excl[r] <= f
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                const int t = __shfl_sync(0xffffffffu, excl, (r + d) & 31);
+                if (r + d < 32 && t <= f) r += d;
+            }
+            const int first = __shfl_sync(0xffffffffu, excl, r);
+            if (f >= total) continue;
+            const HpRing R = wr[r];
+            const size_t n_in_ring = R.n_in_ring, shift = R.shift;
+            size_t ip = (size_t)R.ip_lo + (size_t)(f - first);
             if (ip > n_in_ring) ip -= n_in_ring;
-            const size_t ipix = hp_pixel_index(nside, iring, ip);
+            const size_t ipix = hp_pixel_index(nside, R.iring, ip);
             double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
             if (phi >= twopi) phi -= twopi;
-            double dot = v0 * (st * cos(phi)) + v1 * (st * sin(phi)) + v2 * ct;
+            double sphi, cphi;
+            sincos(phi, &sphi, &cphi);
+            double dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
             if (dot > 1.0) dot = 1.0;
             if (dot < -1.0) dot = -1.0;
             const double dist = acos(dot);
@@ -736,6 +776,7 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             else vf = vf / ((const float *)a.rho)[i];
             atomicAdd(&acc[ipix], isd ? vd : (double)vf);
         }
+        __syncwarp();
     }
 }
 
