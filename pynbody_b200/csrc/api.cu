@@ -77,6 +77,7 @@ struct BlockCache {
     std::mutex mu;
     std::map<std::pair<int, size_t>, std::vector<void *>> free_lists;   // (device, bytes) -> blocks
     size_t cached_bytes = 0;
+    size_t limit = 0;           // idle blocks kept at most: a quarter of the device's memory (set on first use)
     void trim_locked()
     {
         for (auto &kv : free_lists)
@@ -121,6 +122,19 @@ void cache_free(void *p, size_t bytes)
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
     BlockCache &c = block_cache();
     std::lock_guard<std::mutex> lock(c.mu);
+    if (c.limit == 0) {
+        size_t free_b = 0, total_b = 0;
+        c.limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 : (size_t)16 << 30;
+        cudaGetLastError();
+    }
+    // A process that keeps changing its particle count would otherwise pile up idle blocks of ever new size
+    // classes: past the limit everything idle goes back to the driver (the next step re-allocates what it needs).
+    if (c.cached_bytes + bytes > c.limit) {
+        cudaDeviceSynchronize();
+        c.trim_locked();
+        cudaFree(p);
+        return;
+    }
     c.free_lists[{dev, bytes}].push_back(p);
     c.cached_bytes += bytes;
 }
