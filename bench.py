@@ -359,7 +359,7 @@ def run_ours(args):
                      "ncu_warp_inst_per_particle": load_traffic(args.dtype, args.n_side, "warp_inst_per_particle"),
                      "note": "irregular tree search: bound by instruction issue (on-chip neighbour-queue updates), not by "
                              "HBM bytes (SURVEY.md 8d); traffic and issue-slot utilisation from the committed ncu capture "
-                             "profiles/r1_knn_v6_summary.txt"},
+                             "profiles/r1_knn_final_summary.txt"},
         "stages_ms": {"build": float(np.mean(stats["build_ms"])), "smooth_incl_fused_rho": float(np.mean(stats["knn_ms"])),
                       "knn_kernel": knn_kernel_ms, "rho_readback": float(np.mean(stats["rho_ms"])), **extra},
         "render": render,
