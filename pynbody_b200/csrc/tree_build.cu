@@ -61,10 +61,11 @@ __host__ __device__ inline int64_t split_rank(const TreeShape &s, int level, int
 }
 __host__ __device__ inline void seg_of_pos(const TreeShape &s, int level, int64_t p, int64_t &lo, int64_t &hi, int64_t &node)
 {
-    if (s.packed) {
-        const int64_t cap = (int64_t)s.leafcap << (s.levels - level);
-        const int64_t j = p / cap;
-        lo = j * cap;
+    if (s.packed) {                                  // buckets of 32: node ranges are powers of two, no division
+        const int sh = 5 + s.levels - level;
+        const int64_t cap = (int64_t)1 << sh;
+        const int64_t j = p >> sh;
+        lo = j << sh;
         hi = lo + cap - 1;
         if (hi > s.n - 1) hi = s.n - 1;
         node = ((int64_t)1 << level) + j;
@@ -167,7 +168,7 @@ __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__
     const int64_t n = s.n;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= 3 * n) return;
-    int64_t d = i / n, p = i - d * n;
+    int64_t d = (i >= n) + (i >= 2 * n), p = i - d * n;
     int64_t lo, hi, node;
     seg_of_pos(s, level, p, lo, hi, node);
     int64_t m = split_rank(s, level, lo, hi);
