@@ -367,10 +367,24 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
         StageTimer timer(0, t->stream);
         const size_t ts = tsize(dtype);
         DevBuf cols(ts * 3 * n), mass_dev;
+        struct PendingCopy {                // declared after mass_dev: the copy has landed before the buffer is released
+            cudaEvent_t &ev;
+            ~PendingCopy() { if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); ev = nullptr; } }
+        } pending{t->mass_ready};
         fetch_columns(pos, pos_stride0, pos_stride1, 3, dtype, mem, n, cols.p, t->stream);
         if (mass) {
             mass_dev.alloc(ts * n);
-            fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
+            if (mem == PNB_HOST && mass_stride == (int64_t)ts && ts * (size_t)n >= ((size_t)4 << 20) && host_is_pinned(mass)) {
+                // pinned host masses: the copy rides on a second stream behind the sorts of the build and is
+                // only waited for where the tree-ordered arrays are gathered
+                static cudaStream_t side = nullptr;
+                if (!side) PNB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                PNB_CUDA(cudaEventCreateWithFlags(&t->mass_ready, cudaEventDisableTiming));
+                PNB_CUDA(cudaMemcpyAsync(mass_dev.p, mass, ts * (size_t)n, cudaMemcpyHostToDevice, side));
+                PNB_CUDA(cudaEventRecord(t->mass_ready, side));
+            } else {
+                fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
+            }
         }
         build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
         update_mass_uniformity(*t);

@@ -111,6 +111,7 @@ struct Tree {
     int levels = 0;               // depth of the device tree: buckets live at heap level `levels`
     int64_t nsplit = 1;           // number of buckets = 1 << levels
     cudaStream_t stream = nullptr;
+    cudaEvent_t mass_ready = nullptr;   // set while the masses are still on their way to the device (pnb_tree_create)
 
     // particles in tree order (T), structure of arrays
     DevBuf x, y, z, mass;
@@ -167,6 +168,7 @@ void fetch_columns(const void *ptr, int64_t stride0, int64_t stride1, int ncols,
 // Write a dense column-major device buffer ([ncols][n], file order) back to a strided destination.
 void store_columns(void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem,
                    int64_t n, const void *dev_in, cudaStream_t stream);
+bool host_is_pinned(const void *p);
 // tree-order <-> file-order permutations on the device (element size 4 or 8, ncols columns)
 void permute_to_tree(const Tree &t, const void *file_in, void *tree_out, int ncols, int elem, cudaStream_t s);
 void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int ncols, int elem, cudaStream_t s);

@@ -39,6 +39,9 @@ bool is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
+}  // namespace
+bool host_is_pinned(const void *p) { return is_pinned(p); }
+namespace {
 void parallel_memcpy(void *dst, const void *src, size_t bytes)
 {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());

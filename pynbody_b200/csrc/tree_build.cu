@@ -256,6 +256,7 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
         if (mass) t.mass.alloc(sizeof(T) * n);
         t.has_mass = mass != nullptr;
+        if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sorts
         PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
                    t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
     }
