@@ -377,7 +377,10 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
             if (mem == PNB_HOST && mass_stride == (int64_t)ts && ts * (size_t)n >= ((size_t)4 << 20) && host_is_pinned(mass)) {
                 // pinned host masses: the copy rides on a second stream behind the sorts of the build and is
                 // only waited for where the tree-ordered arrays are gathered
-                static cudaStream_t side = nullptr;
+                static cudaStream_t sides[64] = {nullptr};            // one copy stream per device
+                int dev = 0;
+                PNB_CUDA(cudaGetDevice(&dev));
+                cudaStream_t &side = sides[dev & 63];
                 if (!side) PNB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
                 PNB_CUDA(cudaEventCreateWithFlags(&t->mass_ready, cudaEventDisableTiming));
                 PNB_CUDA(cudaMemcpyAsync(mass_dev.p, mass, ts * (size_t)n, cudaMemcpyHostToDevice, side));
