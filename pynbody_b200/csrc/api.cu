@@ -146,6 +146,23 @@ void cache_trim()
     c.trim_locked();
 }
 
+// a second, non-blocking stream per device for copies that run beside the work on the library's stream
+static cudaStream_t copy_stream()
+{
+    static cudaStream_t sides[64] = {nullptr};
+    int dev = 0;
+    PNB_CUDA(cudaGetDevice(&dev));
+    cudaStream_t &side = sides[dev & 63];
+    if (!side) PNB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    return side;
+}
+// an event that is waited for (and destroyed) when it goes out of scope, so that a buffer declared BEFORE it
+// is never released while the copy it marks is still in flight
+struct PendingCopy {
+    cudaEvent_t &ev;
+    ~PendingCopy() { if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); ev = nullptr; } }
+};
+
 static void require_device()
 {
     int n = 0;
@@ -293,11 +310,43 @@ static void populate(Tree &t, int propid, int k, int kernel_id, double period_in
     }
     if (propid < PNB_PROP_RHO || propid > PNB_PROP_QTYCURL) throw Error(PNB_ERR_VALUE, "unknown smoothing property id");
 
+    // sim['smooth'] -> sim['rho'] with pinned host arrays: the density that rode along the kNN pass starts its way
+    // back to the host while the caller's smooth array travels the other way to be checked against the tree's
+    // own (PCIe is full duplex); if the check fails the gather pass below overwrites it
+    const bool period_matches = t.smooth_period == (period > 0 ? period : 0);
+    DevBuf early_rho;
+    cudaEvent_t early_done = nullptr;
+    PendingCopy early_guard{early_done};
+    if (propid == PNB_PROP_RHO && t.smooth_valid && t.smooth_k == k && period_matches && t.rho_valid
+        && t.rho_kernel == kernel_id && t.arr[PNB_ARR_RHO].set()) {
+        const ArrRef &o = t.arr[PNB_ARR_RHO];
+        if (o.mem == PNB_HOST && o.ncols == 1 && o.dtype == t.dtype && o.stride0 == (int64_t)ts
+            && ts * (size_t)t.n >= ((size_t)4 << 20) && host_is_pinned(o.ptr)) {
+            early_rho.alloc(ts * t.n);
+            permute_to_file(t, t.rho_t.p, early_rho.p, 1, (int)ts, t.stream);
+            cudaEvent_t ready = nullptr;
+            PNB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            PNB_CUDA(cudaEventRecord(ready, t.stream));
+            cudaStream_t side = copy_stream();
+            PNB_CUDA(cudaStreamWaitEvent(side, ready, 0));
+            PNB_CUDA(cudaEventDestroy(ready));
+            PNB_CUDA(cudaEventCreateWithFlags(&early_done, cudaEventDisableTiming));
+            PNB_CUDA(cudaMemcpyAsync(o.ptr, early_rho.p, ts * (size_t)t.n, cudaMemcpyDeviceToHost, side));
+            PNB_CUDA(cudaEventRecord(early_done, side));
+        }
+    }
+
     const ArrRef &smr = need(t, PNB_ARR_SMOOTH, "smooth");
     DevBuf smooth_tree = fetch_tree_order(t, smr);
     // is the caller's smooth array the one this tree produced (the usual sim['smooth'] -> sim['rho'] flow)?
-    const bool own_smooth = t.smooth_valid && t.smooth_k == k && t.smooth_period == (period > 0 ? period : 0)
+    const bool own_smooth = t.smooth_valid && t.smooth_k == k && period_matches
                             && device_equal(t, smooth_tree.p, t.smooth_t.p, ts * t.n, /*masked=*/true);
+    if (early_done) {                                               // the early copy has to land either way
+        PNB_CUDA(cudaEventSynchronize(early_done));
+        PNB_CUDA(cudaEventDestroy(early_done));
+        early_done = nullptr;
+        if (own_smooth) { timer.stop(); return; }
+    }
 
     if (propid == PNB_PROP_RHO) {
         const ArrRef &out = need(t, PNB_ARR_RHO, "rho");
@@ -367,21 +416,14 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
         StageTimer timer(0, t->stream);
         const size_t ts = tsize(dtype);
         DevBuf cols(ts * 3 * n), mass_dev;
-        struct PendingCopy {                // declared after mass_dev: the copy has landed before the buffer is released
-            cudaEvent_t &ev;
-            ~PendingCopy() { if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); ev = nullptr; } }
-        } pending{t->mass_ready};
+        PendingCopy pending{t->mass_ready};  // declared after mass_dev: the copy has landed before the buffer is released
         fetch_columns(pos, pos_stride0, pos_stride1, 3, dtype, mem, n, cols.p, t->stream);
         if (mass) {
             mass_dev.alloc(ts * n);
             if (mem == PNB_HOST && mass_stride == (int64_t)ts && ts * (size_t)n >= ((size_t)4 << 20) && host_is_pinned(mass)) {
                 // pinned host masses: the copy rides on a second stream behind the sorts of the build and is
                 // only waited for where the tree-ordered arrays are gathered
-                static cudaStream_t sides[64] = {nullptr};            // one copy stream per device
-                int dev = 0;
-                PNB_CUDA(cudaGetDevice(&dev));
-                cudaStream_t &side = sides[dev & 63];
-                if (!side) PNB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                cudaStream_t side = copy_stream();
                 PNB_CUDA(cudaEventCreateWithFlags(&t->mass_ready, cudaEventDisableTiming));
                 PNB_CUDA(cudaMemcpyAsync(mass_dev.p, mass, ts * (size_t)n, cudaMemcpyHostToDevice, side));
                 PNB_CUDA(cudaEventRecord(t->mass_ready, side));
