@@ -47,6 +47,7 @@ struct Tile {
     double mr[32];                              // ... mass / density (one division per candidate, not per pair)
     Q q[3][32];                                 // ... and up to 3 quantity columns
     T sx[32], sy[32], sz[32];                   // per query lane: its position shifted for this bucket
+    T ball2[32];                                // per query lane: (2h)^2
     double c[8][32];                            // per query lane: ih2, norm, qx, qy, qz, e0, e1, e2 (e = own quantity / mean)
     double acc[3][32];                          // per query lane: running sums
     uint16_t pairs[1024];                       // accepted (query lane << 5 | candidate) pairs of the current bucket
@@ -95,21 +96,19 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
             tile.sx[lane] = sx; tile.sy[lane] = sy; tile.sz[lane] = sz;
             // some lane's shift is not the nearest image for every particle of this cell: image per particle
             const bool wide = PERIODIC && __any_sync(FULL, pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L));
+            __syncwarp();
             // 1. accepted pairs, query by query
             int npairs = 0;
             unsigned todo = __ballot_sync(FULL, pass);
             while (todo) {
                 const int i = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const T ub = __shfl_sync(FULL, ball2, i);
+                // (the query's data comes from shared memory: one broadcast load per value instead of one or two
+                // shuffles)
+                const T ub = tile.ball2[i];
                 T d2;
-                if (!wide) {
-                    const T ux = __shfl_sync(FULL, sx, i), uy = __shfl_sync(FULL, sy, i), uz = __shfl_sync(FULL, sz, i);
-                    d2 = dist2<T>(ux, uy, uz, cx, cy, cz);
-                } else {
-                    const T ux = __shfl_sync(FULL, qx, i), uy = __shfl_sync(FULL, qy, i), uz = __shfl_sync(FULL, qz, i);
-                    d2 = dist2_nearest<T>(ux, uy, uz, cx, cy, cz, L);
-                }
+                if (!wide) d2 = dist2<T>(tile.sx[i], tile.sy[i], tile.sz[i], cx, cy, cz);
+                else d2 = dist2_nearest<T>((T)tile.c[2][i], (T)tile.c[3][i], (T)tile.c[4][i], cx, cy, cz, L);
                 const bool in = lane < cnt && d2 <= ub;                         // smooth.h:310 (non-strict)
                 const unsigned row = __ballot_sync(FULL, in);
                 if (in) tile.pairs[npairs + __popc(row & ((1u << lane) - 1u))] = (uint16_t)(i << 5 | lane);
@@ -226,6 +225,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather(GatherArgs<T, Q> a
     // 1/(pi h^3) for values, 1/(pi h^4) for gradients (smooth.h:634-636, :724-726)
     const double norm = OT::grad ? (double)(T)(0.31830988618379067154 * (double)ih2 * (double)ih2)
                                  : (double)(T)(0.31830988618379067154 * (double)ih * (double)ih2);
+    tile.ball2[lane] = ball2;
     tile.c[0][lane] = (double)ih2; tile.c[1][lane] = norm;
     tile.c[2][lane] = (double)qx; tile.c[3][lane] = (double)qy; tile.c[4][lane] = (double)qz;
     for (int c = 0; c < 3; ++c) { tile.c[5 + c][lane] = qi[c]; tile.acc[c][lane] = 0; }
