@@ -68,6 +68,15 @@ struct Footprint {
     int xa, xb, ya, yb, za, zb;
 };
 
+// the periodic images handled by one pass of the tile pipeline (_render.pyx:237-243, :418): a pair's payload keeps
+// the image number in its top 5 bits, the particle (relative to the range start) in the lower 27
+constexpr int MAX_IMAGES = 32;
+constexpr int IMAGE_SHIFT = 27;
+struct Images {
+    int n;
+    float ox[MAX_IMAGES], oy[MAX_IMAGES], oz[MAX_IMAGES];
+};
+
 struct alignas(16) Rec {
     double xi, yi, zd, kmax2;     // zd: image -> dz = (z - z0) * use_z ; grid -> z
     float xr, yr, zr, inv;        // tile-relative position; image: zr = dz^2; inv = ns / kmax2 (<0: exact path only)
@@ -174,51 +183,58 @@ __global__ void k_prepare(int64_t n, const void *sm, int sm64, const void *qty, 
     w_out[i] = w;
 }
 
-__global__ void k_count_tiles(Geom g, Cols c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+__global__ void k_count_tiles(Geom g, Cols c, int64_t i0, int64_t i1, Images im,
                               unsigned long long *__restrict__ counts)
 {
     int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= i1) return;
-    Footprint f;
     unsigned long long cnt = 0;
-    if (footprint(g, c, i, ox, oy, oz, f)) {
-        int ta, tb, ua, ub, va, vb;
-        tile_span(g, f, ta, tb, ua, ub, va, vb);
-        cnt = (unsigned long long)(tb - ta + 1) * (unsigned long long)(ub - ua + 1) * (unsigned long long)(vb - va + 1);
+    for (int o = 0; o < im.n; ++o) {
+        Footprint f;
+        if (footprint(g, c, i, im.ox[o], im.oy[o], im.oz[o], f)) {
+            int ta, tb, ua, ub, va, vb;
+            tile_span(g, f, ta, tb, ua, ub, va, vb);
+            cnt += (unsigned long long)(tb - ta + 1) * (unsigned long long)(ub - ua + 1) * (unsigned long long)(vb - va + 1);
+        }
     }
     counts[i - i0] = cnt;
 }
 
-__global__ void k_emit_pairs(Geom g, Cols c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+__global__ void k_emit_pairs(Geom g, Cols c, int64_t i0, int64_t i1, Images im,
                              const unsigned long long *__restrict__ offsets, uint32_t *__restrict__ keys,
                              uint32_t *__restrict__ vals)
 {
     int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= i1) return;
-    Footprint f;
-    if (!footprint(g, c, i, ox, oy, oz, f)) return;
-    int ta, tb, ua, ub, va, vb;
-    tile_span(g, f, ta, tb, ua, ub, va, vb);
     unsigned long long o = offsets[i - i0];
-    for (int t = ta; t <= tb; ++t)
-        for (int u = ua; u <= ub; ++u)
-            for (int v = va; v <= vb; ++v) {
-                uint32_t tile = g.grid ? (uint32_t)((t * g.tiles_y + u) * g.tiles_z + v) : (uint32_t)(u * g.tiles_x + t);
-                keys[o] = tile;
-                vals[o] = (uint32_t)(i - i0);
-                ++o;
-            }
+    for (int img = 0; img < im.n; ++img) {
+        Footprint f;
+        if (!footprint(g, c, i, im.ox[img], im.oy[img], im.oz[img], f)) continue;
+        int ta, tb, ua, ub, va, vb;
+        tile_span(g, f, ta, tb, ua, ub, va, vb);
+        const uint32_t payload = (uint32_t)(i - i0) | ((uint32_t)img << IMAGE_SHIFT);
+        for (int t = ta; t <= tb; ++t)
+            for (int u = ua; u <= ub; ++u)
+                for (int v = va; v <= vb; ++v) {
+                    uint32_t tile = g.grid ? (uint32_t)((t * g.tiles_y + u) * g.tiles_z + v) : (uint32_t)(u * g.tiles_x + t);
+                    keys[o] = tile;
+                    vals[o] = payload;
+                    ++o;
+                }
+    }
 }
 
-__global__ void k_make_records(Geom g, Cols c, int64_t i0, float ox, float oy, float oz, int64_t npairs,
+__global__ void k_make_records(Geom g, Cols c, int64_t i0, Images im, int64_t npairs,
                                const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                Rec *__restrict__ recs)
 {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= npairs) return;
     const uint32_t tile = keys[j];
+    const uint32_t payload = vals[j];
+    const int img = (int)(payload >> IMAGE_SHIFT);
     Footprint f;
-    footprint(g, c, i0 + vals[j], ox, oy, oz, f);
+    footprint(g, c, i0 + (payload & ((1u << IMAGE_SHIFT) - 1u)), im.ox[img], im.oy[img], im.oz[img], f);
     int tx, ty, tz = 0, px0, py0, pz0 = 0, sx, sy, sz = 1;
     if (!g.grid) {
         ty = tile / g.tiles_x; tx = tile - ty * g.tiles_x;
@@ -442,8 +458,8 @@ struct Work {
     size_t scan_bytes = 0, sort_bytes = 0;
 };
 
-// render particles [i0, i1) of one periodic image through the tile path
-void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1, float ox, float oy, float oz,
+// render particles [i0, i1) with all periodic images of `im` through the tile path in one pass
+void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1, const Images &im,
                   const float *lut_dev, double *acc, double &kernel_ms)
 {
     typedef unsigned long long u64;
@@ -454,7 +470,7 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     wk.counts.alloc(sizeof(u64) * (m + 1));
     wk.offsets.alloc(sizeof(u64) * (m + 1));
     PNB_CUDA(cudaMemsetAsync(wk.counts.as<u64>() + m, 0, sizeof(u64), s));
-    PNB_LAUNCH(k_count_tiles, nblk(m, BS), BS, 0, s, g, c, i0, i1, ox, oy, oz, wk.counts.as<u64>());
+    PNB_LAUNCH(k_count_tiles, nblk(m, BS), BS, 0, s, g, c, i0, i1, im, wk.counts.as<u64>());
     size_t need = 0;
     PNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, wk.counts.as<u64>(), wk.offsets.as<u64>(), m + 1, s));
     if (need > wk.scan_tmp.bytes) wk.scan_tmp.alloc(need);
@@ -464,17 +480,17 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     PNB_CUDA(cudaMemcpyAsync(&total, wk.offsets.as<u64>() + m, sizeof(u64), cudaMemcpyDeviceToHost, s));
     PNB_CUDA(cudaStreamSynchronize(s));
     if (total == 0) return;
-    if ((int64_t)total > MAX_PAIRS && m > 1) {
-        // too many pairs for one batch: footprints are independent and the sums linear, so split
+    if (((int64_t)total > MAX_PAIRS && m > 1) || m > ((int64_t)1 << IMAGE_SHIFT)) {
+        // too many pairs (or particles) for one batch: footprints are independent and the sums linear, so split
         const int64_t mid = i0 + m / 2;
-        render_range(wk, g, c, i0, mid, ox, oy, oz, lut_dev, acc, kernel_ms);
-        render_range(wk, g, c, mid, i1, ox, oy, oz, lut_dev, acc, kernel_ms);
+        render_range(wk, g, c, i0, mid, im, lut_dev, acc, kernel_ms);
+        render_range(wk, g, c, mid, i1, im, lut_dev, acc, kernel_ms);
         return;
     }
     const int64_t P = (int64_t)total;
     wk.keys.alloc(sizeof(uint32_t) * P); wk.vals.alloc(sizeof(uint32_t) * P);
     wk.keys2.alloc(sizeof(uint32_t) * P); wk.vals2.alloc(sizeof(uint32_t) * P);
-    PNB_LAUNCH(k_emit_pairs, nblk(m, BS), BS, 0, s, g, c, i0, i1, ox, oy, oz, wk.offsets.as<u64>(),
+    PNB_LAUNCH(k_emit_pairs, nblk(m, BS), BS, 0, s, g, c, i0, i1, im, wk.offsets.as<u64>(),
                wk.keys.as<uint32_t>(), wk.vals.as<uint32_t>());
     const int64_t ntiles = (int64_t)g.tiles_x * g.tiles_y * g.tiles_z;
     int bits = 1;
@@ -487,7 +503,7 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
         wk.sort_tmp.p, need, wk.keys.as<uint32_t>(), wk.keys2.as<uint32_t>(), wk.vals.as<uint32_t>(), wk.vals2.as<uint32_t>(), P, 0, bits, s)));
     g_launches += 3;
     wk.recs.alloc(sizeof(Rec) * P);
-    PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, ox, oy, oz, P, wk.keys2.as<uint32_t>(),
+    PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, im, P, wk.keys2.as<uint32_t>(),
                wk.vals2.as<uint32_t>(), wk.recs.as<Rec>());
     const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * (size_t)g.ns;
     KernelTimer timer(2, s);
@@ -576,6 +592,8 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
         if (!wrap_x || nwx < 1) { wrap_x = &zero; nwx = 1; }
         if (!wrap_y || nwy < 1) { wrap_y = &zero; nwy = 1; }
         if (!grid || !wrap_z || nwz < 1) { wrap_z = &zero; nwz = 1; }
+        Images im;
+        im.n = 0;
         for (int i = 0; i < nwx; ++i)
             for (int j = 0; j < nwy; ++j)
                 for (int k = 0; k < nwz; ++k) {
@@ -585,10 +603,16 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
                         PNB_LAUNCH(k_render_scatter, nblk(n * 32, 256), 256, 0, s, g, c, ox, oy, lut_dev.as<float>(), acc.as<double>());
                         timer.stop();
                         kernel_ms += pnb_last_kernel_ms(2);
-                    } else {
-                        render_range(wk, g, c, 0, n, ox, oy, oz, lut_dev.as<float>(), acc.as<double>(), kernel_ms);
+                        continue;
+                    }
+                    // all periodic images go through the tile pipeline together (up to MAX_IMAGES per pass)
+                    im.ox[im.n] = ox; im.oy[im.n] = oy; im.oz[im.n] = oz;
+                    if (++im.n == MAX_IMAGES) {
+                        render_range(wk, g, c, 0, n, im, lut_dev.as<float>(), acc.as<double>(), kernel_ms);
+                        im.n = 0;
                     }
                 }
+        if (im.n > 0) render_range(wk, g, c, 0, n, im, lut_dev.as<float>(), acc.as<double>(), kernel_ms);
         PNB_CUDA(cudaStreamSynchronize(s));
     }
     if (out_mem == PNB_DEVICE) {
