@@ -352,15 +352,17 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     const float cx = (float)(g.pdx * (lx + 0.5)), cy = (float)(g.pdy * (ly + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
     const float nsf = (float)g.ns;
 
-    double a = 0.0;
+    // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
+    // reference keeps its whole sum; slices are combined in double
+    float a = 0.0f;
     uint32_t cur = 0xffffffffu;
     int px = 0, py = 0, pz = 0;
     auto flush = [&]() {
-        if (a != 0.0) {
+        if (a != 0.0f) {
             const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)py * g.nx + px;
-            atomicAdd(&acc[pix], a);
+            atomicAdd(&acc[pix], (double)a);
         }
-        a = 0.0;
+        a = 0.0f;
     };
 
     for (int c = 0; c < nchunks; ++c) {
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                 idx = exact_index<GRID>(g, R, px, py, pz);
             }
             const float val = idx < (unsigned)g.ns ? slut[idx] : 0.0f;
-            a += (double)(val * R.wq);
+            a += val * R.wq;
         }
         __syncthreads();
     }
