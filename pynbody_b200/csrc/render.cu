@@ -39,7 +39,7 @@ namespace pnb {
 
 namespace {
 
-constexpr int TILE2 = 16;                       // image tile: 16 x 16 pixels
+constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, two pixels (lx, lx + 16) per thread
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
@@ -152,8 +152,8 @@ __device__ __forceinline__ void tile_span(const Geom &g, const Footprint &f, int
                                           int &va, int &vb)
 {
     if (!g.grid) {
-        ta = f.xa / TILE2; tb = (f.xb - 1) / TILE2;
-        ua = f.ya / TILE2; ub = (f.yb - 1) / TILE2;
+        ta = f.xa / TILE_X; tb = (f.xb - 1) / TILE_X;
+        ua = f.ya / TILE_Y; ub = (f.yb - 1) / TILE_Y;
         va = 0; vb = 0;
     } else {
         ta = f.xa / GTX; tb = (f.xb - 1) / GTX;
@@ -238,7 +238,7 @@ __global__ void k_make_records(Geom g, Cols c, int64_t i0, Images im, int64_t np
     int tx, ty, tz = 0, px0, py0, pz0 = 0, sx, sy, sz = 1;
     if (!g.grid) {
         ty = tile / g.tiles_x; tx = tile - ty * g.tiles_x;
-        px0 = tx * TILE2; py0 = ty * TILE2; sx = sy = TILE2;
+        px0 = tx * TILE_X; py0 = ty * TILE_Y; sx = TILE_X; sy = TILE_Y;
     } else {
         tz = tile % g.tiles_z; int r = tile / g.tiles_z; ty = r % g.tiles_y; tx = r / g.tiles_y;
         px0 = tx * GTX; py0 = ty * GTY; pz0 = tz * GTZ; sx = GTX; sy = GTY; sz = GTZ;
@@ -346,23 +346,32 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     };
     if (tid == 0) issue(0);
 
+    constexpr int NPIX = GRID ? 1 : 2;                 // pixels per thread (image: lx and lx + 16 of a 32-wide tile)
     int lx, ly, lz = 0;
     if (GRID) { lz = tid & (GTZ - 1); ly = (tid >> 3) & (GTY - 1); lx = tid >> 6; }
-    else { lx = tid & (TILE2 - 1); ly = tid >> 4; }
-    const float cx = (float)(g.pdx * (lx + 0.5)), cy = (float)(g.pdy * (ly + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
+    else { lx = tid & 15; ly = tid >> 4; }
+    float cx[NPIX];
+#pragma unroll
+    for (int q = 0; q < NPIX; ++q) cx[q] = (float)(g.pdx * (lx + 16 * q + 0.5));
+    const float cy = (float)(g.pdy * (ly + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
     const float nsf = (float)g.ns;
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
-    float a = 0.0f;
+    float a[NPIX];
+#pragma unroll
+    for (int q = 0; q < NPIX; ++q) a[q] = 0.0f;
     uint32_t cur = 0xffffffffu;
-    int px = 0, py = 0, pz = 0;
+    int px = 0, py = 0, pz = 0;                        // first pixel of this thread in the current tile
     auto flush = [&]() {
-        if (a != 0.0f) {
-            const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)py * g.nx + px;
-            atomicAdd(&acc[pix], (double)a);
+#pragma unroll
+        for (int q = 0; q < NPIX; ++q) {
+            if (a[q] != 0.0f) {
+                const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)py * g.nx + px + 16 * q;
+                atomicAdd(&acc[pix], (double)a[q]);
+            }
+            a[q] = 0.0f;
         }
-        a = 0.0f;
     };
 
     for (int c = 0; c < nchunks; ++c) {
@@ -380,31 +389,36 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                     pz = tz * GTZ + lz; py = (q % g.tiles_y) * GTY + ly; px = (q / g.tiles_y) * GTX + lx;
                 } else {
                     const int ty = cur / g.tiles_x;
-                    py = ty * TILE2 + ly; px = (cur - ty * g.tiles_x) * TILE2 + lx;
+                    py = ty * TILE_Y + ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
                 }
             }
             const uint32_t box = R.box;
-            bool in = ((unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff))
-                      & ((unsigned)(ly - (int)((box >> 16) & 0xff)) < (box >> 24));
-            if (GRID) in &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
-            if (!in) continue;
-            // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a
-            // non-finite weight poisons the same pixels (w * 0 = NaN)
-            unsigned idx;
-            if (R.inv > 0.0f) {
-                const float ddx = R.xr - cx, ddy = R.yr - cy;
-                float d2 = ddx * ddx + ddy * ddy;
-                if (GRID) { const float ddz = R.zr - cz; d2 += ddz * ddz; }
-                else d2 += R.zr;
-                const float t = fminf(d2 * R.inv, nsf + 2.0f);
-                idx = (unsigned)t;
-                const float fr = t - (float)idx;
-                if ((fr < BORDER || fr > 1.0f - BORDER) && t < nsf + 1.0f) idx = exact_index<GRID>(g, R, px, py, pz);
-            } else {
-                idx = exact_index<GRID>(g, R, px, py, pz);
+            bool in_yz = (unsigned)(ly - (int)((box >> 16) & 0xff)) < (box >> 24);
+            if (GRID) in_yz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+            if (!in_yz) continue;
+            const float ddy = R.yr - cy;
+            float d2yz = ddy * ddy;
+            if (GRID) { const float ddz = R.zr - cz; d2yz += ddz * ddz; }
+            else d2yz += R.zr;
+#pragma unroll
+            for (int q = 0; q < NPIX; ++q) {
+                if (!((unsigned)(lx + 16 * q - (int)(box & 0xff)) < ((box >> 8) & 0xff))) continue;
+                // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a
+                // non-finite weight poisons the same pixels (w * 0 = NaN)
+                unsigned idx;
+                if (R.inv > 0.0f) {
+                    const float ddx = R.xr - cx[q];
+                    const float d2 = ddx * ddx + d2yz;
+                    const float t = fminf(d2 * R.inv, nsf + 2.0f);
+                    idx = (unsigned)t;
+                    const float fr = t - (float)idx;
+                    if ((fr < BORDER || fr > 1.0f - BORDER) && t < nsf + 1.0f) idx = exact_index<GRID>(g, R, px + 16 * q, py, pz);
+                } else {
+                    idx = exact_index<GRID>(g, R, px + 16 * q, py, pz);
+                }
+                const float val = idx < (unsigned)g.ns ? slut[idx] : 0.0f;
+                a[q] += val * R.wq;
             }
-            const float val = idx < (unsigned)g.ns ? slut[idx] : 0.0f;
-            a += val * R.wq;
         }
         __syncthreads();
     }
@@ -564,7 +578,7 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
     g.per_z_dx = (float)((x2 - x1) / (2 * z_camera)); g.per_z_dy = (float)((y2 - y1) / (2 * z_camera));
     g.mid_x = (float)((x2 + x1) / 2); g.mid_y = (float)((y2 + y1) / 2);
     if (grid) { g.tiles_x = (nx + GTX - 1) / GTX; g.tiles_y = (ny + GTY - 1) / GTY; g.tiles_z = (nz + GTZ - 1) / GTZ; }
-    else { g.tiles_x = (nx + TILE2 - 1) / TILE2; g.tiles_y = (ny + TILE2 - 1) / TILE2; g.tiles_z = 1; }
+    else { g.tiles_x = (nx + TILE_X - 1) / TILE_X; g.tiles_y = (ny + TILE_Y - 1) / TILE_Y; g.tiles_z = 1; }
     if ((int64_t)g.tiles_x * g.tiles_y * g.tiles_z >= ((int64_t)1 << 31)) throw Error(PNB_ERR_VALUE, "image too large");
 
     const int64_t n = a->n, npix = (int64_t)nx * ny * nz;
