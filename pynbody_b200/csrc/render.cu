@@ -39,7 +39,7 @@ namespace pnb {
 
 namespace {
 
-constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, two pixels (lx, lx + 16) per thread
+constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, two pixels (rows 2w and 2w + 1 of warp w) per thread
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     const int64_t last = min(npairs, first + (int64_t)SEG);
     const int nchunks = (int)((last - first + CHUNK - 1) / CHUNK);
 
-    for (int i = tid; i < g.ns; i += 256) slut[i] = lut[i];
+    for (int i = tid; i < g.ns + 3; i += 256) slut[i] = i < g.ns ? lut[i] : 0.0f;
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -346,14 +346,17 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     };
     if (tid == 0) issue(0);
 
-    constexpr int NPIX = GRID ? 1 : 2;                 // pixels per thread (image: lx and lx + 16 of a 32-wide tile)
+    // Image tiles are 32 x 16 pixels: a warp is one row of 32 pixels (lane = x) and takes rows 2w and 2w + 1, so the
+    // row test of a record's rectangle is warp-uniform -- rows outside cost the warp three instructions instead of
+    // idling its lanes through the pixel arithmetic.  Grid tiles are 4 x 8 x 8 voxels, one per thread.
+    constexpr int NPIX = GRID ? 1 : 2;
     int lx, ly, lz = 0;
     if (GRID) { lz = tid & (GTZ - 1); ly = (tid >> 3) & (GTY - 1); lx = tid >> 6; }
-    else { lx = tid & 15; ly = tid >> 4; }
-    float cx[NPIX];
+    else { lx = tid & 31; ly = tid >> 5; }
+    const float cx = (float)(g.pdx * (lx + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
+    float cy[NPIX];
 #pragma unroll
-    for (int q = 0; q < NPIX; ++q) cx[q] = (float)(g.pdx * (lx + 16 * q + 0.5));
-    const float cy = (float)(g.pdy * (ly + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
+    for (int q = 0; q < NPIX; ++q) cy[q] = (float)(g.pdy * (NPIX * ly + q + 0.5));
     const float nsf = (float)g.ns;
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
 #pragma unroll
         for (int q = 0; q < NPIX; ++q) {
             if (a[q] != 0.0f) {
-                const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)py * g.nx + px + 16 * q;
+                const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)(py + q) * g.nx + px;
                 atomicAdd(&acc[pix], (double)a[q]);
             }
             a[q] = 0.0f;
@@ -389,35 +392,44 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                     pz = tz * GTZ + lz; py = (q % g.tiles_y) * GTY + ly; px = (q / g.tiles_y) * GTX + lx;
                 } else {
                     const int ty = cur / g.tiles_x;
-                    py = ty * TILE_Y + ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
+                    py = ty * TILE_Y + NPIX * ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
                 }
             }
             const uint32_t box = R.box;
-            bool in_yz = (unsigned)(ly - (int)((box >> 16) & 0xff)) < (box >> 24);
-            if (GRID) in_yz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
-            if (!in_yz) continue;
-            const float ddy = R.yr - cy;
-            float d2yz = ddy * ddy;
-            if (GRID) { const float ddz = R.zr - cz; d2yz += ddz * ddz; }
-            else d2yz += R.zr;
+            // rows of this thread inside the record's rectangle (image: the same for the whole warp)
+            const int row0 = GRID ? ly : NPIX * ly;
+            const unsigned rel = (unsigned)(row0 - (int)((box >> 16) & 0xff)), wy = box >> 24;
+            if (!(rel < wy) && !(NPIX > 1 && rel + 1u < wy)) continue;
+            bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
+            if (GRID) in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+            if (!in_xz) continue;
+            const float ddx = R.xr - cx;
+            float d2xz = ddx * ddx;
+            if (GRID) { const float ddz = R.zr - cz; d2xz += ddz * ddz; }
+            else d2xz += R.zr;
+            // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
+            // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
+            // indices past its end need no test
+            const float inv = R.inv, wq = R.wq;
+            const unsigned ns = (unsigned)g.ns;
+            if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
-            for (int q = 0; q < NPIX; ++q) {
-                if (!((unsigned)(lx + 16 * q - (int)(box & 0xff)) < ((box >> 8) & 0xff))) continue;
-                // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a
-                // non-finite weight poisons the same pixels (w * 0 = NaN)
-                unsigned idx;
-                if (R.inv > 0.0f) {
-                    const float ddx = R.xr - cx[q];
-                    const float d2 = ddx * ddx + d2yz;
-                    const float t = fminf(d2 * R.inv, nsf + 2.0f);
-                    idx = (unsigned)t;
+                for (int q = 0; q < NPIX; ++q) {
+                    if (!(rel + (unsigned)q < wy)) continue;
+                    const float ddy = R.yr - cy[q];
+                    const float d2 = ddy * ddy + d2xz;
+                    const float t = fminf(d2 * inv, nsf + 2.0f);
+                    unsigned idx = (unsigned)t;
                     const float fr = t - (float)idx;
-                    if ((fr < BORDER || fr > 1.0f - BORDER) && t < nsf + 1.0f) idx = exact_index<GRID>(g, R, px + 16 * q, py, pz);
-                } else {
-                    idx = exact_index<GRID>(g, R, px + 16 * q, py, pz);
+                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
+                    a[q] += slut[idx] * wq;
                 }
-                const float val = idx < (unsigned)g.ns ? slut[idx] : 0.0f;
-                a[q] += val * R.wq;
+            } else {                                           // tiny kernels: exact index only
+#pragma unroll
+                for (int q = 0; q < NPIX; ++q) {
+                    if (!(rel + (unsigned)q < wy)) continue;
+                    a[q] += slut[min(exact_index<GRID>(g, R, px, py + q, pz), ns)] * wq;
+                }
             }
         }
         __syncthreads();
@@ -521,7 +533,7 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     wk.recs.alloc(sizeof(Rec) * P);
     PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, im, P, wk.keys2.as<uint32_t>(),
                wk.vals2.as<uint32_t>(), wk.recs.as<Rec>());
-    const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * (size_t)g.ns;
+    const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * ((size_t)g.ns + 3);
     KernelTimer timer(2, s);
     if (g.grid) {
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
