@@ -201,3 +201,26 @@ def test_healpix_medium_and_errors(luts):
     img = _render.render_spherical_image_core(*args)
     assert img.shape == (768,)
     assert_image_close(img, oracle.render_spherical_image_core(*args))
+
+
+def test_many_periodic_images(luts):
+    """An image five box lengths wide: 7 x 7 = 49 periodic images per particle (renderers.py:616-629), more
+    than one pass of the tile pipeline carries (32), and a 3-D grid with 3 x 3 x 3 = 27 images in one pass."""
+    from oracle import oracle
+    from pynbody_b200 import sph
+    from pynbody_b200.sph import _render
+    pos, sm, mass, rho, qty = _particles(4000, 38, np.float64, 0.03, 0.5)
+    kern = ref.LutKernel(luts["cubic2d"], 2)
+    wrap = sph.wrapping_repeat_array(-2.5, 2.5, 1.0)
+    assert len(wrap) == 7
+    args = (160, 160, pos[:, 0], pos[:, 1], pos[:, 2], sm, -2.5, 2.5, -2.5, 2.5, 0.0, 0.0, qty, mass, rho,
+            0.0, np.inf, -np.inf, np.inf, 0.0, kern, wrap, wrap)
+    img = _render.render_image(*args)
+    assert_image_close(img, oracle.render_image(*args))
+    # the picture repeats with the box: pixel (i, j) equals pixel (i + 32, j) (32 pixels = one box length)
+    np.testing.assert_allclose(img[40:72, 40:72], img[72:104, 40:72], rtol=2e-4, atol=1e-6 * img.max())
+    k3 = ref.LutKernel(luts["cubic3d"], 3)
+    w3 = [-1.0, 0.0, 1.0]
+    gargs = (24, 24, 24, pos[:, 0], pos[:, 1], pos[:, 2], sm, -0.5, 0.5, -0.5, 0.5, -0.5, 0.5, qty, mass, rho,
+             0.0, np.inf, k3, w3, w3, w3)
+    assert_image_close(_render.to_3d_grid(*gargs), oracle.to_3d_grid(*gargs))
