@@ -130,11 +130,11 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 double v[NC];
                 if (OP == OP_RHO) {
                     // rho_i += (W * norm) * m_j, each term rounded as the reference rounds it (smooth.h:640-645)
-                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);       // (float or double overload)
                     w *= norm;
                     v[0] = (double)(w * tile.m[j]);
                 } else if (!OT::grad) {
-                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)(d2 * ih2));
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);       // (float or double overload)
                     w *= norm;
                     const double wm = (double)w * tile.mr[j];
                     if (!OT::two_pass || PASS == 0) {
@@ -151,7 +151,7 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 } else {
                     // raw UNWRAPPED separation (smooth.h:736-738, :791-793), wrapped r2 in the kernel
                     const T dx = (T)tile.c[2][ii] - px, dy = (T)tile.c[3][ii] - py, dz = (T)tile.c[4][ii] - pz;
-                    T g = (T)kern_g(a.kernel_id, (double)(d2 * ih2), (double)d2);
+                    T g = (T)kern_g(a.kernel_id, d2 * ih2, d2);
                     g *= norm;
                     const T dq0 = (T)((double)tile.q[0][j] - tile.c[5][ii]);
                     const T dq1 = (T)((double)tile.q[1][j] - tile.c[6][ii]);

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                 T rho = 0;
                 for (int e = 0; e < k; ++e) {
                     T q2 = queue_value(q, e) * ih2;
-                    T w = (T)kern_w(a.kernel_id, a.wendland_self, (double)q2);
+                    T w = (T)kern_w(a.kernel_id, a.wendland_self, q2);
                     w *= norm;
                     rho += w * m;
                 }
