@@ -441,10 +441,17 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
 
 void pnb_tree_destroy(pnb_tree *h) { delete reinterpret_cast<Tree *>(h); }
 
-int64_t pnb_tree_num_particles(const pnb_tree *h) { return reinterpret_cast<const Tree *>(h)->n; }
+// a null handle is a caller error, not a crash
+#define PNB_NEED_TREE(h)                                                     \
+    do {                                                                     \
+        if (!(h)) { set_last_error("tree handle is null"); return PNB_ERR_VALUE; } \
+    } while (0)
+
+int64_t pnb_tree_num_particles(const pnb_tree *h) { PNB_NEED_TREE(h); return reinterpret_cast<const Tree *>(h)->n; }
 
 int pnb_tree_bounds(const pnb_tree *h, double *out6)
 {
+    PNB_NEED_TREE(h);
     const Tree *t = reinterpret_cast<const Tree *>(h);
     for (int d = 0; d < 3; ++d) { out6[d] = t->root_min[d]; out6[3 + d] = t->root_max[d]; }
     return PNB_OK;
@@ -452,6 +459,7 @@ int pnb_tree_bounds(const pnb_tree *h, double *out6)
 
 int64_t pnb_tree_node_count(const pnb_tree *h)
 {
+    PNB_NEED_TREE(h);
     const Tree *t = reinterpret_cast<const Tree *>(h);
     int64_t n = t->n, l = 1;                      // kd.cpp:98-111
     while (n > t->user_leafsize) { n >>= 1; l <<= 1; }
@@ -460,6 +468,7 @@ int64_t pnb_tree_node_count(const pnb_tree *h)
 
 int pnb_tree_order(pnb_tree *h, int64_t *out)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         std::vector<uint32_t> o((size_t)t->n);
@@ -468,10 +477,11 @@ int pnb_tree_order(pnb_tree *h, int64_t *out)
     });
 }
 
-int64_t pnb_tree_num_buckets(const pnb_tree *h) { return reinterpret_cast<const Tree *>(h)->nsplit; }
+int64_t pnb_tree_num_buckets(const pnb_tree *h) { PNB_NEED_TREE(h); return reinterpret_cast<const Tree *>(h)->nsplit; }
 
 int pnb_tree_buckets(pnb_tree *h, int64_t *start, double *bounds)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         std::vector<int32_t> s((size_t)t->nsplit + 1);
@@ -490,12 +500,14 @@ int pnb_tree_buckets(pnb_tree *h, int64_t *start, double *bounds)
 
 int pnb_tree_export(pnb_tree *h, void *kdnodes_out, int64_t n_nodes, int64_t *offsets_out)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] { require_device(); export_reference_tree(*t, kdnodes_out, n_nodes, offsets_out); });
 }
 
 int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t stride1, int ncols, int dtype, int mem)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         if (id < 0 || id > 4) throw Error(PNB_ERR_VALUE, "invalid array id");
@@ -538,6 +550,7 @@ __global__ void k_u8_to_file(const uint32_t *order, const uint8_t *in_tree, uint
 
 int pnb_set_query_mask(pnb_tree *h, const uint8_t *mask, int mem)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         if (!mask) {
@@ -564,6 +577,7 @@ int pnb_set_query_mask(pnb_tree *h, const uint8_t *mask, int mem)
 int pnb_mark_in_balls(pnb_tree *h, const void *centres, int64_t stride0, int64_t stride1, const void *radii,
                       int64_t rstride, int64_t nq, double period_in, uint8_t *flags_out, int mem)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         require_device();
@@ -591,12 +605,14 @@ int pnb_mark_in_balls(pnb_tree *h, const void *centres, int64_t stride0, int64_t
 
 int pnb_populate(pnb_tree *h, int propid, int k, int kernel_id, double period, int *period_ignored)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] { populate(*t, propid, k, kernel_id, period, period_ignored); });
 }
 
 int pnb_knn(pnb_tree *h, int k, double period_in, int64_t *idx_out, void *d2_out, void *h_out, int *period_ignored)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         require_device();
@@ -623,6 +639,7 @@ int pnb_knn(pnb_tree *h, int k, double period_in, int64_t *idx_out, void *d2_out
 int pnb_ball_query(pnb_tree *h, double cx, double cy, double cz, double r, double period_in, int64_t *out,
                    int64_t cap, int64_t *n_found)
 {
+    PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         require_device();

@@ -141,3 +141,15 @@ def test_describe_handles_strides_and_dtypes():
     assert (s0, ncols) == (12, 1) and ptr == a.ctypes.data + 4
     with pytest.raises(ValueError):
         _lib.describe(np.zeros(4, np.int32))
+
+
+def test_null_tree_handle_is_an_error_not_a_crash():
+    """Every entry point that takes a tree handle reports PNB_ERR_VALUE for a null handle (no device needed)."""
+    from pynbody_b200 import _lib
+    L = _lib.lib()
+    assert L.pnb_tree_num_particles(None) == _lib.ERR_VALUE
+    assert L.pnb_tree_node_count(None) == _lib.ERR_VALUE
+    assert L.pnb_tree_num_buckets(None) == _lib.ERR_VALUE
+    assert L.pnb_populate(None, 1, 32, 0, 0.0, None) == _lib.ERR_VALUE
+    assert b"null" in L.pnb_last_error()
+    L.pnb_tree_destroy(None)                      # like free(NULL)
