@@ -36,6 +36,8 @@ extern "C" {
 #define PNB_ERR_RUNTIME  -3   /* -> RuntimeError (gather overflow, smooth.h:253-267) */
 #define PNB_ERR_CUDA     -4   /* -> RuntimeError (CUDA failure / no device) */
 #define PNB_ERR_MEMORY   -5   /* -> MemoryError  */
+/* Every function that takes a `pnb_tree *` returns PNB_ERR_VALUE for a null handle; pnb_tree_destroy(NULL)
+ * is a no-op.  pnb_last_error() returns the message of the last failure on the calling thread. */
 
 #define PNB_F32 0
 #define PNB_F64 1
