@@ -709,7 +709,33 @@ __device__ __forceinline__ size_t hp_pixel_index(size_t nside, size_t iring, siz
     return npix - nr * (nr - 1) * 2 + iphi - 1 - 4 * nr;
 }
 
-__global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *__restrict__ lut, double *__restrict__ acc)
+// Unit vector of every pixel centre, (st cos(phi), st sin(phi), ct, -) exactly as the per-pixel code forms them
+// (healpix.c pix2vec for the RING scheme).  Filled once per call so that a (particle, pixel) pair costs a 32-byte
+// load instead of a double-precision sincos.
+__global__ void k_hp_pixel_vectors(int nside_i, double4 *__restrict__ vec)
+{
+    const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
+    const size_t nside = (size_t)nside_i;
+    const size_t iring = (size_t)blockIdx.y + 1;                 // 1 .. 4 nside - 1
+    size_t n_in_ring, shift;
+    if (iring <= nside) { n_in_ring = 4 * iring; shift = 1; }
+    else if (iring <= 3 * nside) { n_in_ring = 4 * nside; shift = 2 - (iring - nside + 1) % 2; }
+    else { n_in_ring = 4 * (4 * nside - iring); shift = 1; }
+    const size_t ip = (size_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (ip > n_in_ring) return;
+    const double z = hp_z_from_ring_num(nside, iring);
+    const double theta = acos(z);
+    double st, ct;
+    sincos(theta, &st, &ct);
+    double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
+    if (phi >= twopi) phi -= twopi;
+    double sphi, cphi;
+    sincos(phi, &sphi, &cphi);
+    vec[hp_pixel_index(nside, iring, ip)] = make_double4(st * cphi, st * sphi, ct, 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *__restrict__ lut, double *__restrict__ acc,
+                                                        const double4 *__restrict__ pixvec)
 {
     const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
     const int lane = threadIdx.x & 31;
@@ -804,11 +830,18 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             size_t ip = (size_t)R.ip_lo + (size_t)(f - first);
             if (ip > n_in_ring) ip -= n_in_ring;
             const size_t ipix = hp_pixel_index(nside, R.iring, ip);
-            double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
-            if (phi >= twopi) phi -= twopi;
-            double sphi, cphi;
-            sincos(phi, &sphi, &cphi);
-            double dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
+            double dot;
+            if (pixvec && ip >= 1) {             // (ip = 0 happens at phi ~ 0: the reference then takes the direction
+                                                 // of "pixel 0" of the ring but the index before the ring's first)
+                const double4 pv = pixvec[ipix];
+                dot = v0 * pv.x + v1 * pv.y + v2 * pv.z;
+            } else {
+                double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
+                if (phi >= twopi) phi -= twopi;
+                double sphi, cphi;
+                sincos(phi, &sphi, &cphi);
+                dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
+            }
             if (dot > 1.0) dot = 1.0;
             if (dot < -1.0) dot = -1.0;
             const double dist = acos(dot);
@@ -871,8 +904,16 @@ void render_healpix(const pnb_render_arrays *a, int nside, const float *lut, int
         h.pos_f64 = a->pos_dtype; h.h_f64 = a->sm_dtype; h.qty_f64 = a->qty_dtype; h.mass_f64 = a->mass_dtype;
         h.rho_f64 = a->rho_dtype; h.n = n; h.nside = nside; h.ns = n_lut; h.projected = h_power == 2;
         h.max_d = max_d; h.shell_radius = shell_radius;
+        // pixel-centre vectors, if the table fits comfortably (32 B per pixel: nside 2048 -> 1.6 GB)
+        DevBuf pixvec;
+        if (nside <= 2048) {
+            pixvec.alloc(sizeof(double4) * (size_t)npix);
+            dim3 grid((unsigned)((4 * (size_t)nside + 255) / 256), (unsigned)(4 * nside - 1));
+            PNB_LAUNCH(k_hp_pixel_vectors, grid, 256, 0, s, nside, pixvec.as<double4>());
+        }
         KernelTimer timer(2, s);
-        PNB_LAUNCH(k_render_healpix, nblk(n * 32, 256), 256, 0, s, h, lut_dev.as<float>(), acc.as<double>());
+        PNB_LAUNCH(k_render_healpix, nblk(n * 32, 256), 256, 0, s, h, lut_dev.as<float>(), acc.as<double>(),
+                   pixvec.p ? pixvec.as<double4>() : (const double4 *)nullptr);
         timer.stop();
         kernel_ms = pnb_last_kernel_ms(2);
     }
