@@ -163,7 +163,7 @@ struct LeftFlag {
 // stable partition of all three lists about each node's split rank, using the global prefix sum S of
 // "goes to the lower child" flags over the concatenated lists
 __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__ L, const uint8_t *__restrict__ side,
-                            const uint32_t *__restrict__ S, uint32_t *__restrict__ Lnew)
+                            const int8_t *__restrict__ dim, const uint32_t *__restrict__ S, uint32_t *__restrict__ Lnew)
 {
     const int64_t n = s.n;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -173,6 +173,10 @@ __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__
     seg_of_pos(s, level, p, lo, hi, node);
     int64_t m = split_rank(s, level, lo, hi);
     uint32_t id = L[i];
+    if (s.packed && dim[node] == d) {                // the list of the split axis is partitioned as it stands
+        Lnew[i] = id;
+        return;
+    }
     uint32_t left_before = S[i] - S[d * n + lo];     // modular arithmetic: exact because < 2^32
     int64_t dest = side[id] ? (m + 1) + (p - lo) - (int64_t)left_before : lo + (int64_t)left_before;
     Lnew[d * n + dest] = id;
@@ -244,7 +248,7 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
         PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
         g_launches += 2;
-        PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, shape, level, L, side.as<uint8_t>(), S.as<uint32_t>(), Ln);
+        PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
         uint32_t *tmp = L; L = Ln; Ln = tmp;
     }
     PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
