@@ -197,3 +197,24 @@ def test_selection_oracle_errors_and_empty():
     with pytest.raises(ValueError, match="C-contiguous"):
         oracle.selection(np.zeros((4, 6))[:, ::2], "sphere", (0, 0, 0, 1), -1.0)
     assert oracle.selection(np.zeros((0, 3)), "sphere", (0, 0, 0, 1), -1.0).shape == (0,)
+
+
+@pytest.mark.skipif(not ref.available(), reason="compiled reference not built")
+@pytest.mark.parametrize("seed", range(6))
+def test_selection_oracle_equals_compiled_reference_on_random_regions(seed):
+    """Random regions, box sizes and dtypes, including regions that straddle the periodic boundary and cuboids
+    whose upper corner lies beyond the box (Cuboid._get_boundaries adds one box length, filt/__init__.py:301-310)."""
+    rng = np.random.default_rng(100 + seed)
+    dtype = (np.float32, np.float64)[seed % 2]
+    box = float(rng.choice([1.0, 37.5, 1000.0]))
+    pos = np.ascontiguousarray(rng.uniform(-box / 2, box / 2, (5000, 3)).astype(dtype))
+    for _ in range(8):
+        c = rng.uniform(-box / 2, box / 2, 3)
+        r = float(rng.uniform(0.01, 0.6) * box)
+        wrap = dtype(box if rng.random() < 0.7 else -1.0)
+        assert np.array_equal(oracle.selection(pos, "sphere", (c[0], c[1], c[2], r), wrap),
+                              ref.selection(pos, "sphere", (c[0], c[1], c[2], r), wrap))
+        lo = rng.uniform(-box / 2, box / 2, 3)
+        hi = lo + rng.uniform(0.01, 0.9, 3) * box
+        prm = (lo[0], lo[1], lo[2], hi[0], hi[1], hi[2])
+        assert np.array_equal(oracle.selection(pos, "cube", prm, wrap), ref.selection(pos, "cube", prm, wrap))
