@@ -8,9 +8,9 @@
 // root for its 32 query particles, each lane testing every node against its own ball of radius
 // 2 h_i (periodic cell test kd.h:68-154, acceptance d2 <= fl(4 h h), smooth.h:310 with
 // kdmain.cpp:779).  Candidate buckets are staged in shared memory together with the per-particle
-// fields the reduction needs (mass, rho, quantity); accepted candidates are collected in a register
-// bit-mask and reduced with all lanes working together.  Nothing is written to global memory except
-// the final per-particle result: no neighbour lists are materialised.
+// fields the reduction needs (mass, mass/rho, quantity); the accepted (query, candidate) pairs of a
+// bucket are listed in shared memory and evaluated one pair per lane (see gather_sweep).  Nothing is
+// written to global memory except the final per-particle result: no neighbour lists are materialised.
 #include "traverse.cuh"
 
 namespace pnb {
