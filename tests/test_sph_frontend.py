@@ -140,3 +140,56 @@ def test_weighted_denoised_and_healpix_pipelines():
     want = oracle.render_spherical_image_core(rho, mass, temp, hx, hy, hz, sm, 16, k3, 1.0)
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6 * want.max())
     assert sph.render_healpix(hp_pos, mass, rho, sm, nside=None, kernel=k3).shape == (12 * 64 * 64,)
+
+
+def test_pipeline_compositions_on_cpu_with_the_oracle_as_native_layer(monkeypatch):
+    """The decorator logic itself (which passes are made, with which kernel, quantity and geometry) checked on
+    CPU: the native entry points are replaced by the oracle's restatements of the reference functions."""
+    from oracle import oracle
+    from pynbody_b200.sph import _render, kernels
+    monkeypatch.setattr(_render, "render_image", oracle.render_image)
+    monkeypatch.setattr(_render, "to_3d_grid", oracle.to_3d_grid)
+    monkeypatch.setattr(_render, "render_spherical_image_core", oracle.render_spherical_image_core)
+    rng = np.random.default_rng(8)
+    n = 3000
+    pos = rng.uniform(-0.5, 0.5, (n, 3))
+    sm = rng.lognormal(np.log(0.05), 0.3, n)
+    mass = np.full(n, 1.0 / n)
+    rho = rng.uniform(0.5, 2.0, n)
+    temp = rng.uniform(1.0, 2.0, n)
+    k3 = kernels.CubicSplineKernel()
+    k2 = k3.projection()
+    x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+
+    def direct(q, kern, z0=0.0, wrap=(0.0,)):
+        return oracle.render_image(24, 24, x, y, z, sm, -0.5, 0.5, -0.5, 0.5, 0.0, z0, q, mass, rho, 0.0, np.inf, -np.inf,
+                                   np.inf, 0.0, kern, list(wrap), list(wrap))
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # plain projection and slice, periodic offsets generated as ImageRenderer does
+        img = sph.render_image(pos, mass, rho, sm, temp, width=1.0, resolution=24, kernel=k3, boxsize=1.0)
+        assert np.array_equal(img, direct(temp, k2, wrap=(-1.0, 0.0, 1.0)))
+        img = sph.render_image(pos, mass, rho, sm, None, width=1.0, resolution=24, kernel=k3, projected=False, z_plane=0.1)
+        assert np.array_equal(img, direct(rho, k3, z0=0.1))
+        # weighted projection = projected(q w) / projected(w); volume weighting uses w = 1
+        img = sph.render_image(pos, mass, rho, sm, temp, width=1.0, resolution=24, kernel=k3, projected=False, weight=rho)
+        assert np.array_equal(img, direct(temp * rho, k2) / direct(rho, k2), equal_nan=True)
+        img = sph.render(pos, mass, rho, sm, temp, target="image", width=1.0, resolution=24, kernel=k3, projected=False,
+                         weight=True)
+        assert np.array_equal(img, direct(temp, k2) / direct(np.ones(n), k2), equal_nan=True)
+        # denoised slice = slice(q) / slice(1)
+        img = sph.render_image(pos, mass, rho, sm, temp, width=1.0, resolution=24, kernel=k3, projected=False, denoise=True)
+        assert np.array_equal(img, direct(temp, k3) / direct(np.ones(n), k3), equal_nan=True)
+        # volume target: cube of side `width`, denoised
+        grid = sph.render(pos, mass, rho, sm, temp, target="volume", width=1.0, resolution=8, kernel=k3, denoise=True)
+        g = lambda q: oracle.to_3d_grid(8, 8, 8, x, y, z, sm, -0.5, 0.5, -0.5, 0.5, -0.5, 0.5, q, mass, rho, 0.0, np.inf, k3,
+                                        [0.0], [0.0], [0.0])
+        assert np.array_equal(grid, g(temp) / g(np.ones(n)), equal_nan=True)
+    # healpix: projection by default, thin shell with the 3-D kernel when a shell distance is given
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    hp = d * rng.uniform(0.7, 1.3, n)[:, None]
+    got = sph.render(hp, mass, rho, sm, temp, target="healpix", nside=8, kernel=k3)
+    assert np.array_equal(got, oracle.render_spherical_image_core(rho, mass, temp, hp[:, 0], hp[:, 1], hp[:, 2], sm, 8, k2))
+    got = sph.render_healpix(hp, mass, rho, sm, temp, nside=8, kernel=k3, shell_distance=1.0)
+    assert np.array_equal(got, oracle.render_spherical_image_core(rho, mass, temp, hp[:, 0], hp[:, 1], hp[:, 2], sm, 8, k3, 1.0))
