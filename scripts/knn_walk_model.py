@@ -322,3 +322,50 @@ for R,C in ((2,64),(4,64),(4,96),(6,64),(8,64)):
         s=walk_capped(int(h),R,C)
         for k,v in s.items(): tot[k]=tot.get(k,0)+v
     print("capped",R,C,{k:round(v/len(homes),1) for k,v in tot.items()})
+
+
+# ---- a larger bulk fill: the first buckets are absorbed by a selection that costs no insert rounds ----
+def walk_bulkfill(home, nfree, order="tree"):
+    """first `nfree` candidate buckets (incl. own + sibling) are absorbed by a bulk selection (no rounds);
+    the rest go through insert rounds"""
+    hq=pos[leaves[home]]
+    top=np.full(32,np.inf)
+    cur=[[] for _ in range(32)]
+    st=dict(tiles=0,rounds=0)
+    seen=0
+    def visit(node, free):
+        c=pos[leaves[node]]
+        d=((hq[:,None,:]-c[None,:,:])**2).sum(-1)
+        if free:
+            for i in range(32):
+                cur[i]=sorted(cur[i]+list(d[i]))[:K]
+                if len(cur[i])==K: top[i]=cur[i][-1]
+            return
+        g=gap2(hq,node); passl=g<=top
+        st['tiles']+=1; mx=0
+        for i in range(32):
+            if not passl[i]: continue
+            s=np.nonzero(d[i]<top[i])[0]; mx=max(mx,len(s))
+            for j in s:
+                if d[i,j]<top[i]:
+                    cur[i][-1]=d[i,j]; cur[i].sort(); top[i]=cur[i][-1]
+        st['rounds']+=mx
+    visit(home, True); seen=1
+    cell=home
+    while cell!=1:
+        cp=cell^1; stop=next_node(cp)
+        while True:
+            g=gap2(hq,cp)
+            if (g<=top).any():
+                if cp<NB: cp=2*cp; continue
+                visit(cp, seen<nfree); seen+=1
+            cp=next_node(cp)
+            if cp==stop: break
+        cell>>=1
+    return st
+for nfree in (2,3,4,6,8):
+    tot={}
+    for h in homes:
+        s=walk_bulkfill(int(h),nfree)
+        for k,v in s.items(): tot[k]=tot.get(k,0)+v
+    print("bulk fill of first",nfree,"buckets:",{k:round(v/len(homes),1) for k,v in tot.items()})
