@@ -117,14 +117,24 @@ class GpuBackend:
 # ------------------------------------------------------------------------------------------------
 # domain decomposition
 # ------------------------------------------------------------------------------------------------
-def _bisect(sample, weight, lo, hi, ranks, out):
+class Domains(list):
+    """One (lo[3], hi[3]) cuboid per rank, plus the bisection that produced them: ``splits`` is a list of
+    (axis, plane, left, right) with children >= 0 pointing at another split and -(rank + 1) at a leaf."""
+    splits = None
+
+
+def _bisect(sample, weight, lo, hi, ranks, out, splits=None):
     """Recursive coordinate bisection of box [lo,hi) among `ranks`: split planes at the (weighted) quantiles
     of the coordinate sample.  ``sample`` is a [3][m] tensor (one contiguous row per axis) that stays on the
     device it was gathered on -- only the chosen axis and plane of each node come back to the host;
     ``weight`` = estimated search cost per sample point, or None.  lo / hi are host tensors."""
     if len(ranks) == 1:
         out[ranks[0]] = (lo.clone(), hi.clone())
-        return
+        return -(ranks[0] + 1)
+    me = None
+    if splits is not None:
+        me = len(splits)
+        splits.append(None)
     nleft = len(ranks) // 2
     m = int(sample.shape[1])
     if m > 1:
@@ -150,8 +160,11 @@ def _bisect(sample, weight, lo, hi, ranks, out):
     hi_l, lo_r = hi.clone(), lo.clone()
     hi_l[axis] = q
     lo_r[axis] = q
-    _bisect(sample[:, left], None if weight is None else weight[left], lo, hi_l, ranks[:nleft], out)
-    _bisect(sample[:, ~left], None if weight is None else weight[~left], lo_r, hi, ranks[nleft:], out)
+    cl = _bisect(sample[:, left], None if weight is None else weight[left], lo, hi_l, ranks[:nleft], out, splits)
+    cr = _bisect(sample[:, ~left], None if weight is None else weight[~left], lo_r, hi, ranks[nleft:], out, splits)
+    if splits is not None:
+        splits[me] = (axis, float(q), cl, cr)
+    return me
 
 
 # Optional cost feedback (PNB_DIST_COST_FEEDBACK=1): after a smoothing pass the ranks share how long their
@@ -217,14 +230,31 @@ def decompose(pos, boxsize, group=None, sample_per_rank=8192, seed=0):
     else:
         lo = torch.full((3,), float("-inf"), dtype=dt)
         hi = torch.full((3,), float("inf"), dtype=dt)
-    out = [None] * world
-    _bisect(samp, _sample_weights(world, samp), lo, hi, list(range(world)), out)
+    out = Domains([None] * world)
+    out.splits = []
+    _bisect(samp, _sample_weights(world, samp), lo, hi, list(range(world)), out, out.splits)
     return out, periodic
 
 
 def owner_of(pos, domains):
     """Rank owning each particle.  Faces on the outside of the decomposed box are treated as open, so
     a particle sitting exactly on (or rounded just past) the outer edge still has exactly one owner."""
+    splits = getattr(domains, "splits", None)
+    if splits:
+        # walk the bisection: one coordinate comparison per level instead of a box test per rank
+        n = pos.shape[0]
+        dev = pos.device
+        axis = torch.tensor([sp[0] for sp in splits], dtype=torch.int64, device=dev)
+        plane = torch.tensor([sp[1] for sp in splits], dtype=pos.dtype, device=dev)
+        child = torch.tensor([[sp[2], sp[3]] for sp in splits], dtype=torch.int64, device=dev)
+        node = torch.zeros(n, dtype=torch.int64, device=dev)             # >= 0: split index; < 0: -(rank + 1)
+        depth = max(1, int(math.ceil(math.log2(max(len(domains), 2)))) + 1)
+        for _ in range(depth):
+            at = node.clamp(min=0)
+            coord = pos.gather(1, axis[at][:, None]).squeeze(1)
+            nxt = child[at, (coord >= plane[at]).to(torch.int64)]
+            node = torch.where(node >= 0, nxt, node)
+        return -node - 1
     owner = torch.zeros(pos.shape[0], dtype=torch.int64, device=pos.device)
     root_lo = torch.stack([d[0] for d in domains]).min(dim=0).values
     root_hi = torch.stack([d[1] for d in domains]).max(dim=0).values

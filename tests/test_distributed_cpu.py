@@ -118,3 +118,27 @@ def test_decompose_is_balanced_and_tiles_the_box():
     work = np.array([w[(owner2 == r).numpy()].sum() for r in range(8)])
     assert work.min() > 0.9 * work.mean() and work.max() < 1.1 * work.mean()
     assert abs(sum(float(torch.prod(h - l)) for l, h in out2) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_owner_by_bisection_walk_equals_owner_by_box_test(world):
+    """owner_of walks the recorded bisection when it is available; the result must be the one of the plain
+    box test against every rank's cuboid (particles on a split plane go to the upper side in both)."""
+    from pynbody_b200.distributed import Domains, _bisect, owner_of
+    pos, _, _ = synth.clumpy_box(30000, 13, np.float64)
+    tp = torch.from_numpy(pos)
+    doms = Domains([None] * world)
+    doms.splits = []
+    zero, one = torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)
+    _bisect(tp.t().contiguous(), None, zero, one, list(range(world)), doms, doms.splits)
+    assert len(doms.splits) == world - 1
+    plain = list(doms)                                   # a plain list has no bisection attached
+    by_walk, by_box = owner_of(tp, doms), owner_of(tp, plain)
+    assert torch.equal(by_walk, by_box)
+    # points exactly on a split plane and outside the decomposed box
+    axis, plane = doms.splits[0][0], doms.splits[0][1]
+    edge = tp[:64].clone()
+    edge[:32, axis] = plane
+    edge[32:, 0] = 1.5
+    assert torch.equal(owner_of(edge, doms), owner_of(edge, plain))
+    assert int(torch.bincount(by_walk, minlength=world).min()) > 0
