@@ -72,6 +72,13 @@ const char *pnb_last_error(void);
 const char *pnb_version(void);
 /* number of usable CUDA devices (0 if none); never fails */
 int pnb_device_count(void);
+/* Process-wide tuning switches (no reference counterpart):
+ *   "neighbour_lists"  -1 (default) keep each particle's k neighbour ids on the device after the kNN pass when
+ *                      they fit in half of the free device memory, so that rho / mean / dispersion / div / curl
+ *                      stream over them instead of searching again; 0 never; 1 always.  (env PNB_NEIGHBOUR_LISTS)
+ *   "gather_walk"      1: the reductions always use the tree-walking fixed-radius gather.  (env PNB_GATHER_WALK)
+ * PNB_ERR_VALUE for an unknown name. */
+int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */
 int pnb_set_device(int device);
 
@@ -139,6 +146,23 @@ int pnb_mark_in_balls(pnb_tree *t, const void *centres, int64_t stride0, int64_t
  * included with d2 = 0), d2_out T[N][k], h_out T[N] (may be NULL); rows in file order; host memory. */
 int pnb_knn(pnb_tree *t, int k, double period, int64_t *idx_out, void *d2_out, void *h_out,
             int *period_ignored);
+
+/* The same, lazily, as the reference's nn_start / nn_next iteration (kdmain.cpp:344-382, 390-440): pnb_knn_start
+ * runs the search once and leaves every particle's neighbour list resident on the device (ids 4 bytes +
+ * d2 sizeof(T) bytes per neighbour; the registered smooth array, if any, is overwritten with h as the
+ * reference does, smooth.h:429); pnb_knn_rows then copies out the rows of the particles with file index
+ * first .. first+count-1 (idx_out int64[count][k], d2_out T[count][k], h_out T[count] or NULL; host memory), so
+ * a caller iterating over 10^7 particles never holds more than one chunk.  PNB_ERR_VALUE if no list is
+ * resident or the range is outside [0, N]. */
+int pnb_knn_start(pnb_tree *t, int k, double period, int *period_ignored);
+int pnb_knn_rows(pnb_tree *t, int64_t first, int64_t count, int64_t *idx_out, void *d2_out, void *h_out);
+
+/* ---- nCnt of typed_populate's gather (kdmain.cpp:779: smBallGather(4*hsm*hsm), smooth.h:270-324) -----------
+ * Number of particles with d2 <= fl(4 h h) around every particle, for the registered smooth array (file order,
+ * int32[N]; k-1, k, or more on exact ties -- SURVEY.md section 7b).  The reference keeps this count internal
+ * (it decides the k+500 overflow error, smooth.h:253-267); it is exposed so that parity of the gather's
+ * neighbour SET SIZES can be tested.  Always computed by the tree walk, never from the neighbour lists. */
+int pnb_gather_counts(pnb_tree *t, double period, int32_t *counts_out, int mem);
 
 /* ---- kdmain.particles_in_sphere (kdmain.cpp:655-679) ------------------------------------------
  * File-order ids of particles with d2 <= r*r of (cx,cy,cz) (centre and radius are rounded to the

@@ -243,6 +243,13 @@ int orc_populate(void *h, int propid, int k, double period, int kernel_id,
     if (q_is_f64) return populate_f32f64(kd, propid, k, period, kernel_id, sm, mass, rho, qty, out, nthreads);
     return populate_f32f32(kd, propid, k, period, kernel_id, sm, mass, rho, qty, out, nthreads);
 }
+/* nCnt of the gather pass (kdmain.cpp:779) for every particle, file order */
+void orc_gather_counts(void *h, double period, const void *sm, int32_t *counts, int nthreads)
+{
+    kd_t *kd = (kd_t *)h;
+    if (kd->is_f64) gather_counts_f64(kd, period, (const double *)sm, counts, nthreads);
+    else gather_counts_f32(kd, period, (const float *)sm, counts, nthreads);
+}
 /* kdmain.cpp:655-679: centre and radius are parsed in the tree dtype. */
 int64_t orc_ball(void *h, double period, double cx, double cy, double cz, double r,
                  int64_t *out, int64_t cap)

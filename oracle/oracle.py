@@ -43,6 +43,8 @@ def lib():
         L.orc_smooth.argtypes = [_vp, _i32, _dbl, _vp, _i32]
         L.orc_nn.argtypes = [_vp, _i32, _dbl, _vp, _vp, _vp, _vp]
         L.orc_populate.argtypes = [_vp, _i32, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32]
+        L.orc_gather_counts.restype = None
+        L.orc_gather_counts.argtypes = [_vp, _dbl, _vp, _vp, _i32]
         L.orc_ball.restype = _i64
         L.orc_ball.argtypes = [_vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _i64]
         L.orc_render_image.restype = None
@@ -132,6 +134,13 @@ class OracleKDTree:
                 "disp": "qty_disp_nd" if nd else "qty_disp_1d",
                 "div": "qty_div", "curl": "qty_curl"}[op]
         self._populate(mode, nn, smooth, rho, qty, out)
+        return out
+
+    def gather_counts(self, smooth=None):
+        """nCnt of smBallGather(4 h^2) for every particle (kdmain.cpp:779, smooth.h:270-324), file order."""
+        smooth = self._smooth if smooth is None else np.ascontiguousarray(smooth, dtype=self._pos.dtype)
+        out = np.empty(len(self._pos), np.int32)
+        lib().orc_gather_counts(self._h, self.boxsize, _p(smooth), _p(out), self.num_threads)
         return out
 
     def particles_in_sphere(self, center, radius):

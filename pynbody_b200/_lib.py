@@ -41,6 +41,7 @@ SIGNATURES = {
     "pnb_version": (C.c_char_p, []),
     "pnb_device_count": (_i32, []),
     "pnb_set_device": (_i32, [_i32]),
+    "pnb_set_option": (_i32, [C.c_char_p, _i32]),
     "pnb_tree_create": (_vp, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32]),
     "pnb_tree_destroy": (None, [_vp]),
     "pnb_tree_num_particles": (_i64, [_vp]),
@@ -55,6 +56,9 @@ SIGNATURES = {
     "pnb_mark_in_balls": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _vp, _i32]),
     "pnb_populate": (_i32, [_vp, _i32, _i32, _i32, _dbl, _pi32]),
     "pnb_knn": (_i32, [_vp, _i32, _dbl, _vp, _vp, _vp, _pi32]),
+    "pnb_knn_start": (_i32, [_vp, _i32, _dbl, _pi32]),
+    "pnb_knn_rows": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "pnb_gather_counts": (_i32, [_vp, _dbl, _vp, _i32]),
     "pnb_ball_query": (_i32, [_vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _i64, _pi64]),
     "pnb_render_image": (_i32, [_i32, _i32, C.POINTER(RenderArrays)] + [_dbl] * 11
                          + [_vp, _i32, _i32, _dbl, _vp, _i32, _vp, _i32, _vp, _i32]),

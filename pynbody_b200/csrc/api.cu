@@ -5,6 +5,7 @@
 // smInit (smooth.h:71-124), array registration, and moving results back to the caller's borrowed
 // arrays in file order.
 #include "common.cuh"
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -137,6 +138,12 @@ void cache_free(void *p, size_t bytes)
     }
     c.free_lists[{dev, bytes}].push_back(p);
     c.cached_bytes += bytes;
+}
+size_t cached_bytes()
+{
+    BlockCache &c = block_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    return c.cached_bytes;
 }
 void cache_trim()
 {
@@ -289,6 +296,25 @@ static void update_mass_uniformity(Tree &t)
     t.uniform_mass = m0;
 }
 
+int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 auto (keep them if they fit), 0 never, 1 always
+int g_opt_gather_walk = 0;          // pnb_set_option("gather_walk"): 1 = reductions always walk the tree
+static struct OptionsFromEnv {
+    OptionsFromEnv()
+    {
+        if (const char *e = getenv("PNB_NEIGHBOUR_LISTS")) g_opt_neighbour_lists = atoi(e);
+        if (const char *e = getenv("PNB_GATHER_WALK")) g_opt_gather_walk = atoi(e);
+    }
+} g_options_from_env;
+
+// The resident neighbour lists serve a reduction iff they come from this tree's own kNN pass with the same k
+// (the caller has verified that the smooth array is that pass's result and that the period matches).
+// PNB_GATHER=walk forces the tree-walking gather (tests compare the two paths).
+static bool lists_usable(const Tree &t, int k)
+{
+    if (g_opt_gather_walk) return false;
+    return t.nn_valid && t.nn_k == k && t.nn_ids.p != nullptr;
+}
+
 static void populate(Tree &t, int propid, int k, int kernel_id, double period_in, int *period_ignored)
 {
     require_device();
@@ -303,7 +329,7 @@ static void populate(Tree &t, int propid, int k, int kernel_id, double period_in
 
     if (propid == PNB_PROP_HSM) {
         const ArrRef &sm = need(t, PNB_ARR_SMOOTH, "smooth");       // kdmain.cpp:633-639
-        run_knn(t, k, period, /*fuse_rho=*/t.has_mass, kp, nullptr, nullptr);
+        run_knn(t, k, period, /*fuse_rho=*/t.has_mass, kp, /*keep_ids=*/neighbour_lists_fit(t, k, false), false);
         store_from_tree_order(t, sm, t.smooth_t.p);
         timer.stop();
         return;
@@ -354,7 +380,9 @@ static void populate(Tree &t, int propid, int k, int kernel_id, double period_in
             store_from_tree_order(t, out, t.rho_t.p);                // density fused with the kNN pass
         } else {
             DevBuf rho_tree(ts * t.n);
-            if (run_gather(t, propid, k, period, kp, smooth_tree.p, nullptr, nullptr, t.dtype, rho_tree.p))
+            if (own_smooth && lists_usable(t, k))
+                run_gather_lists(t, propid, k, period, kp, smooth_tree.p, nullptr, nullptr, t.dtype, rho_tree.p);
+            else if (run_gather(t, propid, k, period, kp, smooth_tree.p, nullptr, nullptr, t.dtype, rho_tree.p))
                 throw Error(PNB_ERR_RUNTIME, "Buffer overflow in smoothing operation. This probably means that your smoothing lengths are too large compared to the number of neighbours you specified.");
             store_from_tree_order(t, out, rho_tree.p);
         }
@@ -374,10 +402,84 @@ static void populate(Tree &t, int propid, int k, int kernel_id, double period_in
     DevBuf rho_tree = fetch_tree_order(t, rhor);
     DevBuf qty_tree = fetch_tree_order(t, qty);
     DevBuf out_tree(tsize(out.dtype) * out.ncols * t.n);
-    if (run_gather(t, propid, k, period, kp, smooth_tree.p, rho_tree.p, qty_tree.p, qty.dtype, out_tree.p))
+    if (own_smooth && lists_usable(t, k))
+        run_gather_lists(t, propid, k, period, kp, smooth_tree.p, rho_tree.p, qty_tree.p, qty.dtype, out_tree.p);
+    else if (run_gather(t, propid, k, period, kp, smooth_tree.p, rho_tree.p, qty_tree.p, qty.dtype, out_tree.p))
         throw Error(PNB_ERR_RUNTIME, "Buffer overflow in smoothing operation. This probably means that your smoothing lengths are too large compared to the number of neighbours you specified.");
     store_from_tree_order(t, out, out_tree.p);
     timer.stop();
+}
+
+// rows of the resident neighbour lists for the particles with FILE index first .. first+count-1
+template <typename T>
+__global__ void k_nn_rows(int64_t first, int64_t count, int k, int K2, const uint32_t *__restrict__ inv,
+                          const uint32_t *__restrict__ order, const uint32_t *__restrict__ ids,
+                          const T *__restrict__ d2, const T *__restrict__ smooth_t, int64_t *__restrict__ idx_out,
+                          T *__restrict__ d2_out, T *__restrict__ h_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= count) return;
+    const uint32_t p = inv[first + r];
+    const size_t base = (size_t)(p >> 5) * K2 * 32 + (p & 31u);
+    for (int e = lane; e < k; e += 32) {
+        idx_out[r * k + e] = (int64_t)order[ids[base + (size_t)e * 32]];
+        d2_out[r * k + e] = d2[base + (size_t)e * 32];
+    }
+    if (lane == 0 && h_out) h_out[r] = smooth_t[p];
+}
+__global__ void k_invert_order(const uint32_t *__restrict__ order, uint32_t *__restrict__ inv, int64_t n)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n) inv[order[p]] = (uint32_t)p;
+}
+
+static void knn_start(Tree &t, int k, double period_in, int *period_ignored)
+{
+    require_device();
+    if (k > t.n) throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
+    if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
+    const double period = effective_period(t, period_in, period_ignored);
+    StageTimer timer(1, t.stream);
+    run_knn(t, k, period, false, make_kernel_params(0, k), /*keep_ids=*/true, /*keep_d2=*/true);
+    if (!t.inv_order.p) {
+        t.inv_order.alloc(sizeof(uint32_t) * (size_t)t.n);
+        PNB_LAUNCH(k_invert_order, (unsigned)((t.n + 255) / 256), 256, 0, t.stream, t.order.as<uint32_t>(),
+                   t.inv_order.as<uint32_t>(), t.n);
+    }
+    if (t.arr[PNB_ARR_SMOOTH].set()) store_from_tree_order(t, t.arr[PNB_ARR_SMOOTH], t.smooth_t.p);   // smooth.h:429
+    PNB_CUDA(cudaStreamSynchronize(t.stream));
+    timer.stop();
+}
+
+static void knn_rows(Tree &t, int64_t first, int64_t count, int64_t *idx_out, void *d2_out, void *h_out)
+{
+    require_device();
+    if (!t.nn_valid || !t.nn_d2.p || !t.inv_order.p)
+        throw Error(PNB_ERR_VALUE, "pnb_knn_rows: no neighbour lists; call pnb_knn_start first");
+    if (first < 0 || count < 0 || first + count > t.n) throw Error(PNB_ERR_VALUE, "pnb_knn_rows: row range outside the particle set");
+    const int k = t.nn_k;
+    const size_t ts = tsize(t.dtype);
+    // staged through a bounded device buffer (<= 256 MiB of rows at a time)
+    const int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)k * (8 + (int64_t)ts)));
+    DevBuf idx(sizeof(int64_t) * (size_t)std::min(chunk, std::max<int64_t>(count, 1)) * k),
+           d2(ts * (size_t)std::min(chunk, std::max<int64_t>(count, 1)) * k), hh(ts * (size_t)std::min(chunk, std::max<int64_t>(count, 1)));
+    for (int64_t done = 0; done < count; done += chunk) {
+        const int64_t m = std::min(chunk, count - done);
+        const unsigned grid = (unsigned)((m + 7) / 8);
+        if (t.dtype == PNB_F64)
+            PNB_LAUNCH((k_nn_rows<double>), grid, 256, 0, t.stream, first + done, m, k, t.nn_K2, t.inv_order.as<uint32_t>(),
+                       t.order.as<uint32_t>(), t.nn_ids.as<uint32_t>(), t.nn_d2.as<double>(), t.smooth_t.as<double>(),
+                       idx.as<int64_t>(), d2.as<double>(), hh.as<double>());
+        else
+            PNB_LAUNCH((k_nn_rows<float>), grid, 256, 0, t.stream, first + done, m, k, t.nn_K2, t.inv_order.as<uint32_t>(),
+                       t.order.as<uint32_t>(), t.nn_ids.as<uint32_t>(), t.nn_d2.as<float>(), t.smooth_t.as<float>(),
+                       idx.as<int64_t>(), d2.as<float>(), hh.as<float>());
+        PNB_CUDA(cudaMemcpyAsync(idx_out + done * k, idx.p, sizeof(int64_t) * (size_t)m * k, cudaMemcpyDeviceToHost, t.stream));
+        PNB_CUDA(cudaMemcpyAsync((char *)d2_out + ts * (size_t)done * k, d2.p, ts * (size_t)m * k, cudaMemcpyDeviceToHost, t.stream));
+        if (h_out) PNB_CUDA(cudaMemcpyAsync((char *)h_out + ts * (size_t)done, hh.p, ts * (size_t)m, cudaMemcpyDeviceToHost, t.stream));
+        PNB_CUDA(cudaStreamSynchronize(t.stream));
+    }
 }
 
 }  // namespace pnb
@@ -394,6 +496,16 @@ int pnb_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int pnb_set_option(const char *name, int value)
+{
+    return guarded([&] {
+        if (!name) throw Error(PNB_ERR_VALUE, "option name is null");
+        if (!strcmp(name, "neighbour_lists")) g_opt_neighbour_lists = value;
+        else if (!strcmp(name, "gather_walk")) g_opt_gather_walk = value;
+        else throw Error(PNB_ERR_VALUE, std::string("unknown option ") + name);
+    });
 }
 
 int pnb_set_device(int device)
@@ -528,6 +640,7 @@ int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t strid
             const bool same = t->has_mass && device_equal(*t, m.p, t->mass.p, tsize(dtype) * (size_t)t->n);
             if (!same) {
                 t->mass = std::move(m);
+                t->pos4.release();
                 t->has_mass = true;
                 t->rho_valid = false;
                 update_mass_uniformity(*t);
@@ -554,11 +667,12 @@ int pnb_set_query_mask(pnb_tree *h, const uint8_t *mask, int mem)
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         if (!mask) {
-            if (t->query_mask.p) { t->query_mask.release(); t->smooth_valid = false; t->rho_valid = false; }
+            if (t->query_mask.p) { t->query_mask.release(); t->smooth_valid = false; t->rho_valid = false; t->nn_valid = false; }
             return;
         }
         t->smooth_valid = false;
         t->rho_valid = false;
+        t->nn_valid = false;
         require_device();
         DevBuf file_mask;
         const uint8_t *src = mask;
@@ -610,29 +724,47 @@ int pnb_populate(pnb_tree *h, int propid, int k, int kernel_id, double period, i
     return guarded([&] { populate(*t, propid, k, kernel_id, period, period_ignored); });
 }
 
+int pnb_knn_start(pnb_tree *h, int k, double period, int *period_ignored)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] { knn_start(*t, k, period, period_ignored); });
+}
+
+int pnb_knn_rows(pnb_tree *h, int64_t first, int64_t count, int64_t *idx_out, void *d2_out, void *h_out)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] { knn_rows(*t, first, count, idx_out, d2_out, h_out); });
+}
+
 int pnb_knn(pnb_tree *h, int k, double period_in, int64_t *idx_out, void *d2_out, void *h_out, int *period_ignored)
 {
     PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
+        knn_start(*t, k, period_in, period_ignored);
+        knn_rows(*t, 0, t->n, idx_out, d2_out, h_out);
+    });
+}
+
+int pnb_gather_counts(pnb_tree *h, double period_in, int32_t *counts_out, int mem)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
         require_device();
-        if (k > t->n) throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
-        if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
-        const double period = effective_period(*t, period_in, period_ignored);
-        const size_t ts = tsize(t->dtype);
-        StageTimer timer(1, t->stream);
-        DevBuf idx(sizeof(int64_t) * (size_t)t->n * k), d2(ts * (size_t)t->n * k);
-        run_knn(*t, k, period, false, make_kernel_params(0, k), idx.as<int64_t>(), d2.p);
-        PNB_CUDA(cudaMemcpyAsync(idx_out, idx.p, idx.bytes, cudaMemcpyDeviceToHost, t->stream));
-        PNB_CUDA(cudaMemcpyAsync(d2_out, d2.p, d2.bytes, cudaMemcpyDeviceToHost, t->stream));
-        if (h_out) {
-            DevBuf hf(ts * t->n);
-            permute_to_file(*t, t->smooth_t.p, hf.p, 1, (int)ts, t->stream);
-            PNB_CUDA(cudaMemcpyAsync(h_out, hf.p, hf.bytes, cudaMemcpyDeviceToHost, t->stream));
-            PNB_CUDA(cudaStreamSynchronize(t->stream));
-        }
+        if (!counts_out) throw Error(PNB_ERR_VALUE, "counts pointer is null");
+        const double period = effective_period(*t, period_in, nullptr);
+        const ArrRef &smr = need(*t, PNB_ARR_SMOOTH, "smooth");
+        DevBuf smooth_tree = fetch_tree_order(*t, smr);
+        DevBuf counts_tree(sizeof(int32_t) * (size_t)t->n), counts_file(sizeof(int32_t) * (size_t)t->n);
+        PNB_CUDA(cudaMemsetAsync(counts_tree.p, 0, counts_tree.bytes, t->stream));
+        run_gather_counts(*t, period, smooth_tree.p, counts_tree.as<int32_t>());
+        permute_to_file(*t, counts_tree.p, counts_file.p, 1, 4, t->stream);
+        PNB_CUDA(cudaMemcpyAsync(counts_out, counts_file.p, counts_file.bytes,
+                                 mem == PNB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, t->stream));
         PNB_CUDA(cudaStreamSynchronize(t->stream));
-        timer.stop();
     });
 }
 

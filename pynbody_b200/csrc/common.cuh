@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <stdexcept>
@@ -48,6 +49,7 @@ extern thread_local int64_t g_launches;
 void *cache_alloc(size_t bytes);
 void cache_free(void *p, size_t bytes);
 void cache_trim();
+size_t cached_bytes();      // idle bytes the cache could hand out or give back
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;     // requested size
@@ -119,6 +121,7 @@ struct Tree {
     bool mass_is_uniform = false; // every particle has the same mass (then density can ride along the kNN pass)
     double uniform_mass = 0;
     DevBuf order;                 // uint32[n]: tree position -> file index
+    DevBuf inv_order;             // uint32[n]: file index -> tree position (made on demand: pnb_knn_rows)
     DevBuf box;                   // T[2*nsplit][6]: tight bounds of every node (heap index, root = 1)
     DevBuf bucket_start;          // int32[nsplit + 1]
     DevBuf split_dim, split_val;  // int8 / T [2*nsplit]: split axis and value of internal nodes (export only)
@@ -133,6 +136,14 @@ struct Tree {
     int rho_kernel = -1;
 
     DevBuf query_mask;            // uint8[n] tree order, or empty: restricts populate / knn to a subset
+
+    // neighbour lists of the last kNN pass (knn.cu): entry e of the particle at tree position 32*b+l is at
+    // [(b*nn_K2 + e)*32 + l]; valid together with smooth_t (same k, same period, same query mask)
+    DevBuf nn_ids;                // uint32[nsplit][nn_K2][32] tree positions of the neighbours (~0u: padding slot)
+    DevBuf nn_d2;                 // T, same layout: their squared distances (kept only for nn())
+    bool nn_valid = false;
+    DevBuf pos4;                  // packed {x, y, z, m} records in tree order for the list reductions (gather_list.cu)
+    int nn_k = 0, nn_K2 = 0;
 
     ArrRef arr[5];
 };
@@ -185,8 +196,17 @@ struct KernelParams {
 KernelParams make_kernel_params(int kernel_id, int k);
 
 // kNN pass: writes t.smooth_t (and t.rho_t when fuse_rho); optional neighbour lists (file order rows)
+// keep_ids: also record every particle's neighbour list in t.nn_ids (and the distances in t.nn_d2 if keep_d2)
 void run_knn(Tree &t, int k, double period /* <=0: open */, bool fuse_rho, const KernelParams &kp,
-             int64_t *nn_idx_dev, void *nn_d2_dev);
+             bool keep_ids, bool keep_d2);
+bool neighbour_lists_fit(const Tree &t, int k, bool with_d2);
+extern int g_opt_neighbour_lists, g_opt_gather_walk;     // pnb_set_option (api.cu)
+// reductions over the resident neighbour lists (gather_list.cu); same arguments as run_gather
+void run_gather_lists(Tree &t, int propid, int k, double period, const KernelParams &kp,
+                      const void *smooth_tree, const void *rho_tree, const void *qty_tree, int qdtype,
+                      void *out_tree);
+// nCnt of the reference's gather for every particle (tree order), through the tree walk (gather.cu)
+void run_gather_counts(Tree &t, double period, const void *smooth_tree, int32_t *counts_tree);
 // gather pass for property ids 2..8.  All inputs are dense device arrays in TREE order.
 // smooth/rho: T[n]; qty: Tq [ncols][n]; out: T[n] (rho) or Tq[ncols_out][n].
 // Returns true if some particle found more than k+500 neighbours (smooth.h:253-267).

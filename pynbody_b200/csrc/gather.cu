@@ -18,7 +18,8 @@ namespace pnb {
 constexpr int GATHER_WARPS = 4;
 constexpr int RESMOOTH_SAFE = 500;   // smooth.h:15
 
-enum { OP_RHO = 2, OP_MEAN1 = 3, OP_MEAN3 = 4, OP_DISP1 = 5, OP_DISP3 = 6, OP_DIV = 7, OP_CURL = 8 };
+enum { OP_RHO = 2, OP_MEAN1 = 3, OP_MEAN3 = 4, OP_DISP1 = 5, OP_DISP3 = 6, OP_DIV = 7, OP_CURL = 8,
+       OP_COUNT = 9 /* only the neighbour count nCnt of the gather (kdmain.cpp:779) */ };
 
 template <typename T, typename Q>
 struct GatherArgs {
@@ -34,7 +35,7 @@ struct GatherArgs {
 };
 
 template <int OP> struct OpTraits {
-    static constexpr int qcols = (OP == OP_MEAN1 || OP == OP_DISP1) ? 1 : (OP == OP_RHO ? 0 : 3);
+    static constexpr int qcols = (OP == OP_MEAN1 || OP == OP_DISP1) ? 1 : ((OP == OP_RHO || OP == OP_COUNT) ? 0 : 3);
     static constexpr int ocols = (OP == OP_MEAN3 || OP == OP_CURL) ? 3 : 1;
     static constexpr bool two_pass = (OP == OP_DISP1 || OP == OP_DISP3);
     static constexpr bool grad = (OP == OP_DIV || OP == OP_CURL);
@@ -66,7 +67,7 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                                              T qx, T qy, T qz, T ball2, int &count)
 {
     using OT = OpTraits<OP>;
-    constexpr int NC = (OT::two_pass && PASS == 1) ? 1 : (OP == OP_RHO || OP == OP_DIV ? 1 : OT::qcols);
+    constexpr int NC = (OT::two_pass && PASS == 1) ? 1 : (OP == OP_RHO || OP == OP_DIV || OP == OP_COUNT ? 1 : OT::qcols);
     const TreeView<T> &tv = a.tv;
     const T L = tv.period;
     int64_t cp = 1;
@@ -86,8 +87,8 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 const int64_t j = start + lane;
                 cx = tv.x[j]; cy = tv.y[j]; cz = tv.z[j];
                 tile.x[lane] = cx; tile.y[lane] = cy; tile.z[lane] = cz;
-                tile.m[lane] = tv.mass[j];
-                if (OP != OP_RHO) {
+                if (OP != OP_COUNT) tile.m[lane] = tv.mass[j];
+                if (OP != OP_RHO && OP != OP_COUNT) {
                     tile.mr[lane] = (double)tile.m[lane] / (double)a.rho_t[j];
 #pragma unroll
                     for (int c = 0; c < OT::qcols; ++c) tile.q[c][lane] = a.qty_t[(int64_t)c * tv.n + j];
@@ -111,9 +112,9 @@ __device__ __forceinline__ void gather_sweep(const GatherArgs<T, Q> &a, Tile<T, 
                 else d2 = dist2_nearest<T>((T)tile.c[2][i], (T)tile.c[3][i], (T)tile.c[4][i], cx, cy, cz, L);
                 const bool in = lane < cnt && d2 <= ub;                         // smooth.h:310 (non-strict)
                 const unsigned row = __ballot_sync(FULL, in);
-                if (in) tile.pairs[npairs + __popc(row & ((1u << lane) - 1u))] = (uint16_t)(i << 5 | lane);
+                if (OP != OP_COUNT && in) tile.pairs[npairs + __popc(row & ((1u << lane) - 1u))] = (uint16_t)(i << 5 | lane);
                 if (PASS == 0 && lane == i) count += __popc(row);
-                npairs += __popc(row);
+                if (OP != OP_COUNT) npairs += __popc(row);
             }
             __syncwarp();
             // 2. one interaction per lane
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) k_gather(GatherArgs<T, Q> a
     }
     __syncwarp();
     if (!active) return;
+    if (OP == OP_COUNT) { reinterpret_cast<int32_t *>(a.out_t)[p] = count; return; }
     if (count > a.k + RESMOOTH_SAFE) atomicOr(a.overflow, 1);      // smooth.h:253-267
     if (OP == OP_RHO) {
         reinterpret_cast<T *>(a.out_t)[p] = (T)tile.acc[0][lane];
@@ -294,6 +296,27 @@ static bool run_gather_typed(Tree &t, int propid, int k, double period, const Ke
     PNB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, t.stream));
     PNB_CUDA(cudaStreamSynchronize(t.stream));
     return h != 0;
+}
+
+void run_gather_counts(Tree &t, double period, const void *smooth_tree, int32_t *counts_tree)
+{
+    const KernelParams kp = make_kernel_params(0, 1);
+    if (t.dtype == PNB_F64) {
+        GatherArgs<double, double> a;
+        a.tv = make_view<double>(t, period);
+        a.k = 1; a.kernel_id = 0; a.wendland_self = kp.wendland_self;
+        a.smooth_t = (const double *)smooth_tree; a.rho_t = nullptr; a.qty_t = nullptr;
+        a.out_t = counts_tree; a.overflow = nullptr;
+        launch_gather<double, double, OP_COUNT>(t, a);
+    } else {
+        GatherArgs<float, float> a;
+        a.tv = make_view<float>(t, period);
+        a.k = 1; a.kernel_id = 0; a.wendland_self = kp.wendland_self;
+        a.smooth_t = (const float *)smooth_tree; a.rho_t = nullptr; a.qty_t = nullptr;
+        a.out_t = counts_tree; a.overflow = nullptr;
+        launch_gather<float, float, OP_COUNT>(t, a);
+    }
+    PNB_CUDA(cudaStreamSynchronize(t.stream));
 }
 
 bool run_gather(Tree &t, int propid, int k, double period, const KernelParams &kp, const void *smooth_tree,

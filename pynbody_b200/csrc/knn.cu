@@ -16,6 +16,14 @@
 // The kernel is persistent: warps take buckets in tree order from a global counter.
 // (-DKNN_STATS builds a variant that counts buckets, survivors, insert rounds and node tests.)
 //
+// NEIGHBOUR LISTS.  With KEEP_IDS the id of every queued neighbour is written straight to its final place in
+// the tree's resident neighbour list (Tree::nn_ids, uint32 tree positions, laid out [bucket][slot][lane] so that
+// a warp reads or writes one 128-byte line per slot): the queue's slot e of lane l IS list entry e of particle
+// 32*bucket+l.  The ids never enter shared memory (which bounds occupancy), cost one fire-and-forget global
+// store per insertion, and stay in L2 while a bucket is being worked on.  Every later reduction over the same
+// neighbours (density with unequal masses, mean, dispersion, div, curl; gather_list.cu) and nn() read these
+// lists instead of walking the tree again.
+//
 // The queue (the reference's max-heap, pq.h) is a TOURNAMENT TREE per lane in shared memory,
 // lane-interleaved (element e of lane l at [e*32+l]: conflict-free): K2 = 2^ceil(log2 k) leaf slots
 // hold the keys, K2-1 one-byte internal nodes hold the leaf index of the larger child's winner; the
@@ -53,8 +61,8 @@ struct KnnArgs {
     double uniform_mass;
     int kernel_id;
     double wendland_self;
-    int64_t *nn_idx;        // [n][k] file-order rows, or null
-    T *nn_d2;               // [n][k]
+    uint32_t *nn_ids;       // [nsplit][K2][32] neighbour list (KEEP_IDS), tree positions; padding slots hold ~0u
+    T *nn_d2;               // same layout: the queued distances, written once at the end of a search, or null
     unsigned long long *next_bucket;   // work counter
     uint32_t *lo_scratch;   // [resident warps][K2][32] low words of the queued d2 (float64 only)
 };
@@ -70,7 +78,7 @@ struct Queue {
     Key *hd;                // leaves [K2], stride 32
     uint32_t *lo;           // low words [K2], stride 32, global memory (float64)
     W_t *W;                 // internal nodes [K2] (heap order, node 0 unused), stride 32: winner leaf index
-    int32_t *hi;            // neighbour ids [K2] (WITH_IDX)
+    uint32_t *hi;           // neighbour ids [K2], stride 32, GLOBAL memory: the tree's resident list (KEEP_IDS)
     int LOG, K2;
     T top;                  // float: the root winner's value = k-th smallest d2 so far.  double: an UPPER BOUND of it
                             // (exact high word, low word all ones) -- the exact low word is fetched only on demand
@@ -111,7 +119,7 @@ __device__ __forceinline__ double queue_value(const Queue<double, W_t> &q, int e
 // LOGC >= 0: tree depth known at compile time (k <= 32 / 64 / 128: the path is fully unrolled without
 // predicates); LOGC < 0: depth read from the queue (any k <= 1024)
 template <typename W_t, int LOGC, bool WITH_IDX>
-__device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v, int32_t id)
+__device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v, uint32_t id)
 {
     constexpr int NL = LOGC >= 0 ? LOGC : MAXLOG;
     const int e = q.etop;
@@ -141,7 +149,7 @@ __device__ __forceinline__ void queue_replace_max(Queue<float, W_t> &q, float v,
 }
 
 template <typename W_t, int LOGC, bool WITH_IDX>
-__device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double v, int32_t id)
+__device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double v, uint32_t id)
 {
     constexpr int NL = LOGC >= 0 ? LOGC : MAXLOG;
     const int e = q.etop;
@@ -271,7 +279,7 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
                               : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
             leaf_store(q, filled + j, d2);
-            if (WITH_IDX) q.hi[(filled + j) * 32] = start + j;
+            if (WITH_IDX) q.hi[(filled + j) * 32] = (uint32_t)(start + j);
         }
         filled += take;
         if (filled < k) return;
@@ -324,7 +332,7 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             mask &= mask - 1;
             const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
                               : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (below_top(q, d2)) { queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, start + j); ins = true; }
+            if (below_top(q, d2)) { queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, (uint32_t)(start + j)); ins = true; }
         }
 #ifdef KNN_STATS
         unsigned b = __ballot_sync(FULL, ins);
@@ -338,8 +346,7 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
 template <typename T, typename W_t, bool WITH_IDX>
 __host__ __device__ inline size_t knn_smem_per_warp(int K2)
 {
-    size_t b = (size_t)K2 * 32 * sizeof(typename KeyOf<T>::type) + (size_t)K2 * 32 * sizeof(W_t)
-               + (WITH_IDX ? (size_t)K2 * 32 * 4 : 0) + 96 * sizeof(T);
+    size_t b = (size_t)K2 * 32 * sizeof(typename KeyOf<T>::type) + (size_t)K2 * 32 * sizeof(W_t) + 96 * sizeof(T);
     return (b + 127) & ~(size_t)127;
 }
 
@@ -365,7 +372,6 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     q.hd = reinterpret_cast<Key *>(base) + lane;
     unsigned char *after = base + (size_t)K2 * 32 * sizeof(Key);
     q.hi = nullptr;
-    if (WITH_IDX) { q.hi = reinterpret_cast<int32_t *>(after) + lane; after += (size_t)K2 * 32 * 4; }
     q.W = reinterpret_cast<W_t *>(after) + lane;
     after += (size_t)K2 * 32 * sizeof(W_t);
     T *tile = reinterpret_cast<T *>(after);       // 16-byte aligned: every array above is a multiple of 32 bytes
@@ -384,11 +390,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         if (!__any_sync(FULL, active)) continue;    // no query of this bucket is selected
         T qx = 0, qy = 0, qz = 0;
         if (active) { qx = tv.x[start + lane]; qy = tv.y[start + lane]; qz = tv.z[start + lane]; }
+        if (WITH_IDX) q.hi = a.nn_ids + (size_t)bucket * K2 * 32 + lane;
 
         for (int e = k; e < K2; ++e) {              // padding leaves hold the smallest key and never win
             q.hd[e * 32] = padding_key(T());
             if (sizeof(T) == 8) q.lo[e * 32] = 0u;
-            if (WITH_IDX) q.hi[e * 32] = -1;
+            if (WITH_IDX) q.hi[e * 32] = ~0u;
         }
         int filled = 0;                             // leaves filled so far; -1 once the tournament has been built
         q.etop = 0;
@@ -447,13 +454,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                 }
                 a.rho_t[p] = rho;
             }
-            if (WITH_IDX && a.nn_idx) {
-                const int64_t row = (int64_t)tv.order[p] * k;
-                for (int e = 0; e < k; ++e) {
-                    a.nn_idx[row + e] = (int64_t)tv.order[q.hi[e * 32]];
-                    a.nn_d2[row + e] = queue_value(q, e);
-                }
-            }
+        }
+        if (WITH_IDX && a.nn_d2) {                  // the queued distances, beside the ids (nn() only)
+            T *d2o = a.nn_d2 + (size_t)bucket * K2 * 32 + lane;
+            for (int e = 0; e < k; ++e) d2o[e * 32] = queue_value(q, e);
         }
         __syncwarp();
     }
@@ -520,16 +524,17 @@ static void launch_knn(Tree &t, KnnArgs<T> &a)
 }
 
 template <typename T, typename W_t, int LOGC>
-static void dispatch_knn(Tree &t, KnnArgs<T> &a, bool with_idx, bool fuse_rho)
+static void dispatch_knn(Tree &t, KnnArgs<T> &a, bool keep_ids, bool fuse_rho)
 {
-    if (with_idx) launch_knn<T, W_t, LOGC, true, false>(t, a);
-    else if (fuse_rho) launch_knn<T, W_t, LOGC, false, true>(t, a);
+    if (keep_ids) {
+        if (fuse_rho) launch_knn<T, W_t, LOGC, true, true>(t, a);
+        else launch_knn<T, W_t, LOGC, true, false>(t, a);
+    } else if (fuse_rho) launch_knn<T, W_t, LOGC, false, true>(t, a);
     else launch_knn<T, W_t, LOGC, false, false>(t, a);
 }
 
 template <typename T>
-static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp,
-                          int64_t *nn_idx_dev, void *nn_d2_dev)
+static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp, bool keep_ids, bool keep_d2)
 {
     if (!t.smooth_t.p) t.smooth_t.alloc(sizeof(T) * t.n);
     if (fuse_rho && !t.rho_t.p) t.rho_t.alloc(sizeof(T) * t.n);
@@ -539,34 +544,64 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     a.LOG = 0;
     while ((1 << a.LOG) < k) ++a.LOG;
     if (a.LOG > MAXLOG) throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large (at most 1024)");
+    const size_t slots = (size_t)t.nsplit * ((size_t)1 << a.LOG) * 32;
+    t.nn_valid = false;
+    if (keep_ids) {
+        if (t.nn_ids.bytes != slots * sizeof(uint32_t)) t.nn_ids.alloc(slots * sizeof(uint32_t));
+        if (keep_d2) { if (t.nn_d2.bytes != slots * sizeof(T)) t.nn_d2.alloc(slots * sizeof(T)); }
+        else t.nn_d2.release();
+    } else {
+        t.nn_ids.release();
+        t.nn_d2.release();
+    }
     a.smooth_t = t.smooth_t.as<T>();
     a.rho_t = t.rho_t.as<T>();
     a.uniform_mass = t.uniform_mass;
     a.kernel_id = kp.kernel_id;
     a.wendland_self = kp.wendland_self;
-    a.nn_idx = nn_idx_dev;
-    a.nn_d2 = (T *)nn_d2_dev;
-    const bool idx = nn_idx_dev != nullptr;
+    a.nn_ids = keep_ids ? t.nn_ids.as<uint32_t>() : nullptr;
+    a.nn_d2 = keep_ids && keep_d2 ? t.nn_d2.as<T>() : nullptr;
     switch (a.LOG) {                                   // the usual neighbour counts get fully unrolled queues
-    case 5: dispatch_knn<T, uint8_t, 5>(t, a, idx, fuse_rho); break;
-    case 6: dispatch_knn<T, uint8_t, 6>(t, a, idx, fuse_rho); break;
-    case 7: dispatch_knn<T, uint8_t, 7>(t, a, idx, fuse_rho); break;
+    case 5: dispatch_knn<T, uint8_t, 5>(t, a, keep_ids, fuse_rho); break;
+    case 6: dispatch_knn<T, uint8_t, 6>(t, a, keep_ids, fuse_rho); break;
+    case 7: dispatch_knn<T, uint8_t, 7>(t, a, keep_ids, fuse_rho); break;
     default:
-        if (a.LOG <= 8) dispatch_knn<T, uint8_t, -1>(t, a, idx, fuse_rho);
-        else dispatch_knn<T, uint16_t, -1>(t, a, idx, fuse_rho);
+        if (a.LOG <= 8) dispatch_knn<T, uint8_t, -1>(t, a, keep_ids, fuse_rho);
+        else dispatch_knn<T, uint16_t, -1>(t, a, keep_ids, fuse_rho);
+    }
+    if (keep_ids) {
+        t.nn_valid = true;
+        t.nn_k = k;
+        t.nn_K2 = 1 << a.LOG;
     }
 }
 
-void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp, int64_t *nn_idx_dev, void *nn_d2_dev)
+// Neighbour lists cost n * K2 * 4 bytes (k = 64: 256 B per particle).  They are kept when they fit beside
+// everything else: at most half of the device memory that is free right now (pnb_set_option
+// "neighbour_lists" / PNB_NEIGHBOUR_LISTS: 0 disables them, 1 forces them).  Without lists the reductions fall back to the tree-walking gather (gather.cu).
+bool neighbour_lists_fit(const Tree &t, int k, bool with_d2)
+{
+    if (g_opt_neighbour_lists == 0) return false;
+    if (g_opt_neighbour_lists == 1) return true;
+    int LOG = 0;
+    while ((1 << LOG) < k) ++LOG;
+    const size_t per = 4 + (with_d2 ? tsize(t.dtype) : 0);
+    const size_t need = (size_t)t.nsplit * ((size_t)1 << LOG) * 32 * per;
+    size_t have = t.nn_ids.cap + t.nn_d2.cap;          // what this tree already holds for the purpose
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    return need <= have + (free_b + cached_bytes()) / 2;
+}
+
+void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp, bool keep_ids, bool keep_d2)
 {
     if (k > t.n)
         throw Error(PNB_ERR_VALUE, "Number of smoothing particles exceeds number of particles in tree");
     if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
-    // the density can ride along only when every particle has the same mass (no neighbour ids are kept)
+    // the density can ride along only when every particle has the same mass
     if (fuse_rho && !(t.has_mass && t.mass_is_uniform)) fuse_rho = false;
-    if (nn_idx_dev) fuse_rho = false;
-    if (t.dtype == PNB_F64) run_knn_typed<double>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
-    else run_knn_typed<float>(t, k, period, fuse_rho, kp, nn_idx_dev, nn_d2_dev);
+    if (t.dtype == PNB_F64) run_knn_typed<double>(t, k, period, fuse_rho, kp, keep_ids, keep_d2);
+    else run_knn_typed<float>(t, k, period, fuse_rho, kp, keep_ids, keep_d2);
     t.smooth_valid = true;                  // (for the particles selected by the query mask, if one is set)
     t.smooth_k = k;
     t.smooth_period = period > 0 ? period : 0;

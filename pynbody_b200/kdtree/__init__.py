@@ -140,6 +140,15 @@ class KDTree:
         finally:
             smx.nn_result = None
 
+    def gather_neighbour_counts(self):
+        """How many particles the reference's fixed-radius gather (d2 <= 4 h^2) finds around each particle for
+        the registered smooth array: int32[N] (GPU-side addition; the reference keeps nCnt internal)."""
+        smx = kdmain.nn_start(self.kdtree, 1, self._period())
+        try:
+            return kdmain.gather_counts(self.kdtree, smx)
+        finally:
+            kdmain.nn_stop(self.kdtree, smx)
+
     @staticmethod
     def array_name_to_id(name):
         try:

@@ -49,7 +49,9 @@ class _SmoothingContext:
 
     def __init__(self, k, period):
         self.k, self.period = int(k), float(period)
-        self.nn_result = None
+        self.nn_result = None       # the chunk of neighbour-list rows currently on the host
+        self.nn_first = 0           # file index of its first row
+        self.nn_started = False     # the device search of this nn() iteration has run
         self.nn_cursor = 0
 
 
@@ -163,23 +165,37 @@ def nn_start(kd, nn, period):
 
 def nn_stop(kd, smx):
     smx.nn_result = None
+    smx.nn_started = False
 
 
 def nn_rewind(smx):
     smx.nn_cursor = 0
 
 
-def _run_knn(kd, smx):
+NN_CHUNK_ROWS = 1 << 16       # rows of the neighbour lists fetched per device round trip by nn_next
+
+
+def _start_knn(kd, smx):
+    """One device search for all particles; the lists stay on the device (pnb_knn_start).  The registered
+    smooth array is overwritten with h, as the reference's nn iteration does (smooth.h:429)."""
     L = _lib.lib()
-    np_dtype = np.float64 if kd.dtype_code == _lib.F64 else np.float32
-    idx = np.empty((kd.n, smx.k), np.int64)
-    d2 = np.empty((kd.n, smx.k), np_dtype)
-    h = np.empty(kd.n, np_dtype)
-    _lib.check(L.pnb_knn(kd.require_built(), smx.k, smx.period, idx.ctypes.data, d2.ctypes.data, h.ctypes.data, None))
-    smx.nn_result = (idx, d2, h)
     sm = kd.arrays[0]
-    if sm is not None and isinstance(sm, np.ndarray):
-        sm[...] = h                                  # nn() overwrites the smooth array (smooth.h:429)
+    if sm is not None:
+        p, s0, s1, ncols, code, mem, _ = _lib.describe(sm)
+        _lib.check(L.pnb_set_array(kd.require_built(), 0, p, s0, s1, ncols, code, mem))
+    _lib.check(L.pnb_knn_start(kd.require_built(), smx.k, smx.period, None))
+    smx.nn_started = True
+    smx.nn_result = None
+    smx.nn_first = 0
+
+
+def _fetch_rows(kd, smx, first, count):
+    np_dtype = np.float64 if kd.dtype_code == _lib.F64 else np.float32
+    idx = np.empty((count, smx.k), np.int64)
+    d2 = np.empty((count, smx.k), np_dtype)
+    h = np.empty(count, np_dtype)
+    _lib.check(_lib.lib().pnb_knn_rows(kd.require_built(), first, count, idx.ctypes.data, d2.ctypes.data, h.ctypes.data))
+    return idx, d2, h
 
 
 def nn_next(kd, smx):
@@ -187,22 +203,41 @@ def nn_next(kd, smx):
 
     Particles are yielded in file order; the reference's order (its thread-0 'snake' walk) is an
     artefact no caller relies on.  Lists are unsorted and include the particle itself at d2 = 0.
+    Rows come from the device NN_CHUNK_ROWS at a time, so iterating over 10^7 particles never holds
+    more than one chunk on the host.
     """
-    if smx.nn_result is None:
-        _run_knn(kd, smx)
+    if not getattr(smx, "nn_started", False):
+        _start_knn(kd, smx)
     i = smx.nn_cursor
     if i >= kd.n:
         return None
+    if smx.nn_result is None or not (smx.nn_first <= i < smx.nn_first + len(smx.nn_result[2])):
+        smx.nn_first = i
+        smx.nn_result = _fetch_rows(kd, smx, i, min(NN_CHUNK_ROWS, kd.n - i))
     idx, d2, h = smx.nn_result
+    r = i - smx.nn_first
     smx.nn_cursor = i + 1
-    return [i, float(h[i]), idx[i].tolist(), d2[i].tolist()]
+    return [i, float(h[r]), idx[r].tolist(), d2[r].tolist()]
 
 
 def all_neighbours(kd, smx):
-    """Array form of the full nn() output: (idx[N,k] int64, d2[N,k], h[N])."""
-    if smx.nn_result is None:
-        _run_knn(kd, smx)
-    return smx.nn_result
+    """Array form of the full nn() output: (idx[N,k] int64, d2[N,k], h[N]) -- N*k*(8+sizeof T) bytes on the host."""
+    _start_knn(kd, smx)
+    return _fetch_rows(kd, smx, 0, kd.n)
+
+
+def gather_counts(kd, smx):
+    """Number of particles the reference's gather finds around every particle for the registered smooth array
+    (nCnt = smBallGather(4 h^2), kdmain.cpp:779), int32[N] in file order (pnb_gather_counts)."""
+    L = _lib.lib()
+    sm = kd.arrays[0]
+    if sm is None:
+        raise ValueError("smooth array has not been set")
+    p, s0, s1, ncols, code, mem, _ = _lib.describe(sm)
+    _lib.check(L.pnb_set_array(kd.require_built(), 0, p, s0, s1, ncols, code, mem))
+    out = np.empty(kd.n, np.int32)
+    _lib.check(L.pnb_gather_counts(kd.require_built(), smx.period, out.ctypes.data, _lib.HOST))
+    return out
 
 
 def particles_in_sphere(kd, smx, x, y, z, r):
@@ -270,6 +305,11 @@ def populate(kd, smx, propid, procid, kernel_id=0):
             s1, ncols = 0, 1
         _lib.check(L.pnb_set_array(h, slot, p, s0, s1, ncols, code, mem))
     _lib.check(L.pnb_populate(h, propid, smx.k, int(kernel_id), smx.period, None))
+
+
+def set_option(name, value):
+    """Process-wide switches of the library (pnb_set_option): "neighbour_lists" (-1 auto / 0 / 1), "gather_walk" (0 / 1)."""
+    _lib.check(_lib.lib().pnb_set_option(name.encode(), int(value)))
 
 
 def last_device_ms(stage):
