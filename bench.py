@@ -15,8 +15,10 @@ WendlandC2 kernel, 64 neighbours, float64, one B200 per rank.
 ``e2e``     the same step from HOST arrays in pinned memory through the same public API: host->device
             copies of pos/mass (and smooth/mass again for populate('rho'), as the reference ABI
             re-reads its borrowed arrays) and device->host copies of smooth/rho are inside the timed region.
-``--impl reference``  the reference's own compiled C++ path (oracle/_ref, built from /root/reference by
-            oracle/Makefile) on all host cores, on a bounded sample of the same workload.
+``--impl reference``  the reference's own compiled C++ / Cython path (oracle/_ref, built from /root/reference by
+            oracle/Makefile) on all host cores, on the SAME 256^3 particle set: about 10 s per pass, so the number of
+            timed passes is bounded by wall time (CPU_BUDGET_S) instead of shrinking the workload; plus one exact
+            2048^2 render_image of the same particles (the Mpix/s half of the metric).
 """
 from __future__ import annotations
 
@@ -49,12 +51,27 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(dtype, n_side, what=None):
-    """DRAM bytes of one k_knn launch for this workload from the committed ncu capture (profiles/), or None;
-    ``what`` selects another figure of the same capture (issue_active_pct, warp_inst_per_particle)."""
+def source_hash():
+    """Hash of the sources the dominant kernels are compiled from; ncu-derived constants are only quoted for
+    the sources they were captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("knn.cu", "traverse.cuh", "tree_morton.cu", "render.cu"):
+        with open(os.path.join(ROOT, "pynbody_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_ncu(key):
+    """A per-launch figure from the committed ncu capture (profiles/r2_ncu_constants.json: DRAM bytes, issue-slot
+    utilisation, warp instructions per particle), or None when the capture was taken on other sources --
+    stale constants are not printed."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(f"{dtype}:{n_side}" + (f":{what}" if what else ""))
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as f:
+            d = json.load(f)
+        if d.get("source_hash") != source_hash():
+            return None
+        return d.get(key)
     except Exception:
         return None
 
@@ -110,41 +127,82 @@ def make_particles(n_side, seed, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
+CPU_BUDGET_S = 100.0      # the CPU arm repeats the FULL workload until this much wall time is spent (>= 1 pass)
+
+
 def reference_step(pos, mass, threads):
     """The reference's own path for sim['rho'] (sph/__init__.py:40-94), via its compiled modules."""
     from oracle import ref
     kd = ref.RefKDTree(pos, mass, 16, 1.0, threads, 1)
-    kd.smooth(K_NEIGHBOURS)
-    kd.rho(K_NEIGHBOURS)
-    return kd
+    sm = kd.smooth(K_NEIGHBOURS)
+    rho = kd.rho(K_NEIGHBOURS)
+    return sm, rho
 
 
 def oracle_step(pos, mass, threads):
     from oracle import oracle
     kd = oracle.OracleKDTree(pos, mass, 16, 1.0, threads, 1)
-    kd.smooth(K_NEIGHBOURS)
-    kd.rho(K_NEIGHBOURS)
-    return kd
+    sm = kd.smooth(K_NEIGHBOURS)
+    rho = kd.rho(K_NEIGHBOURS)
+    return sm, rho
 
 
-def cpu_arm(sample_side, dtype, steps, warmup):
+def render_args(res, pos, sm, rho, mass, kern):
+    """render_image arguments of BASELINE.json configs[2]: projected density of the whole periodic box, with the
+    3 x 3 wrap offsets ImageRenderer generates for width = boxsize (renderers.py:616-629)."""
+    wrap = [-1.0, 0.0, 1.0]
+    return (res, res, pos[:, 0], pos[:, 1], pos[:, 2], sm, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5, rho, mass, rho,
+            0.0, float("inf"), float("-inf"), float("inf"), 0.0, kern, wrap, wrap)
+
+
+def cpu_render(pos, sm, rho, mass, res, threads):
+    """The reference's _render.render_image (exact, threaded as ThreadedImageRenderer splits it,
+    renderers.py:558-573) on all host cores."""
+    from oracle import ref, oracle
+    from pynbody_b200.sph import kernels
+    kern = kernels.create_kernel(KERNEL).projection()
+    a = render_args(res, pos, sm, rho, mass, kern)
+    t0 = time.perf_counter()
+    if ref.available():
+        ref.render_image(*a, num_threads=threads)
+        kind = "reference"
+    else:
+        oracle.render_image(*a)
+        kind, threads = "port", 1
+    dt = time.perf_counter() - t0
+    return {"value": res * res / dt / 1e6, "unit": "Mpix/s", "cores": threads, "kind": kind, "seconds": dt,
+            "sample": f"the full workload once: {res}x{res} projected density of all {len(pos)} particles, 3x3 periodic images, "
+                      f"exact (approximate_fast=False), particle-strided over {threads} threads"}
+
+
+def cpu_arm(n_side, dtype, steps, budget_s, render_res=0):
+    """The reference's CPU implementation on all host cores, on the FULL workload (the same particle set the
+    GPU arm runs).  One pass is ~10 s on 16 cores, so the number of timed passes is bounded by wall time, not
+    by shrinking the particle set."""
     from oracle import ref
     threads = os.cpu_count() or 1
-    pos, vel, mass = make_particles(sample_side, 2, dtype)
+    pos, vel, mass = make_particles(n_side, 2, dtype)
     if ref.available():
         kind, fn = "reference", reference_step
     else:
         kind, fn = "port", oracle_step
-    for _ in range(warmup):
-        fn(pos, mass, threads)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fn(pos, mass, threads)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": len(pos) / dt, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"{sample_side}^3 = {len(pos)} particles of the same Zel'dovich box recipe, {np.dtype(dtype).name}, "
-                      f"k={K_NEIGHBOURS}, WendlandC2: tree build + smooth + rho, {steps} timed run(s)",
-            "seconds_per_step": dt}
+    times = []
+    t_start = time.perf_counter()
+    sm = rho = None
+    while len(times) < max(steps, 1):
+        t0 = time.perf_counter()
+        sm, rho = fn(pos, mass, threads)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    dt = float(np.mean(times))
+    out = {"value": len(pos) / dt, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": f"the full workload: {n_side}^3 = {len(pos)} particles, {np.dtype(dtype).name}, k={K_NEIGHBOURS}, "
+                     f"WendlandC2: tree build + smooth + rho, {len(times)} timed pass(es) of {dt:.1f} s",
+           "seconds_per_step": dt, "passes": len(times)}
+    if render_res:
+        out["render"] = cpu_render(pos, sm, rho, mass, render_res, threads)
+    return out
 
 
 def run_reference(args):
@@ -152,25 +210,28 @@ def run_reference(args):
     if rank != 0:
         return
     dtype = np.float64 if args.dtype == "f64" else np.float32
-    res = cpu_arm(args.cpu_sample_side, dtype, args.steps, args.warmup)
+    res = cpu_arm(args.n_side, dtype, args.steps, CPU_BUDGET_S, 0 if args.no_render else args.render_res)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, reference=True),
+            "config": workload_config(args),
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "steps_timed": res["passes"], "gpu_launches": 0}
+    if "render" in res:
+        r = res["render"]
+        line["render"] = {"image": {"resolution": args.render_res, "ms": r["seconds"] * 1e3, "mpix_per_s": r["value"],
+                                    "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}}}
     print(json.dumps(line))
 
 
-def workload_config(args, reference=False):
+def workload_config(args):
     n = args.n_side ** 3
     return {"workload": f"C2: {n}-particle ({args.n_side}^3) clustered Zel'dovich-like periodic box per GPU, "
                         f"sim['rho'] = kd-tree build + smooth + rho, k={K_NEIGHBOURS}, WendlandC2, {args.dtype}",
             "particles_per_gpu": n, "k": K_NEIGHBOURS, "kernel": "WendlandC2", "boxsize": 1.0,
             "parallelism": "one independent box per GPU (no data-path collective)" if args.gpus > 1 else "single GPU",
-            "l2_policy": "inputs (pos+mass, 32 B/particle f64) exceed the 126 MB L2; no explicit flush",
-            **({"reference_sample_side": args.cpu_sample_side} if reference else {})}
+            "l2_policy": "inputs (pos+mass, 32 B/particle f64) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -279,11 +340,22 @@ def run_ours(args):
             del out
         extra[name + "_ms"] = round(kdmain.last_device_ms(1), 3)
         extra[name + "_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+    # sim['rho'] when the masses are NOT all equal (any real gas snapshot): the density cannot ride in the kNN
+    # epilogue; it is summed over the resident neighbour lists instead (gather_list.cu)
+    d_mass2 = d_mass * (1.0 + 0.25 * torch.sin(torch.arange(n, device="cuda", dtype=d_mass.dtype)))
+    for _ in range(2):
+        step(d_pos, d_mass2, d_sm, d_rho, False)
+    uneq_ms = timed(lambda: step(d_pos, d_mass2, d_sm, d_rho, False), 3) / 3
+    extra["unequal_masses_step_ms"] = round(uneq_ms, 3)
+    extra["unequal_masses_rho_ms"] = round(kdmain.last_device_ms(1), 3)
+    extra["unequal_masses_rho_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+    # and with a foreign smooth array (not this tree's own): the tree-walking fixed-radius gather of the reference
     sm2 = d_sm.clone(); sm2[0] = sm2[0] * (1 + 1e-7)
     kd.set_array_ref("smooth", sm2); kd.set_array_ref("rho", d_rho)
     kd.populate("rho", K_NEIGHBOURS)
-    extra["rho_gather_ms"] = round(kdmain.last_device_ms(1), 3)
-    extra["rho_gather_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+    extra["rho_tree_walk_ms"] = round(kdmain.last_device_ms(1), 3)
+    extra["rho_tree_walk_kernel_ms"] = round(kdmain.last_kernel_ms(1), 3)
+    del d_mass2, sm2
 
     # C3: projected density image and 3-D grid of the same particles (BASELINE.json configs[2]),
     # device-resident inputs, periodic wrap offsets as ImageRenderer generates them (renderers.py:616-629)
@@ -295,13 +367,30 @@ def run_ours(args):
         wrap = [-1.0, 0.0, 1.0]
         res = args.render_res
         def once():
-            return _render.render_image(res, res, d_pos[:, 0], d_pos[:, 1], d_pos[:, 2], d_sm, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5,
-                                        d_rho, d_mass, d_rho, 0.0, float("inf"), float("-inf"), float("inf"), 0.0, k2, wrap, wrap)
+            return _render.render_image(*render_args(res, d_pos, d_sm, d_rho, d_mass, k2))
         once()
-        ms = timed(once, 2) / 2
+        ms = timed(once, 3) / 3
         call_ms, kern_ms = _render.last_render_ms()
+        # end to end: the seven particle arrays in pinned HOST memory (x, y, z = column views of pos), image back to the host
+        hp, hs, hr, hm = h_pos.numpy(), h_sm.numpy(), h_rho.numpy(), h_mass.numpy()
+        hs[...] = d_sm.cpu().numpy(); hr[...] = d_rho.cpu().numpy()
+        def once_host():
+            return _render.render_image(*render_args(res, hp, hs, hr, hm, k2))
+        once_host()
+        e2e_img_ms = timed(once_host, 3) / 3
+        # compulsory bytes N x 7 x s_in + 4 nx ny out + ~16 B/particle binning traffic
+        img_bytes = n * 7 * tsz + 4 * res * res + n * 16
+        peak_r, peak_src_r = load_peaks()
         render["image"] = {"resolution": res, "mode": "projected density, 3x3 periodic images, exact (approximate_fast=False)",
-                           "ms": ms, "mpix_per_s": world * res * res / (ms * 1e-3) / 1e6, "tile_kernel_ms": kern_ms}
+                           "ms": ms, "mpix_per_s": world * res * res / (ms * 1e-3) / 1e6, "tile_kernel_ms": kern_ms,
+                           "e2e": {"value": world * res * res / (e2e_img_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms": e2e_img_ms,
+                                   "h2d_bytes_per_step": n * 7 * tsz, "d2h_bytes_per_step": 4 * res * res},
+                           "roofline": {"bound": "hbm", "kernel": "k_render_tiles", "achieved": img_bytes / (kern_ms * 1e-3) / 1e9,
+                                        "peak": peak_r, "unit": "GB/s", "frac": img_bytes / (kern_ms * 1e-3) / 1e9 / peak_r,
+                                        "traffic": load_ncu(f"k_render_tiles:{args.dtype}:{args.n_side}:dram_bytes"),
+                                        "algorithmic_bytes_per_launch": img_bytes, "peak_source": peak_src_r, "kernel_ms": kern_ms,
+                                        "pixel_updates_per_launch": load_ncu(f"k_render_tiles:{args.dtype}:{args.n_side}:pixel_updates"),
+                                        "note": "work-bound (pixel updates), not byte-bound: SURVEY.md 8(d)"}}
         gres = args.grid_res
         def gonce():
             return _render.to_3d_grid(gres, gres, gres, d_pos[:, 0], d_pos[:, 1], d_pos[:, 2], d_sm, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0,
@@ -350,23 +439,29 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_knn (kNN smoothing lengths + fused density)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(args.dtype, args.n_side), "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": load_ncu(f"k_knn:{args.dtype}:{args.n_side}:dram_bytes"), "algorithmic_bytes_per_launch": alg_bytes,
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": 6 * tsz,
                      "kernel_ms": knn_kernel_ms,
                      "logical_gather_gbs": gather_bytes / (knn_kernel_ms * 1e-3) / 1e9,
                      "neighbour_interactions_per_s": n * K_NEIGHBOURS / (knn_kernel_ms * 1e-3),
-                     "ncu_issue_active_pct": load_traffic(args.dtype, args.n_side, "issue_active_pct"),
-                     "ncu_warp_inst_per_particle": load_traffic(args.dtype, args.n_side, "warp_inst_per_particle"),
+                     "ncu_issue_active_pct": load_ncu(f"k_knn:{args.dtype}:{args.n_side}:issue_active_pct"),
+                     "ncu_warp_inst_per_particle": load_ncu(f"k_knn:{args.dtype}:{args.n_side}:warp_inst_per_particle"),
+                     "ncu_source_hash": source_hash(),
                      "note": "irregular tree search: bound by instruction issue (on-chip neighbour-queue updates), not by "
-                             "HBM bytes (SURVEY.md 8d); traffic and issue-slot utilisation from the committed ncu capture "
-                             "profiles/r1_knn_final_summary.txt"},
+                             "HBM bytes (SURVEY.md 8d); traffic / issue-slot figures come from the committed ncu capture "
+                             "(profiles/r2_ncu_constants.json) and are null unless it was taken on these very sources"},
         "stages_ms": {"build": float(np.mean(stats["build_ms"])), "smooth_incl_fused_rho": float(np.mean(stats["knn_ms"])),
                       "knn_kernel": knn_kernel_ms, "rho_readback": float(np.mean(stats["rho_ms"])), **extra},
+        "unequal_masses": {"ms_per_step": extra["unequal_masses_step_ms"], "value": world * n / (extra["unequal_masses_step_ms"] * 1e-3),
+                           "unit": UNIT, "note": "same step with particle masses that differ: density from the resident "
+                                                 "neighbour lists instead of the kNN epilogue"},
         "render": render,
     }
     if world == 1 and not args.no_cpu_baseline:
-        res = cpu_arm(args.cpu_sample_side, dtype, 1, 0)
+        res = cpu_arm(args.n_side, dtype, 1, 0.0, 0 if args.no_render else args.render_res)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if "render" in res and "image" in render:
+            render["image"]["cpu_baseline"] = {k: res["render"][k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -511,7 +606,6 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n-side", type=int, default=256, help="particles per GPU = n_side^3 (256 -> 16.7M)")
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
-    ap.add_argument("--cpu-sample-side", type=int, default=128, help="CPU baseline sample = side^3 particles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="per-step stage times on stderr")
     ap.add_argument("--no-render", action="store_true", help="skip the C3 image / grid timings")

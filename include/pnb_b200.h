@@ -77,6 +77,8 @@ int pnb_device_count(void);
  *                      they fit in half of the free device memory, so that rho / mean / dispersion / div / curl
  *                      stream over them instead of searching again; 0 never; 1 always.  (env PNB_NEIGHBOUR_LISTS)
  *   "gather_walk"      1: the reductions always use the tree-walking fixed-radius gather.  (env PNB_GATHER_WALK)
+ *   "tree_build"       0 (default): device tree from one Morton sort + shared-memory kd levels; 1: the level-by-level
+ *                      median-split build over three per-axis sorts.  Results do not depend on it.  (env PNB_TREE_BUILD)
  * PNB_ERR_VALUE for an unknown name. */
 int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */
@@ -112,6 +114,9 @@ int pnb_tree_export(pnb_tree *t, void *kdnodes_out, int64_t n_nodes, int64_t *of
  * (int64[n_buckets + 1]) and tight bounds (double[n_buckets][6] = min xyz, max xyz), host memory */
 int64_t pnb_tree_num_buckets(const pnb_tree *t);
 int pnb_tree_buckets(pnb_tree *t, int64_t *start, double *bounds);
+/* tight bounds of EVERY node of the device tree in heap order (root = 1, children 2i / 2i+1, buckets at
+ * n_buckets .. 2 n_buckets - 1; node 0 unused): double[2 * n_buckets][6] = min xyz, max xyz, host memory */
+int pnb_tree_node_bounds(pnb_tree *t, double *bounds);
 
 /* ---- kdmain.set_arrayref (kdmain.cpp:511-579) ------------------------------------------------
  * Registers a borrowed array for slot `id`.  ncols is 1 (N) or 3 (N x 3, qty / qty_sm only).

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pnb_tree_export": (_i32, [_vp, _vp, _i64, _vp]),
     "pnb_tree_num_buckets": (_i64, [_vp]),
     "pnb_tree_buckets": (_i32, [_vp, _vp, _vp]),
+    "pnb_tree_node_bounds": (_i32, [_vp, _vp]),
     "pnb_set_array": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _i32]),
     "pnb_set_query_mask": (_i32, [_vp, _vp, _i32]),
     "pnb_mark_in_balls": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _vp, _i32]),

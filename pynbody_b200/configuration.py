@@ -23,13 +23,30 @@ _defaults = {
 }
 
 
-def _load():
-    try:
-        import pynbody  # noqa: F401
-        from pynbody import config as ref_config
-        return ref_config
-    except Exception:
-        return _defaults
+class _LiveConfig:
+    """Mapping that resolves every lookup at call time: pynbody's own ``config`` once pynbody has been imported
+    (by the user, or by ``install()``), the defaults above otherwise.  Resolving lazily matters: this module is
+    usually imported before pynbody is."""
+
+    @staticmethod
+    def _target():
+        import sys
+        ref = sys.modules.get("pynbody")
+        cfg = getattr(ref, "config", None) if ref is not None else None
+        return cfg if cfg is not None else _defaults
+
+    def __getitem__(self, key):
+        return self._target()[key]
+
+    def __setitem__(self, key, value):
+        self._target()[key] = value
+
+    def __contains__(self, key):
+        return key in self._target()
+
+    def get(self, key, default=None):
+        t = self._target()
+        return t.get(key, default) if hasattr(t, "get") else (t[key] if key in t else default)
 
 
-config = _load()
+config = _LiveConfig()

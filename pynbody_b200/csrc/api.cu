@@ -297,12 +297,14 @@ static void update_mass_uniformity(Tree &t)
 }
 
 int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 auto (keep them if they fit), 0 never, 1 always
+int g_opt_tree_build = 0;           // pnb_set_option("tree_build"): 0 = Morton sort + in-shared-memory kd levels, 1 = level-by-level kd build
 int g_opt_gather_walk = 0;          // pnb_set_option("gather_walk"): 1 = reductions always walk the tree
 static struct OptionsFromEnv {
     OptionsFromEnv()
     {
         if (const char *e = getenv("PNB_NEIGHBOUR_LISTS")) g_opt_neighbour_lists = atoi(e);
         if (const char *e = getenv("PNB_GATHER_WALK")) g_opt_gather_walk = atoi(e);
+        if (const char *e = getenv("PNB_TREE_BUILD")) g_opt_tree_build = atoi(e);
     }
 } g_options_from_env;
 
@@ -504,6 +506,7 @@ int pnb_set_option(const char *name, int value)
         if (!name) throw Error(PNB_ERR_VALUE, "option name is null");
         if (!strcmp(name, "neighbour_lists")) g_opt_neighbour_lists = value;
         else if (!strcmp(name, "gather_walk")) g_opt_gather_walk = value;
+        else if (!strcmp(name, "tree_build")) g_opt_tree_build = value;
         else throw Error(PNB_ERR_VALUE, std::string("unknown option ") + name);
     });
 }
@@ -543,7 +546,8 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
                 fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
             }
         }
-        build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
+        if (g_opt_tree_build == 1) build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
+        else build_tree_morton(*t, cols, mass ? mass_dev.p : nullptr);
         update_mass_uniformity(*t);
         timer.stop();
     });
@@ -605,6 +609,22 @@ int pnb_tree_buckets(pnb_tree *h, int64_t *start, double *bounds)
         } else {
             std::vector<float> b(nb);
             PNB_CUDA(cudaMemcpy(b.data(), t->box.as<float>() + nb, sizeof(float) * nb, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nb; ++i) bounds[i] = (double)b[i];
+        }
+    });
+}
+
+int pnb_tree_node_bounds(pnb_tree *h, double *bounds)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        const size_t nb = (size_t)t->nsplit * 2 * 6;
+        if (t->dtype == PNB_F64) {
+            PNB_CUDA(cudaMemcpy(bounds, t->box.p, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> b(nb);
+            PNB_CUDA(cudaMemcpy(b.data(), t->box.p, sizeof(float) * nb, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < nb; ++i) bounds[i] = (double)b[i];
         }
     });

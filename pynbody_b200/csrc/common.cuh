@@ -187,6 +187,8 @@ void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int nco
 // ---- stages --------------------------------------------------------------------------------------
 // cols: file-order coordinates as dense columns T[3][n]; mass_dev: T[n] in file order or null
 void build_tree(Tree &t, DevBuf &cols, const void *mass_dev, const TreeShape &shape, bool want_soa);
+// the device tree (32-particle buckets): one Morton sort + the lower levels as a kd-tree in shared memory (tree_morton.cu)
+void build_tree_morton(Tree &t, DevBuf &cols, const void *mass_dev);
 
 struct KernelParams {
     int kernel_id;
@@ -200,7 +202,7 @@ KernelParams make_kernel_params(int kernel_id, int k);
 void run_knn(Tree &t, int k, double period /* <=0: open */, bool fuse_rho, const KernelParams &kp,
              bool keep_ids, bool keep_d2);
 bool neighbour_lists_fit(const Tree &t, int k, bool with_d2);
-extern int g_opt_neighbour_lists, g_opt_gather_walk;     // pnb_set_option (api.cu)
+extern int g_opt_neighbour_lists, g_opt_gather_walk, g_opt_tree_build;     // pnb_set_option (api.cu)
 // reductions over the resident neighbour lists (gather_list.cu); same arguments as run_gather
 void run_gather_lists(Tree &t, int propid, int k, double period, const KernelParams &kp,
                       const void *smooth_tree, const void *rho_tree, const void *qty_tree, int qdtype,

@@ -1,0 +1,355 @@
+// tree_morton.cu -- K1: the device tree, built Morton-first.
+//
+// Replaces kdBuildTree / kdBuildNode / kdSelect / kdUpPass (pynbody/kdtree/kd.cpp:31-238) for the tree the
+// kernels traverse.  (The reference-SHAPED tree that KDTree.serialize() exposes is a different object with the
+// reference's split rule; it is built on demand by tree_build.cu / export.cu.)
+//
+// The tree is the same implicit complete binary tree as before -- heap order, root = 1, every bucket at depth
+// `levels`, bucket j = tree ranks [32j, 32j+32) -- but it is built in two regimes:
+//
+//   coarse  one 63-bit Morton key per particle (21 bits per axis over the cube around the particle set), ONE
+//           radix sort of (key, id) pairs.  Consecutive runs of SEG = 4096 (float32) / 2048 (float64) particles
+//           of the sorted order are the sub-trees at depth `levels - LSEG`; the levels above them split the
+//           Morton order by rank.  This replaces 12 of the 19 breadth-first levels of the old build (each a
+//           pass over all particles plus a global prefix sum) by a single sort.
+//   fine    one CTA per segment loads its particles into shared memory and builds the lower LSEG = 7 / 6
+//           levels as a genuine kd-tree there: per level the tight bounds of every node, split along the
+//           longest axis, exact median by rank via a bitonic sort of (coordinate, slot) pairs inside each node.
+//           Bucket quality -- which is what the neighbour search pays for -- is that of a median-split
+//           kd-tree; only the segment outlines follow the Morton curve.  The CTA then writes its particles in
+//           tree order as structure-of-arrays (x[], y[], z[], mass[], order[]): a bucket is 32 consecutive
+//           elements = one 128/256-byte line per coordinate.
+//
+// Node bounds are tight everywhere: computed from the particles inside the segments, as unions of children
+// above them.  Trailing empty nodes carry inverted (+inf, -inf) bounds so that no search opens them.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace pnb {
+
+namespace {
+
+template <typename T> struct Ord;
+template <> struct Ord<float> {
+    typedef uint32_t U;
+    static __device__ __forceinline__ U enc(float v) { U u = __float_as_uint(v); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+    static __device__ __forceinline__ float dec(U u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Ord<double> {
+    typedef unsigned long long U;
+    static __device__ __forceinline__ U enc(double v)
+    {
+        U u = (U)__double_as_longlong(v);
+        return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double dec(U u)
+    {
+        return __longlong_as_double((long long)((u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u));
+    }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+};
+
+// ---- global bounds: [0..2] = min xyz, [3..5] = max xyz, order-preserving unsigned encoding -------------------
+template <typename T>
+__global__ void k_bounds_init(typename Ord<T>::U *b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = ~(typename Ord<T>::U)0;
+    else if (threadIdx.x < 6) b[threadIdx.x] = 0;
+}
+template <typename T>
+__global__ void k_bounds(const T *__restrict__ c, int64_t n, typename Ord<T>::U *__restrict__ b)
+{
+    typedef typename Ord<T>::U U;
+    T mn[3], mx[3];
+    for (int d = 0; d < 3; ++d) { mn[d] = Ord<T>::inf(); mx[d] = -Ord<T>::inf(); }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        for (int d = 0; d < 3; ++d) {
+            const T v = c[d * n + i];
+            mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v);
+        }
+    for (int d = 0; d < 3; ++d)
+        for (int o = 16; o; o >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&b[d], (U)Ord<T>::enc(mn[d]));
+            atomicMax(&b[3 + d], (U)Ord<T>::enc(mx[d]));
+        }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v)       // bit i -> bit 3i
+{
+    uint64_t x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+template <typename T>
+__global__ void k_morton_keys(const T *__restrict__ c, int64_t n, const typename Ord<T>::U *__restrict__ b,
+                              uint64_t *__restrict__ keys, uint32_t *__restrict__ ids)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mn[3], ext = 0;
+    for (int d = 0; d < 3; ++d) {
+        mn[d] = (double)Ord<T>::dec(b[d]);
+        ext = fmax(ext, (double)Ord<T>::dec(b[3 + d]) - mn[d]);
+    }
+    const double scale = ext > 0 ? 2097152.0 / ext : 0.0;       // 2^21 cells across the longest extent
+    uint64_t key = 0;
+    for (int d = 0; d < 3; ++d) {
+        double q = ((double)c[d * n + i] - mn[d]) * scale;
+        uint32_t u = q >= 2097151.0 ? 2097151u : (q > 0 ? (uint32_t)q : 0u);
+        key |= spread21(u) << d;
+    }
+    keys[i] = key;
+    ids[i] = (uint32_t)i;
+}
+
+// ---- fine levels: one CTA per segment -------------------------------------------------------------------------
+template <typename T> struct SegCfg;
+template <> struct SegCfg<float> { static constexpr int LSEG = 7; };     // 4096 particles, 1024 threads
+template <> struct SegCfg<double> { static constexpr int LSEG = 6; };    // 2048 particles,  512 threads
+
+template <typename T>
+struct SegArgs {
+    int64_t n, nsplit;
+    int levels, lseg;                 // lseg = min(levels, LSEG): levels built inside a segment
+    const T *cols;                    // [3][n] file order
+    const T *mass;                    // [n] file order or null
+    const uint32_t *ids;              // [n] Morton order -> file index
+    T *x, *y, *z, *m;                 // tree order
+    uint32_t *order;                  // tree position -> file index
+    T *box;                           // [2*nsplit][6]
+};
+
+template <typename T>
+__global__ void __launch_bounds__((32 << SegCfg<T>::LSEG) / 4) k_build_segment(SegArgs<T> a)
+{
+    typedef typename Ord<T>::U U;
+    constexpr int SEG = 32 << SegCfg<T>::LSEG;
+    constexpr int NT = SEG / 4;
+    constexpr int MAXSUB = SEG / 64;                 // nodes of the deepest split level
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    T *px = reinterpret_cast<T *>(seg_smem);
+    T *py = px + SEG, *pz = py + SEG, *sk = pz + SEG;
+    U *sbox = reinterpret_cast<U *>(sk + SEG);       // [MAXSUB][6]
+    uint16_t *perm = reinterpret_cast<uint16_t *>(sbox + MAXSUB * 6);
+    uint8_t *axis = reinterpret_cast<uint8_t *>(perm + SEG);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int segn = 32 << a.lseg;                   // slots of this segment (<= SEG)
+    const int64_t base = (int64_t)blockIdx.x * segn;
+    const int cnt = (int)max((int64_t)0, min((int64_t)segn, a.n - base));
+    const int ltop = a.levels - a.lseg;              // depth of the segment roots
+    const T inf = Ord<T>::inf();
+
+    for (int i = tid; i < segn; i += NT) {
+        if (i < cnt) {
+            const uint32_t id = a.ids[base + i];
+            px[i] = a.cols[id]; py[i] = a.cols[a.n + id]; pz[i] = a.cols[2 * a.n + id];
+        } else {
+            px[i] = py[i] = pz[i] = inf;             // padding sorts to the end and is skipped by the bounds
+        }
+        perm[i] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    for (int l = 0; l <= a.lseg; ++l) {
+        const int m = segn >> l;                     // slots per node of this level
+        const int nsub = 1 << l;
+        const bool leaf = l == a.lseg;
+        // 1. tight bounds of every node of the level (leaf level: straight to global memory)
+        if (!leaf) {
+            for (int i = tid; i < nsub * 6; i += NT) sbox[i] = (i % 6) < 3 ? ~(U)0 : (U)0;
+            __syncthreads();
+        }
+        for (int g = warp; g < segn / 32; g += NT / 32) {
+            const int li = perm[g * 32 + lane];
+            const bool valid = li < cnt;
+            T mn[3], mx[3];
+            mn[0] = valid ? px[li] : inf; mn[1] = valid ? py[li] : inf; mn[2] = valid ? pz[li] : inf;
+            mx[0] = valid ? px[li] : -inf; mx[1] = valid ? py[li] : -inf; mx[2] = valid ? pz[li] : -inf;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+                    mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+                }
+            if (leaf) {
+                if (lane < 6) {
+                    const int64_t node = a.nsplit + (int64_t)blockIdx.x * (segn / 32) + g;
+                    const T v = lane == 0 ? mn[0] : lane == 1 ? mn[1] : lane == 2 ? mn[2] : lane == 3 ? mx[0] : lane == 4 ? mx[1] : mx[2];
+                    a.box[node * 6 + lane] = v;
+                }
+            } else if (lane == 0) {
+                U *b = sbox + (g >> (a.lseg - l)) * 6;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    atomicMin(&b[d], (U)Ord<T>::enc(mn[d]));
+                    atomicMax(&b[3 + d], (U)Ord<T>::enc(mx[d]));
+                }
+            }
+        }
+        if (leaf) break;
+        __syncthreads();
+        // 2. node bounds out, split axis = longest extent of the tight box
+        for (int s = tid; s < nsub; s += NT) {
+            T mn[3], mx[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { mn[d] = Ord<T>::dec(sbox[s * 6 + d]); mx[d] = Ord<T>::dec(sbox[s * 6 + 3 + d]); }
+            const int64_t node = ((int64_t)1 << (ltop + l)) + (int64_t)blockIdx.x * nsub + s;
+            T *b = a.box + node * 6;
+            b[0] = mn[0]; b[1] = mn[1]; b[2] = mn[2]; b[3] = mx[0]; b[4] = mx[1]; b[5] = mx[2];
+            int d = 0;
+            if (mx[1] - mn[1] > mx[d] - mn[d]) d = 1;
+            if (mx[2] - mn[2] > mx[d] - mn[d]) d = 2;
+            axis[s] = (uint8_t)d;
+        }
+        __syncthreads();
+        // 3. sort every node's slots by the coordinate along its axis: the lower half is the lower child
+        for (int i = tid; i < segn; i += NT) {
+            const int d = axis[i >> (5 + a.lseg - l)], li = perm[i];
+            sk[i] = d == 0 ? px[li] : d == 1 ? py[li] : pz[li];
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= m; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < segn / 2; t += NT) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int p = i | j;
+                    const bool up = ((i & (m - 1)) & k2) == 0;
+                    const T ka = sk[i], kb = sk[p];
+                    if ((ka > kb) == up && ka != kb) {
+                        sk[i] = kb; sk[p] = ka;
+                        const uint16_t t16 = perm[i]; perm[i] = perm[p]; perm[p] = t16;
+                    }
+                }
+                // pairs with j <= 32 stay inside the 64-slot blocks a warp owns (t -> i maps aligned runs of 32
+                // pair indices onto aligned runs of 64 slots): a block barrier is needed only around wider strides
+                const int jn = j > 1 ? (j >> 1) : k2;
+                if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
+            }
+        __syncthreads();
+    }
+    __syncthreads();
+    // tree-ordered structure of arrays
+    for (int i = tid; i < cnt; i += NT) {
+        const int li = perm[i];
+        const uint32_t id = a.ids[base + li];
+        a.x[base + i] = px[li]; a.y[base + i] = py[li]; a.z[base + i] = pz[li];
+        a.order[base + i] = id;
+        if (a.mass) a.m[base + i] = a.mass[id];
+    }
+}
+
+// levels above the segments: union of the children's bounds, bottom-up, one block
+template <typename T>
+__global__ void k_upper_bounds(T *__restrict__ box, int ltop)
+{
+    for (int level = ltop - 1; level >= 0; --level) {
+        const int64_t nn = (int64_t)1 << level;
+        for (int64_t j = threadIdx.x; j < nn; j += blockDim.x) {
+            const int64_t node = nn + j;
+            const T *l = box + 2 * node * 6, *r = l + 6;
+            T *o = box + node * 6;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { o[d] = fmin(l[d], r[d]); o[3 + d] = fmax(l[3 + d], r[3 + d]); }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_bucket_starts(int64_t n, int64_t nsplit, int32_t *__restrict__ bs)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j <= nsplit) bs[j] = (int32_t)min(n, 32 * j);
+}
+
+template <typename T>
+size_t segment_smem()
+{
+    constexpr int SEG = 32 << SegCfg<T>::LSEG;
+    return (size_t)SEG * 4 * sizeof(T) + (size_t)(SEG / 64) * 6 * sizeof(typename Ord<T>::U) + (size_t)SEG * 2 + SEG / 64 + 16;
+}
+
+template <typename T>
+void build_morton_typed(Tree &t, DevBuf &c, const T *mass)
+{
+    typedef typename Ord<T>::U U;
+    const int64_t n = t.n;
+    cudaStream_t s = t.stream;
+    const int BS = 256;
+    const unsigned nb = (unsigned)((n + BS - 1) / BS);
+
+    DevBuf bounds(sizeof(U) * 6), ids_sorted(sizeof(uint32_t) * n);
+    PNB_LAUNCH((k_bounds_init<T>), 1, 32, 0, s, bounds.as<U>());
+    PNB_LAUNCH((k_bounds<T>), std::min<unsigned>(nb, 148 * 8), BS, 0, s, c.as<T>(), n, bounds.as<U>());
+    {
+        DevBuf keys_in(sizeof(uint64_t) * n), keys_out(sizeof(uint64_t) * n), ids_in(sizeof(uint32_t) * n);
+        PNB_LAUNCH((k_morton_keys<T>), nb, BS, 0, s, c.as<T>(), n, bounds.as<U>(), keys_in.as<uint64_t>(), ids_in.as<uint32_t>());
+        size_t tmp_bytes = 0;
+        PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint64_t, uint32_t, int64_t>(
+            nullptr, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(), ids_in.as<uint32_t>(),
+            ids_sorted.as<uint32_t>(), n, 0, 63, s)));
+        DevBuf tmp(tmp_bytes);
+        PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint64_t, uint32_t, int64_t>(
+            tmp.p, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(), ids_in.as<uint32_t>(),
+            ids_sorted.as<uint32_t>(), n, 0, 63, s)));
+        g_launches += 9;                               // CUB's histogram + onesweep passes (approximate count)
+        PNB_CUDA(cudaStreamSynchronize(s));            // keys/tmp go back to the block cache on scope exit
+    }
+
+    t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
+    t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
+    t.order.alloc(sizeof(uint32_t) * n);
+    t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
+    if (mass) t.mass.alloc(sizeof(T) * n);
+    t.has_mass = mass != nullptr;
+    PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2, s));      // node 0 is unused
+
+    SegArgs<T> a;
+    a.n = n; a.nsplit = t.nsplit; a.levels = t.levels;
+    a.lseg = std::min(t.levels, SegCfg<T>::LSEG);
+    a.cols = c.as<T>(); a.mass = mass; a.ids = ids_sorted.as<uint32_t>();
+    a.x = t.x.as<T>(); a.y = t.y.as<T>(); a.z = t.z.as<T>(); a.m = t.mass.as<T>();
+    a.order = t.order.as<uint32_t>(); a.box = t.box.as<T>();
+    const size_t smem = segment_smem<T>();
+    PNB_CUDA(cudaFuncSetAttribute(k_build_segment<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sort
+    const unsigned nseg = (unsigned)(t.nsplit >> a.lseg);
+    PNB_LAUNCH((k_build_segment<T>), nseg, (32 << SegCfg<T>::LSEG) / 4, smem, s, a);
+    const int ltop = t.levels - a.lseg;
+    if (ltop > 0) PNB_LAUNCH((k_upper_bounds<T>), 1, 1024, 0, s, t.box.as<T>(), ltop);
+    PNB_LAUNCH(k_bucket_starts, (unsigned)((t.nsplit + 1 + BS - 1) / BS), BS, 0, s, n, t.nsplit, t.bucket_start.as<int32_t>());
+
+    T rb[6];
+    PNB_CUDA(cudaMemcpyAsync(rb, t.box.as<T>() + 6, sizeof(rb), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    for (int d = 0; d < 3; ++d) { t.root_min[d] = (double)rb[d]; t.root_max[d] = (double)rb[3 + d]; }
+}
+
+}  // namespace
+
+// cols: file-order coordinates as dense columns T[3][n]; mass_dev: T[n] in file order or null
+void build_tree_morton(Tree &t, DevBuf &cols, const void *mass_dev)
+{
+    if (t.n < 1) throw Error(PNB_ERR_VALUE, "kd-tree needs at least one particle");
+    if (t.n >= ((int64_t)1 << 31)) throw Error(PNB_ERR_VALUE, "at most 2^31-1 particles per device tree");
+    t.shape = packed_shape(t.n);
+    t.levels = t.shape.levels;
+    t.nsplit = (int64_t)1 << t.levels;
+    if (t.dtype == PNB_F64) build_morton_typed<double>(t, cols, (const double *)mass_dev);
+    else build_morton_typed<float>(t, cols, (const float *)mass_dev);
+}
+
+}  // namespace pnb

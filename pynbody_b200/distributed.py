@@ -516,9 +516,12 @@ class DistributedKDTree:
         else:
             # interior queries see only owned particles; boundary queries run on tree2 with the halo's rho / qty
             out = self.tree1.reduce(op, self._sm_own, self._rho_own, q_own, k, kernel_id, self._interior)
+            # halo exchange #2 is a collective: EVERY rank takes part, also one without boundary queries of its
+            # own (an isolated clump, a void at its split plane) -- the others still need its particles' values
+            rho2 = self._tree2_values(self._rho_own)
+            qty2 = self._tree2_values(q_own)
             if self._fidx.numel() > 0:
-                out2 = self.tree2.reduce(op, self._tree2_values(self._sm_own, 1.0), self._tree2_values(self._rho_own),
-                                         self._tree2_values(q_own), k, kernel_id, self._mask2)
+                out2 = self.tree2.reduce(op, self._tree2_values(self._sm_own, 1.0), rho2, qty2, k, kernel_id, self._mask2)
                 out = out.clone()
                 out[self._fidx] = out2[self._f2]
         if out.dim() == 2 and op in ("disp", "div"):

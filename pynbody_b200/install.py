@@ -10,6 +10,7 @@ filt/__init__.py:232,257,299) and end up on the GPU.
 """
 from __future__ import annotations
 
+import gc
 import importlib
 
 _saved = {}
@@ -37,6 +38,11 @@ def install(pynbody=None, replace_kdtree_class=True, healpix=True, filters=True)
                       render_image=getattr(rnd, "render_image", None), to_3d_grid=getattr(rnd, "to_3d_grid", None),
                       healpix=getattr(rnd, "render_spherical_image_core", None),
                       selection=getattr(sel, "selection", None) if sel else None)
+    # trees built so far belong to the extension that built them: let unreferenced ones die first, and route the
+    # ``free`` of any survivor (KDTree.__del__ resolves ``kdmain`` at call time) back to the reference module
+    gc.collect()
+    if _saved["kdmain"] is not None and _saved["kdmain"] is not kdmain:
+        kdmain._foreign_free = getattr(_saved["kdmain"], "free", None)
     kdt.kdmain = kdmain                      # the reference KDTree class resolves `kdmain.*` at call time
     if replace_kdtree_class:
         kdt.KDTree = KDTree                  # lazily materialised kdnodes / particle_offsets
@@ -63,6 +69,7 @@ def uninstall(pynbody=None):
     kdt = importlib.import_module(pynbody.__name__ + ".kdtree")
     rnd = importlib.import_module(pynbody.__name__ + ".sph._render")
     sel = _optional(pynbody.__name__ + ".filt.geometry_selection")
+    gc.collect()                             # GPU trees nobody references any more are freed by the module that owns them
     kdt.kdmain, kdt.KDTree = _saved["kdmain"], _saved["KDTree"]
     rnd.render_image, rnd.to_3d_grid = _saved["render_image"], _saved["to_3d_grid"]
     if _saved["healpix"] is not None:

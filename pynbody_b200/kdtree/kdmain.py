@@ -140,7 +140,15 @@ def import_prebuilt(kd, kdnodes, particle_offsets, _unused=0):
     _create_device_tree(kd)
 
 
+_foreign_free = None     # set by install(): the reference module's ``free`` for trees it built before the swap
+
+
 def free(kd):
+    if kd is not None and not isinstance(kd, _KDContext):
+        # a tree of the reference's own extension (a PyCapsule) being collected after install()
+        if _foreign_free is not None:
+            _foreign_free(kd)
+        return
     if kd is not None and kd.handle is not None:
         _lib.lib().pnb_tree_destroy(kd.handle)
         kd.handle = None

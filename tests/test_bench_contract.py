@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(extra_env=None, *flags):
     env = dict(os.environ)
     env.update(extra_env or {})
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-sample-side", "20",
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n-side", "20", "--render-res", "64",
                            "--steps", "2", "--warmup", "1", *flags], capture_output=True, text=True, env=env, timeout=300)
 
 
@@ -34,6 +34,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the arm runs the workload it names (the same particle set as the GPU arm), and the render half of the metric
+    assert d["config"]["particles_per_gpu"] == 20 ** 3 and "8000 particles" in d["cpu_baseline"]["sample"]
+    img = d["render"]["image"]
+    assert img["mpix_per_s"] > 0 and img["cpu_baseline"]["unit"] == "Mpix/s" and img["resolution"] == 64
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -35,6 +35,14 @@ def _worker(rank, world, port, gen, n, k, periodic, outdir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        if gen == "three_clumps":
+            # fixed split planes in the voids between the clumps (x = 0.3 and x = 0.7), in the form decompose() returns
+            import pynbody_b200.distributed as D
+            inf = float("inf")
+            doms = D.Domains([(torch.tensor([lo, -inf, -inf], dtype=torch.float64), torch.tensor([hi, inf, inf], dtype=torch.float64))
+                              for lo, hi in ((-inf, 0.3), (0.3, 0.7), (0.7, inf))])
+            doms.splits = [(0, 0.3, -1, 1), (0, 0.7, -2, -3)]
+            D.decompose = lambda *a, **kw: (doms, False)
         pos, vel, mass = _particles(gen, n)
         # every rank starts with an arbitrary (strided) share of the particles, as a file chunk would be
         mine = slice(rank, None, world)
@@ -52,6 +60,15 @@ def _particles(gen, n):
     if gen == "uniform":
         pos, vel, mass = synth.uniform_box(n, 5, np.float64)
         rng = np.random.default_rng(6)
+        mass = rng.uniform(0.5, 1.5, n) / n
+    elif gen == "three_clumps":
+        # three well separated clumps along x in an open box; the worker pins the split planes into the voids.
+        # The outer clumps are tight (no ball reaches a face: zero boundary queries on ranks 0 and 2); the middle
+        # one has a few stragglers next to the x = 0.3 plane whose balls cross it
+        rng = np.random.default_rng(8)
+        pos = np.concatenate([rng.normal(0.0, 0.004, (n // 3, 3)) + np.array([c, 0.5, 0.5]) for c in (0.1, 0.5, 0.9)])
+        pos[n // 3: n // 3 + 5] = np.array([0.3001, 0.5, 0.5]) + rng.normal(0.0, 1e-5, (5, 3))
+        vel = rng.normal(0.0, 1.0, (n, 3))
         mass = rng.uniform(0.5, 1.5, n) / n
     else:
         pos, vel, mass = synth.clumpy_box(n, 7, np.float64, n_clumps=6)
@@ -84,6 +101,25 @@ def test_distributed_equals_single_rank(world, gen, periodic, tmp_path):
     assert owned == n                                   # every particle has exactly one owner
     assert 0 < flagged < n and 0 < halo < 2 * n         # a real halo was exchanged, and it is need-based
     assert np.array_equal(sm, sm1), "smoothing lengths must not depend on the decomposition"
+    np.testing.assert_allclose(rho, rho1, rtol=1e-12)
+    np.testing.assert_allclose(vm, vm1, rtol=1e-9, atol=1e-12)
+
+
+def test_rank_without_boundary_queries_still_joins_every_collective(tmp_path):
+    """Three ranks, one of which has NO boundary query (an isolated clump): the halo-value exchanges of sph_op
+    are collectives and every rank must enter them (a rank that skipped them hung the others or mis-paired the
+    all-to-all with the next one).  mp.spawn would time out / fail on a mismatch; results must equal one rank's."""
+    world, n, k = 3, 3000, 16
+    mp.spawn(_worker, args=(world, _free_port(), "three_clumps", n, k, False, str(tmp_path)), nprocs=world, join=True)
+    sm1, rho1, vm1 = _single("three_clumps", n, k, False)
+    sm = np.empty(n); rho = np.empty(n); vm = np.empty((n, 3))
+    flagged = []
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        sm[r::world], rho[r::world], vm[r::world] = z["sm"], z["rho"], z["vm"]
+        flagged.append(int(z["flagged"]))
+    assert min(flagged) == 0 and max(flagged) > 0, flagged
+    assert np.array_equal(sm, sm1)
     np.testing.assert_allclose(rho, rho1, rtol=1e-12)
     np.testing.assert_allclose(vm, vm1, rtol=1e-9, atol=1e-12)
 

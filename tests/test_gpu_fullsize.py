@@ -113,7 +113,7 @@ def test_neighbour_sets_and_gather_counts_at_2e5(dtype, k, kernel_id):
     assert np.array_equal(sm, h), "nn() must overwrite the registered smooth array (smooth.h:429)"
     inv = np.empty(n, np.int64)
     inv[visit] = np.arange(n)                       # oracle rows are in its visiting order
-    idx_o, d2_o, sm_o = idx_o[inv], d2_o[inv], sm_o[inv]
+    idx_o, d2_o = idx_o[inv], d2_o[inv]           # (the smoothing lengths already are in file order)
     assert np.array_equal(h, sm_o)
     # distances: identical multisets
     assert np.array_equal(np.sort(d2, axis=1), np.sort(d2_o, axis=1))
@@ -189,8 +189,11 @@ def test_c3_2048_image_and_256_grid_against_compiled_reference():
     want = ref.render_image(*args, num_threads=threads)
     assert img.shape == (2048, 2048) and img.dtype == np.float32
     np.testing.assert_allclose(img, want, rtol=1e-4, atol=1e-6 * want.max())
-    # mass conservation: integral of the projected image = total mass (the box is fully covered)
-    assert abs(img.astype(np.float64).sum() / 2048 ** 2 - mass.sum()) < 1e-4 * mass.sum()
+    # mass conservation: integral of the projected image = total mass (the box is fully covered) up to the
+    # renderer's 201-entry nearest-lower kernel table (_render.pyx:186-193; the reference's image integrates
+    # to the same 1.0125)
+    assert abs(img.astype(np.float64).sum() / 2048 ** 2 - mass.sum()) < 0.02 * mass.sum()
+    assert abs(img.astype(np.float64).sum() - want.astype(np.float64).sum()) < 1e-5 * want.astype(np.float64).sum()
     kern3 = kernels.WendlandC2Kernel()
     gargs = (256, 256, 256, x, y, z, sm, -0.5, 0.5, -0.5, 0.5, -0.5, 0.5, rho, mass, rho, 0.0, np.inf, kern3,
              wrap, wrap, wrap)

@@ -18,6 +18,7 @@ import pytest
 
 import cases
 from pynbody_b200 import synth
+from pynbody_b200.kdtree import kdmain
 
 pytestmark = pytest.mark.gpu
 
@@ -92,6 +93,44 @@ def test_tree_invariants(n, dtype):
             assert np.array_equal(bounds[b, 3:], p.max(axis=0))
         else:
             assert np.all(bounds[b, :3] == np.inf) and np.all(bounds[b, 3:] == -np.inf)
+
+
+@pytest.mark.parametrize("build", [0, 1], ids=["morton", "levelwise"])
+@pytest.mark.parametrize("n,dtype", [(40, np.float64), (2048, np.float64), (2049, np.float64), (4096, np.float32),
+                                     (70_001, np.float32), (300_000, np.float64)])
+def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype):
+    """Device tree from the Morton sort + shared-memory kd levels (default) and from the level-by-level build:
+    every node's bounds are the union of its children's (the searches prune on them), buckets are tight, and
+    the smoothing lengths -- which must not depend on the tree -- equal the oracle's bit for bit."""
+    from oracle import oracle
+    from pynbody_b200 import _lib
+    pos, vel, mass = synth.clumpy_box(n, 3 + n % 7, dtype)
+    kdmain.set_option("tree_build", build)
+    try:
+        kd = _tree(pos, mass, 1.0)
+    finally:
+        kdmain.set_option("tree_build", 0)
+    L = _lib.lib()
+    h = kd.kdtree.handle
+    nb = L.pnb_tree_num_buckets(h)
+    boxes = np.empty((2 * nb, 6))
+    _lib.check(L.pnb_tree_node_bounds(h, boxes.ctypes.data))
+    order = np.empty(n, np.int64)
+    _lib.check(L.pnb_tree_order(h, order.ctypes.data))
+    assert np.array_equal(np.sort(order), np.arange(n))
+    for node in range(nb - 1, 0, -1):
+        lo = np.minimum(boxes[2 * node, :3], boxes[2 * node + 1, :3])
+        hi = np.maximum(boxes[2 * node, 3:], boxes[2 * node + 1, 3:])
+        assert np.array_equal(boxes[node, :3], lo) and np.array_equal(boxes[node, 3:], hi), node
+    p64 = pos.astype(np.float64)
+    assert np.array_equal(boxes[1, :3], p64.min(axis=0)) and np.array_equal(boxes[1, 3:], p64.max(axis=0))
+    for b in range(0, nb, max(1, nb // 40)):
+        p = p64[order[32 * b:32 * b + 32]]
+        if len(p):
+            assert np.array_equal(boxes[nb + b, :3], p.min(axis=0)) and np.array_equal(boxes[nb + b, 3:], p.max(axis=0))
+    k = min(32, n)
+    sm = _smooth(kd, pos, k)
+    assert np.array_equal(sm, oracle.OracleKDTree(pos, mass, 16, 1.0, None, 0).smooth(k))
 
 
 @pytest.mark.parametrize("n,leafsize,dtype", [(5000, 16, np.float64), (5000, 32, np.float32), (777, 8, np.float64),

@@ -121,6 +121,7 @@ def test_reference_kdtree_class_on_our_native_module(pyn):
     f = refpynbody.new_gas_snapshot(pyn, pos, vel, mass, boxsize=1.0)
     ref = {k: np.array(f[k]) for k in ("smooth", "rho", "v_mean", "v_div")}
     ref_nodes = np.array(f.kdtree.kdnodes)
+    del f
     install.install(pyn, replace_kdtree_class=False)
     try:
         g = refpynbody.new_gas_snapshot(pyn, pos, vel, mass, boxsize=1.0)
@@ -129,6 +130,7 @@ def test_reference_kdtree_class_on_our_native_module(pyn):
         nodes = np.array(g.kdtree.kdnodes)
         offsets = np.array(g.kdtree.particle_offsets)
         near = g.kdtree.particles_in_sphere((0.1, 0.2, 0.3), 0.07)
+        del g                        # its tree belongs to the GPU module: release it before the swap back
     finally:
         install.uninstall(pyn)
     assert np.array_equal(ref["smooth"], got["smooth"])
