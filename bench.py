@@ -97,9 +97,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons of the samples taken between t0 and t1 (the timed region).  The
+        sampler is started before the warm-up so that nvidia-smi's own start-up (hundreds of ms of driver
+        queries) stays out of the timed steps."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -109,7 +112,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.25)]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -305,13 +309,14 @@ def run_ours(args):
         barrier()
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        step(d_pos, d_mass, d_sm, d_rho, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(d_pos, d_mass, d_sm, d_rho, False)
+    t_region = time.time()
     total_ms = timed(lambda: step(d_pos, d_mass, d_sm, d_rho, True), args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region, time.time()) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
@@ -527,15 +532,16 @@ def run_ours_distributed(args):
         barrier()
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        step(pos, mass)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(pos, mass)
     l0 = kdmain.total_launches()
+    t_region = time.time()
     total_ms = timed(lambda: step(pos, mass), args.steps)
     launches = kdmain.total_launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region, time.time()) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     step_e2e()
     e2e_ms = timed(step_e2e, args.steps) / args.steps

@@ -77,8 +77,10 @@ int pnb_device_count(void);
  *                      they fit in half of the free device memory, so that rho / mean / dispersion / div / curl
  *                      stream over them instead of searching again; 0 never; 1 always.  (env PNB_NEIGHBOUR_LISTS)
  *   "gather_walk"      1: the reductions always use the tree-walking fixed-radius gather.  (env PNB_GATHER_WALK)
- *   "tree_build"       0 (default): device tree from one Morton sort + shared-memory kd levels; 1: the level-by-level
- *                      median-split build over three per-axis sorts.  Results do not depend on it.  (env PNB_TREE_BUILD)
+ *   "tree_build"       how the device tree is built; results do not depend on it.  1 (default): median-split kd-tree,
+ *                      upper levels by global passes over three per-axis sorted lists, the lowest levels per sub-tree
+ *                      in shared memory; 2: every level by global passes; 0: one Morton-key sort for the upper levels
+ *                      + shared-memory kd levels (cheapest build, slower searches).  (env PNB_TREE_BUILD)
  * PNB_ERR_VALUE for an unknown name. */
 int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */

@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnb_b200.so")
+# PNB_B200_LIB selects another build of the same library (developer builds with kernel statistics: `make stats`)
+LIB_PATH = os.environ.get("PNB_B200_LIB") or os.path.join(_HERE, "libpnb_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_VALUE, ERR_TYPE, ERR_RUNTIME, ERR_CUDA, ERR_MEMORY = 0, -1, -2, -3, -4, -5

@@ -297,7 +297,12 @@ static void update_mass_uniformity(Tree &t)
 }
 
 int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 auto (keep them if they fit), 0 never, 1 always
-int g_opt_tree_build = 0;           // pnb_set_option("tree_build"): 0 = Morton sort + in-shared-memory kd levels, 1 = level-by-level kd build
+// pnb_set_option("tree_build"): how the device tree is built.  1 (default) = median-split kd-tree: upper levels by
+// global passes over three per-axis sorted lists, the lowest 6-7 levels per sub-tree in shared memory; 2 = every level
+// by global passes (the round-1 build); 0 = one Morton-key sort for the upper levels + shared-memory kd levels below
+// (cheapest build, 7.6 vs 15.8 ms at 16.7 M float64 particles, but its buckets cost the neighbour search +28 %:
+// 65.5 vs 51.3 ms -- measured, profiles/r2_tree_build_variants.md)
+int g_opt_tree_build = 1;
 int g_opt_gather_walk = 0;          // pnb_set_option("gather_walk"): 1 = reductions always walk the tree
 static struct OptionsFromEnv {
     OptionsFromEnv()
@@ -546,8 +551,8 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
                 fetch_columns(mass, mass_stride, 0, 1, dtype, mem, n, mass_dev.p, t->stream);
             }
         }
-        if (g_opt_tree_build == 1) build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
-        else build_tree_morton(*t, cols, mass ? mass_dev.p : nullptr);
+        if (g_opt_tree_build == 0) build_tree_morton(*t, cols, mass ? mass_dev.p : nullptr);
+        else build_tree(*t, cols, mass ? mass_dev.p : nullptr, packed_shape(n), true);
         update_mass_uniformity(*t);
         timer.stop();
     });

@@ -189,6 +189,10 @@ void permute_to_file(const Tree &t, const void *tree_in, void *file_out, int nco
 void build_tree(Tree &t, DevBuf &cols, const void *mass_dev, const TreeShape &shape, bool want_soa);
 // the device tree (32-particle buckets): one Morton sort + the lower levels as a kd-tree in shared memory (tree_morton.cu)
 void build_tree_morton(Tree &t, DevBuf &cols, const void *mass_dev);
+// the lowest levels of the packed device tree, built per sub-tree in shared memory (tree_morton.cu): `ids` orders the
+// particles so that sub-tree j at depth levels - lseg owns entries [j * (32 << lseg), ...)
+int segment_levels(int dtype);
+void build_tree_segments(Tree &t, const void *cols, const void *mass_dev, const uint32_t *ids, int lseg);
 
 struct KernelParams {
     int kernel_id;

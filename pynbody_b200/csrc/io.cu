@@ -219,6 +219,17 @@ void fetch_columns(const void *ptr, int64_t s0, int64_t s1, int ncols, int dtype
         host_to_device(dev_out, ptr, (size_t)(n * elem), stream);
         return;
     }
+    if (ncols == 1 && s0 > elem && s0 <= 8 * elem && n > 4096) {
+        // a column view of a wider host array (e.g. pos[:, 1], stride 3 elements): picking the elements out on the
+        // host is a scalar loop at well under 1 GB/s; ship the enclosing span and pick on the device instead
+        const size_t span = (size_t)((n - 1) * s0 + elem);
+        DevBuf wide(span);
+        host_to_device(wide.p, ptr, span, stream);
+        if (elem == 8) PNB_LAUNCH((k_strided_to_columns<uint64_t>), nblk(n, BS), BS, 0, stream, wide.as<unsigned char>(), s0, 0, 1, n, (uint64_t *)dev_out);
+        else PNB_LAUNCH((k_strided_to_columns<uint32_t>), nblk(n, BS), BS, 0, stream, wide.as<unsigned char>(), s0, 0, 1, n, (uint32_t *)dev_out);
+        PNB_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
     DevBuf stage((size_t)(n * ncols * elem));
     if (dense_rows(s0, s1, ncols, elem)) {
         host_to_device(stage.p, ptr, stage.bytes, stream);

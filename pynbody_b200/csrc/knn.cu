@@ -547,10 +547,18 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     const size_t slots = (size_t)t.nsplit * ((size_t)1 << a.LOG) * 32;
     t.nn_valid = false;
     if (keep_ids) {
-        if (t.nn_ids.bytes != slots * sizeof(uint32_t)) t.nn_ids.alloc(slots * sizeof(uint32_t));
-        if (keep_d2) { if (t.nn_d2.bytes != slots * sizeof(T)) t.nn_d2.alloc(slots * sizeof(T)); }
-        else t.nn_d2.release();
-    } else {
+        try {
+            if (t.nn_ids.bytes != slots * sizeof(uint32_t)) t.nn_ids.alloc(slots * sizeof(uint32_t));
+            if (keep_d2) { if (t.nn_d2.bytes != slots * sizeof(T)) t.nn_d2.alloc(slots * sizeof(T)); }
+            else t.nn_d2.release();
+        } catch (const Error &e) {
+            if (e.code != PNB_ERR_MEMORY || keep_d2) throw;      // nn() needs its lists; populate() can do without
+            t.nn_ids.release();
+            t.nn_d2.release();
+            keep_ids = false;
+        }
+    }
+    if (!keep_ids) {
         t.nn_ids.release();
         t.nn_d2.release();
     }
@@ -576,21 +584,25 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     }
 }
 
-// Neighbour lists cost n * K2 * 4 bytes (k = 64: 256 B per particle).  They are kept when they fit beside
-// everything else: at most half of the device memory that is free right now (pnb_set_option
-// "neighbour_lists" / PNB_NEIGHBOUR_LISTS: 0 disables them, 1 forces them).  Without lists the reductions fall back to the tree-walking gather (gather.cu).
+// Neighbour lists cost n * K2 * 4 bytes (k = 64: 256 B per particle).  They are kept when they take at most a
+// quarter of the device's memory (16.7 M particles: 4.3 GB; 134 M: 34 GB); pnb_set_option "neighbour_lists" /
+// PNB_NEIGHBOUR_LISTS: 0 disables them, 1 forces them.  Without lists -- or if the allocation fails -- the
+// reductions fall back to the tree-walking gather (gather.cu).  (No per-call cudaMemGetInfo: a driver query
+// per step serialises against anything else talking to the driver, e.g. a monitoring nvidia-smi.)
 bool neighbour_lists_fit(const Tree &t, int k, bool with_d2)
 {
     if (g_opt_neighbour_lists == 0) return false;
     if (g_opt_neighbour_lists == 1) return true;
+    static size_t total = 0;
+    if (!total) {
+        size_t free_b = 0;
+        if (cudaMemGetInfo(&free_b, &total) != cudaSuccess) { cudaGetLastError(); total = 0; return false; }
+    }
     int LOG = 0;
     while ((1 << LOG) < k) ++LOG;
     const size_t per = 4 + (with_d2 ? tsize(t.dtype) : 0);
     const size_t need = (size_t)t.nsplit * ((size_t)1 << LOG) * 32 * per;
-    size_t have = t.nn_ids.cap + t.nn_d2.cap;          // what this tree already holds for the purpose
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
-    return need <= have + (free_b + cached_bytes()) / 2;
+    return need <= total / 4;
 }
 
 void run_knn(Tree &t, int k, double period, bool fuse_rho, const KernelParams &kp, bool keep_ids, bool keep_d2)

@@ -546,6 +546,24 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     kernel_ms += pnb_last_kernel_ms(2);
 }
 
+// x, y, z as three dense device columns inside `dpos` (ps * 3 * n bytes).  The usual caller passes the columns of one
+// C-contiguous N x 3 position array (renderers.py:660-665: sim['x'], sim['y'], sim['z']); from host memory those come
+// over in ONE contiguous copy and are separated on the device.
+void fetch_positions(const pnb_render_arrays *a, DevBuf &dpos, void *&dx, void *&dy, void *&dz, cudaStream_t s)
+{
+    const int64_t n = a->n;
+    const int64_t ps = (int64_t)tsize(a->pos_dtype);
+    dx = dpos.p; dy = (char *)dpos.p + ps * n; dz = (char *)dpos.p + 2 * ps * n;
+    const char *x = (const char *)a->x, *y = (const char *)a->y, *z = (const char *)a->z;
+    if (y == x + ps && z == x + 2 * ps && a->pos_stride == 3 * ps) {
+        fetch_columns(a->x, 3 * ps, ps, 3, a->pos_dtype, a->mem, n, dpos.p, s);
+        return;
+    }
+    fetch_columns(a->x, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dx, s);
+    fetch_columns(a->y, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dy, s);
+    fetch_columns(a->z, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dz, s);
+}
+
 void check_arrays(const pnb_render_arrays *a)
 {
     if (!a) throw Error(PNB_ERR_VALUE, "render arrays are null");
@@ -601,19 +619,23 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
     double kernel_ms = 0;
     if (n > 0) {
         const size_t ps = tsize(a->pos_dtype);
-        DevBuf dx(ps * n), dy(ps * n), dz(ps * n), dsm(tsize(a->sm_dtype) * n), dq(tsize(a->qty_dtype) * n),
-            dm(tsize(a->mass_dtype) * n), dr(tsize(a->rho_dtype) * n), hd(sizeof(double) * n), wd(sizeof(double) * n);
-        fetch_columns(a->x, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dx.p, s);
-        fetch_columns(a->y, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dy.p, s);
-        fetch_columns(a->z, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dz.p, s);
+        DevBuf dpos(ps * 3 * n), dsm(tsize(a->sm_dtype) * n), dq, dm(tsize(a->mass_dtype) * n), dr(tsize(a->rho_dtype) * n),
+            hd(sizeof(double) * n), wd(sizeof(double) * n);
+        void *dxp, *dyp, *dzp;
+        fetch_positions(a, dpos, dxp, dyp, dzp, s);
         fetch_columns(a->sm, a->sm_stride, 0, 1, a->sm_dtype, a->mem, n, dsm.p, s);
-        fetch_columns(a->qty, a->qty_stride, 0, 1, a->qty_dtype, a->mem, n, dq.p, s);
         fetch_columns(a->mass, a->mass_stride, 0, 1, a->mass_dtype, a->mem, n, dm.p, s);
         fetch_columns(a->rho, a->rho_stride, 0, 1, a->rho_dtype, a->mem, n, dr.p, s);
-        PNB_LAUNCH(k_prepare, nblk(n, 256), 256, 0, s, n, dsm.p, a->sm_dtype, dq.p, a->qty_dtype, dm.p, a->mass_dtype,
+        const void *dqp = dr.p;                               // rendering rho itself (qty is the rho array): one copy serves both
+        if (!(a->qty == a->rho && a->qty_stride == a->rho_stride && a->qty_dtype == a->rho_dtype)) {
+            dq.alloc(tsize(a->qty_dtype) * n);
+            fetch_columns(a->qty, a->qty_stride, 0, 1, a->qty_dtype, a->mem, n, dq.p, s);
+            dqp = dq.p;
+        }
+        PNB_LAUNCH(k_prepare, nblk(n, 256), 256, 0, s, n, dsm.p, a->sm_dtype, dqp, a->qty_dtype, dm.p, a->mass_dtype,
                    dr.p, a->rho_dtype, hd.as<double>(), wd.as<double>());
         Cols c;
-        c.x = dx.p; c.y = dy.p; c.z = dz.p; c.pos_f64 = a->pos_dtype; c.h = hd.as<double>(); c.w = wd.as<double>(); c.n = n;
+        c.x = dxp; c.y = dyp; c.z = dzp; c.pos_f64 = a->pos_dtype; c.h = hd.as<double>(); c.w = wd.as<double>(); c.n = n;
         Work wk;
         wk.s = s;
         const double zero = 0.0;
@@ -890,17 +912,16 @@ void render_healpix(const pnb_render_arrays *a, int nside, const float *lut, int
     double kernel_ms = 0;
     if (n > 0) {
         const size_t ps = tsize(a->pos_dtype);
-        DevBuf dx(ps * n), dy(ps * n), dz(ps * n), dh(tsize(a->sm_dtype) * n), dq(tsize(a->qty_dtype) * n),
+        DevBuf dpos(ps * 3 * n), dh(tsize(a->sm_dtype) * n), dq(tsize(a->qty_dtype) * n),
             dm(tsize(a->mass_dtype) * n), dr(tsize(a->rho_dtype) * n);
-        fetch_columns(a->x, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dx.p, s);
-        fetch_columns(a->y, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dy.p, s);
-        fetch_columns(a->z, a->pos_stride, 0, 1, a->pos_dtype, a->mem, n, dz.p, s);
+        void *dxp, *dyp, *dzp;
+        fetch_positions(a, dpos, dxp, dyp, dzp, s);
         fetch_columns(a->sm, a->sm_stride, 0, 1, a->sm_dtype, a->mem, n, dh.p, s);
         fetch_columns(a->qty, a->qty_stride, 0, 1, a->qty_dtype, a->mem, n, dq.p, s);
         fetch_columns(a->mass, a->mass_stride, 0, 1, a->mass_dtype, a->mem, n, dm.p, s);
         fetch_columns(a->rho, a->rho_stride, 0, 1, a->rho_dtype, a->mem, n, dr.p, s);
         HpArgs h;
-        h.x = dx.p; h.y = dy.p; h.z = dz.p; h.h = dh.p; h.qty = dq.p; h.mass = dm.p; h.rho = dr.p;
+        h.x = dxp; h.y = dyp; h.z = dzp; h.h = dh.p; h.qty = dq.p; h.mass = dm.p; h.rho = dr.p;
         h.pos_f64 = a->pos_dtype; h.h_f64 = a->sm_dtype; h.qty_f64 = a->qty_dtype; h.mass_f64 = a->mass_dtype;
         h.rho_f64 = a->rho_dtype; h.n = n; h.nside = nside; h.ns = n_lut; h.projected = h_power == 2;
         h.max_d = max_d; h.shell_radius = shell_radius;

@@ -29,6 +29,7 @@
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
+#include <algorithm>
 
 namespace pnb {
 
@@ -225,7 +226,7 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     }
 
     t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
-    t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
+    if (!(shape.packed && want_soa && g_opt_tree_build != 2)) t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
     DevBuf dim(sizeof(int8_t) * 2 * t.nsplit), split(sizeof(T) * 2 * t.nsplit);
     DevBuf side(sizeof(uint8_t) * n), S(sizeof(uint32_t) * 3 * n);
     PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2 * t.nsplit, s));
@@ -239,7 +240,12 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     }
     DevBuf scan_tmp(scan_bytes);
 
-    for (int level = 0; level < levels; ++level) {
+    // The packed device tree finishes its lowest levels per sub-tree in shared memory (tree_morton.cu: exact
+    // medians by an in-CTA sort, tight bounds, tree-ordered structure of arrays) instead of one global pass +
+    // prefix sum per level; the reference-shaped tree (export) runs every level here.
+    const int lseg = (shape.packed && want_soa && g_opt_tree_build != 2) ? std::min(levels, segment_levels(t.dtype)) : 0;
+    const int global_levels = levels - lseg;
+    for (int level = 0; level < global_levels; ++level) {
         int64_t nn = (int64_t)1 << level;
         PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
                    dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr);
@@ -251,18 +257,21 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
         uint32_t *tmp = L; L = Ln; Ln = tmp;
     }
-    PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
-               dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>());
-
-    t.order.alloc(sizeof(uint32_t) * n);
-    PNB_CUDA(cudaMemcpyAsync(t.order.p, L, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
-    if (want_soa) {                                    // tree-ordered structure of arrays
-        t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
-        if (mass) t.mass.alloc(sizeof(T) * n);
-        t.has_mass = mass != nullptr;
-        if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sorts
-        PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
-                   t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
+    if (lseg > 0) {
+        build_tree_segments(t, c.p, mass, L, lseg);
+    } else {
+        PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
+                   dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>());
+        t.order.alloc(sizeof(uint32_t) * n);
+        PNB_CUDA(cudaMemcpyAsync(t.order.p, L, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
+        if (want_soa) {                                    // tree-ordered structure of arrays
+            t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
+            if (mass) t.mass.alloc(sizeof(T) * n);
+            t.has_mass = mass != nullptr;
+            if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sorts
+            PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
+                       t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
+        }
     }
     T rb[6];
     PNB_CUDA(cudaMemcpyAsync(rb, t.box.as<T>() + 6, sizeof(rb), cudaMemcpyDeviceToHost, s));

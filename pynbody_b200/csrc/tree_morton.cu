@@ -282,6 +282,35 @@ size_t segment_smem()
     return (size_t)SEG * 4 * sizeof(T) + (size_t)(SEG / 64) * 6 * sizeof(typename Ord<T>::U) + (size_t)SEG * 2 + SEG / 64 + 16;
 }
 
+// The lower `lseg` levels of the device tree, one CTA per sub-tree: `ids` lists the particles (file indices) so
+// that the sub-tree rooted at node (levels - lseg, j) owns entries [j * 32 << lseg, ...).  Writes the bounds of
+// the nodes at depth >= levels - lseg, the bucket offsets and the tree-ordered structure of arrays; t.box must
+// have been allocated.
+template <typename T>
+void build_segments(Tree &t, const T *cols, const T *mass, const uint32_t *ids, int lseg)
+{
+    const int64_t n = t.n;
+    cudaStream_t s = t.stream;
+    const int BS = 256;
+    t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
+    t.order.alloc(sizeof(uint32_t) * n);
+    t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
+    if (mass) t.mass.alloc(sizeof(T) * n);
+    t.has_mass = mass != nullptr;
+    SegArgs<T> a;
+    a.n = n; a.nsplit = t.nsplit; a.levels = t.levels;
+    a.lseg = lseg;
+    a.cols = cols; a.mass = mass; a.ids = ids;
+    a.x = t.x.as<T>(); a.y = t.y.as<T>(); a.z = t.z.as<T>(); a.m = t.mass.as<T>();
+    a.order = t.order.as<uint32_t>(); a.box = t.box.as<T>();
+    const size_t smem = segment_smem<T>();
+    PNB_CUDA(cudaFuncSetAttribute(k_build_segment<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sorts
+    const unsigned nseg = (unsigned)(t.nsplit >> lseg);
+    PNB_LAUNCH((k_build_segment<T>), nseg, (32 << SegCfg<T>::LSEG) / 4, smem, s, a);
+    PNB_LAUNCH(k_bucket_starts, (unsigned)((t.nsplit + 1 + BS - 1) / BS), BS, 0, s, n, t.nsplit, t.bucket_start.as<int32_t>());
+}
+
 template <typename T>
 void build_morton_typed(Tree &t, DevBuf &c, const T *mass)
 {
@@ -310,27 +339,11 @@ void build_morton_typed(Tree &t, DevBuf &c, const T *mass)
     }
 
     t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
-    t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
-    t.order.alloc(sizeof(uint32_t) * n);
-    t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
-    if (mass) t.mass.alloc(sizeof(T) * n);
-    t.has_mass = mass != nullptr;
     PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2, s));      // node 0 is unused
-
-    SegArgs<T> a;
-    a.n = n; a.nsplit = t.nsplit; a.levels = t.levels;
-    a.lseg = std::min(t.levels, SegCfg<T>::LSEG);
-    a.cols = c.as<T>(); a.mass = mass; a.ids = ids_sorted.as<uint32_t>();
-    a.x = t.x.as<T>(); a.y = t.y.as<T>(); a.z = t.z.as<T>(); a.m = t.mass.as<T>();
-    a.order = t.order.as<uint32_t>(); a.box = t.box.as<T>();
-    const size_t smem = segment_smem<T>();
-    PNB_CUDA(cudaFuncSetAttribute(k_build_segment<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sort
-    const unsigned nseg = (unsigned)(t.nsplit >> a.lseg);
-    PNB_LAUNCH((k_build_segment<T>), nseg, (32 << SegCfg<T>::LSEG) / 4, smem, s, a);
-    const int ltop = t.levels - a.lseg;
+    const int lseg = std::min(t.levels, SegCfg<T>::LSEG);
+    build_segments<T>(t, c.as<T>(), mass, ids_sorted.as<uint32_t>(), lseg);
+    const int ltop = t.levels - lseg;
     if (ltop > 0) PNB_LAUNCH((k_upper_bounds<T>), 1, 1024, 0, s, t.box.as<T>(), ltop);
-    PNB_LAUNCH(k_bucket_starts, (unsigned)((t.nsplit + 1 + BS - 1) / BS), BS, 0, s, n, t.nsplit, t.bucket_start.as<int32_t>());
 
     T rb[6];
     PNB_CUDA(cudaMemcpyAsync(rb, t.box.as<T>() + 6, sizeof(rb), cudaMemcpyDeviceToHost, s));
@@ -339,6 +352,13 @@ void build_morton_typed(Tree &t, DevBuf &c, const T *mass)
 }
 
 }  // namespace
+
+int segment_levels(int dtype) { return dtype == PNB_F64 ? SegCfg<double>::LSEG : SegCfg<float>::LSEG; }
+void build_tree_segments(Tree &t, const void *cols, const void *mass_dev, const uint32_t *ids, int lseg)
+{
+    if (t.dtype == PNB_F64) build_segments<double>(t, (const double *)cols, (const double *)mass_dev, ids, lseg);
+    else build_segments<float>(t, (const float *)cols, (const float *)mass_dev, ids, lseg);
+}
 
 // cols: file-order coordinates as dense columns T[3][n]; mass_dev: T[n] in file order or null
 void build_tree_morton(Tree &t, DevBuf &cols, const void *mass_dev)

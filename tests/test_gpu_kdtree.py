@@ -95,7 +95,7 @@ def test_tree_invariants(n, dtype):
             assert np.all(bounds[b, :3] == np.inf) and np.all(bounds[b, 3:] == -np.inf)
 
 
-@pytest.mark.parametrize("build", [0, 1], ids=["morton", "levelwise"])
+@pytest.mark.parametrize("build", [0, 1, 2], ids=["morton", "kd_hybrid", "kd_levelwise"])
 @pytest.mark.parametrize("n,dtype", [(40, np.float64), (2048, np.float64), (2049, np.float64), (4096, np.float32),
                                      (70_001, np.float32), (300_000, np.float64)])
 def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype):
@@ -105,11 +105,12 @@ def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype
     from oracle import oracle
     from pynbody_b200 import _lib
     pos, vel, mass = synth.clumpy_box(n, 3 + n % 7, dtype)
+    boxsize = 1.0 if n > 1000 else None          # (a 40-particle periodic box has balls of half the box: SURVEY 8a item 4)
     kdmain.set_option("tree_build", build)
     try:
-        kd = _tree(pos, mass, 1.0)
+        kd = _tree(pos, mass, boxsize)
     finally:
-        kdmain.set_option("tree_build", 0)
+        kdmain.set_option("tree_build", 1)
     L = _lib.lib()
     h = kd.kdtree.handle
     nb = L.pnb_tree_num_buckets(h)
@@ -130,7 +131,7 @@ def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype
             assert np.array_equal(boxes[nb + b, :3], p.min(axis=0)) and np.array_equal(boxes[nb + b, 3:], p.max(axis=0))
     k = min(32, n)
     sm = _smooth(kd, pos, k)
-    assert np.array_equal(sm, oracle.OracleKDTree(pos, mass, 16, 1.0, None, 0).smooth(k))
+    assert np.array_equal(sm, oracle.OracleKDTree(pos, mass, 16, boxsize, None, 0).smooth(k))
 
 
 @pytest.mark.parametrize("n,leafsize,dtype", [(5000, 16, np.float64), (5000, 32, np.float32), (777, 8, np.float64),
