@@ -77,10 +77,10 @@ int pnb_device_count(void);
  *                      they fit in half of the free device memory, so that rho / mean / dispersion / div / curl
  *                      stream over them instead of searching again; 0 never; 1 always.  (env PNB_NEIGHBOUR_LISTS)
  *   "gather_walk"      1: the reductions always use the tree-walking fixed-radius gather.  (env PNB_GATHER_WALK)
- *   "tree_build"       how the device tree is built; results do not depend on it.  1 (default): median-split kd-tree,
- *                      upper levels by global passes over three per-axis sorted lists, the lowest levels per sub-tree
- *                      in shared memory; 2: every level by global passes; 0: one Morton-key sort for the upper levels
- *                      + shared-memory kd levels (cheapest build, slower searches).  (env PNB_TREE_BUILD)
+ *   "tree_build"       how the device tree is built; results do not depend on it.  2 (default): median-split kd-tree,
+ *                      every level by global passes over three per-axis sorted lists; 1: the same with the lowest levels
+ *                      built per sub-tree in shared memory; 0: one Morton-key sort for the upper levels + shared-memory
+ *                      kd levels (cheapest build, slower searches).  (env PNB_TREE_BUILD)
  * PNB_ERR_VALUE for an unknown name. */
 int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */
@@ -147,6 +147,20 @@ int pnb_set_query_mask(pnb_tree *t, const uint8_t *mask, int mem);
 int pnb_mark_in_balls(pnb_tree *t, const void *centres, int64_t stride0, int64_t stride1,
                       const void *radii, int64_t rstride, int64_t nq, double period,
                       uint8_t *flags_out, int mem);
+
+/* pnb_route_plan / pnb_route_pack: moving particles to the rank that owns their spatial domain (device memory only).
+ * The domains are the leaves of a recursive coordinate bisection given as n_splits nodes: particles with
+ * coordinate[split_axis[s]] >= split_plane[s] go to split_child[2s+1], the others to split_child[2s]; a child >= 0
+ * is another node, a child < 0 is rank -(child + 1); node 0 is the root (n_splits == 0: everything is rank 0's).
+ * plan:  owner_out uint8[n] (device) and counts_out int64[n_ranks] (HOST): particles per destination.
+ * pack:  packed_out T[n][4] (device) = rows {x, y, z, m} destination-major -- rank 0's first, in their original
+ *        order (a stable multi-split) -- and src_index_out int64[n] (device) = original index of every row; the
+ *        ranges [sum(counts[:r]), sum(counts[:r+1])) are what an all-to-all sends to rank r.  mass may be NULL. */
+int pnb_route_plan(const void *pos, int64_t stride0, int64_t stride1, int64_t n, int dtype,
+                   const int32_t *split_axis, const double *split_plane, const int32_t *split_child, int n_splits,
+                   int n_ranks, uint8_t *owner_out, int64_t *counts_out);
+int pnb_route_pack(const void *pos, int64_t stride0, int64_t stride1, const void *mass, int64_t mass_stride, int64_t n,
+                   int dtype, const uint8_t *owner, int n_ranks, void *packed_out, int64_t *src_index_out);
 
 /* ---- kdmain.nn_next, all particles at once (kdmain.cpp:390-440) -------------------------------
  * Neighbour lists for every particle: idx_out int64[N][k] (file-order ids, unsorted, self

@@ -56,6 +56,8 @@ SIGNATURES = {
     "pnb_set_array": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _i32]),
     "pnb_set_query_mask": (_i32, [_vp, _vp, _i32]),
     "pnb_mark_in_balls": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _vp, _i32]),
+    "pnb_route_plan": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "pnb_route_pack": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "pnb_populate": (_i32, [_vp, _i32, _i32, _i32, _dbl, _pi32]),
     "pnb_knn": (_i32, [_vp, _i32, _dbl, _vp, _vp, _vp, _pi32]),
     "pnb_knn_start": (_i32, [_vp, _i32, _dbl, _pi32]),

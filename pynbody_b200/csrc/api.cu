@@ -297,12 +297,14 @@ static void update_mass_uniformity(Tree &t)
 }
 
 int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 auto (keep them if they fit), 0 never, 1 always
-// pnb_set_option("tree_build"): how the device tree is built.  1 (default) = median-split kd-tree: upper levels by
-// global passes over three per-axis sorted lists, the lowest 6-7 levels per sub-tree in shared memory; 2 = every level
-// by global passes (the round-1 build); 0 = one Morton-key sort for the upper levels + shared-memory kd levels below
-// (cheapest build, 7.6 vs 15.8 ms at 16.7 M float64 particles, but its buckets cost the neighbour search +28 %:
-// 65.5 vs 51.3 ms -- measured, profiles/r2_tree_build_variants.md)
-int g_opt_tree_build = 1;
+// pnb_set_option("tree_build"): how the device tree is built (results never depend on it).
+//   2 (default)  median-split kd-tree, every level by global passes over three per-axis sorted lists (tree_build.cu)
+//   1            the same, but the lowest 6-7 levels per sub-tree in shared memory (tree_morton.cu: k_build_segment)
+//   0            one Morton-key sort for the upper levels + shared-memory kd levels below
+// Measured at 16.7 M float64 particles (profiles/r2_tree_build_variants.md): build 15.8 / 17.9 / 7.6 ms, kNN kernel
+// 51.3 / 51.3 / 65.5 ms: the Morton tree is the cheapest to build but its buckets cost the neighbour search +28 %,
+// and the shared-memory sorting network (5.8 ms for 6 levels) does not yet beat six global passes (3.6 ms).
+int g_opt_tree_build = 2;
 int g_opt_gather_walk = 0;          // pnb_set_option("gather_walk"): 1 = reductions always walk the tree
 static struct OptionsFromEnv {
     OptionsFromEnv()

@@ -100,8 +100,88 @@ __device__ __forceinline__ T image_delta(T q, T x, T L, T half)
     return d;
 }
 
+// one (query, neighbour) term of the reduction; PASS 1 = second sweep of the dispersion operators
+template <typename T, typename Q, int OP, bool PERIODIC, int PASS>
+__device__ __forceinline__ void gl_term(const GlArgs<T, Q> &a, const Rec4<T> &pj, const Rec4<double> &qj, T qx, T qy, T qz,
+                                        T L, T half, T ball2, T ih2, T norm, const double (&own)[3], const Q (&mean)[3],
+                                        double (&acc)[3])
+{
+    using OT = GlTraits<OP>;
+    const T dx = image_delta<T, PERIODIC>(qx, pj.a, L, half), dy = image_delta<T, PERIODIC>(qy, pj.b, L, half),
+            dz = image_delta<T, PERIODIC>(qz, pj.c, L, half);
+    const T d2 = Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
+    if (!(d2 <= ball2)) return;                                     // smooth.h:310 (non-strict)
+    if (OP == GL_RHO) {
+        // rho_i += (W * norm) * m_j, each term rounded as the reference rounds it (smooth.h:640-645)
+        T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);
+        w *= norm;
+        acc[0] += (double)(w * pj.d);
+    } else if (!OT::grad) {
+        T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);
+        w *= norm;
+        const double wm = (double)w * qj.a;
+        if (PASS == 0) {
+            acc[0] += (double)(Q)(wm * qj.b);
+            if (OT::qcols > 1) { acc[1] += (double)(Q)(wm * qj.c); acc[2] += (double)(Q)(wm * qj.d); }
+        } else {                                                    // squared deviations from the mean (smooth.h:814-918)
+            Q tq = mean[0] - (Q)qj.b;
+            acc[0] += (double)(Q)(wm * (double)tq * (double)tq);
+            if (OT::qcols > 1) {
+                tq = mean[1] - (Q)qj.c;
+                acc[0] += (double)(Q)(wm * (double)tq * (double)tq);
+                tq = mean[2] - (Q)qj.d;
+                acc[0] += (double)(Q)(wm * (double)tq * (double)tq);
+            }
+        }
+    } else {
+        // raw UNWRAPPED separation (smooth.h:736-738, :791-793), wrapped r2 in the kernel gradient
+        const T ux = qx - pj.a, uy = qy - pj.b, uz = qz - pj.c;
+        T g = (T)kern_g(a.kernel_id, d2 * ih2, d2);
+        g *= norm;
+        const T dq0 = (T)(qj.b - own[0]), dq1 = (T)(qj.c - own[1]), dq2 = (T)(qj.d - own[2]);
+        const double gm = (double)g * qj.a;
+        if (OP == GL_DIV) {
+            const T dv = ux * dq0 + uy * dq1 + uz * dq2;
+            acc[0] += (double)(Q)(gm * (double)dv);
+        } else {
+            const T c0 = uy * dq2 - uz * dq1, c1 = uz * dq0 - ux * dq2, c2 = ux * dq1 - uy * dq0;
+            acc[0] += (double)(Q)(gm * (double)c0);
+            acc[1] += (double)(Q)(gm * (double)c1);
+            acc[2] += (double)(Q)(gm * (double)c2);
+        }
+    }
+}
+
+// one sweep over the lane's neighbour list, U list slots at a time: the U id loads, then the U (+U) record gathers are
+// issued before any of them is consumed, so that each warp keeps several L1/L2 round trips in flight (the kernel is
+// bound by the latency of these gathers, not by bytes or issue slots: profiles/r2_gather_list_summary.txt)
+template <typename T, typename Q, int OP, bool PERIODIC, int PASS>
+__device__ __forceinline__ void gl_sweep(const GlArgs<T, Q> &a, const uint32_t *ids, uint32_t self, T qx, T qy, T qz,
+                                         T L, T half, T ball2, T ih2, T norm, const double (&own)[3], const Q (&mean)[3],
+                                         double (&acc)[3])
+{
+    constexpr int U = OP == GL_RHO ? 4 : 2;
+    for (int e0 = 0; e0 < a.k; e0 += U) {
+        uint32_t j[U];
+        Rec4<T> pj[U];
+        Rec4<double> qj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = e0 + u < a.k ? ids[(e0 + u) * 32] : self;     // (filler slots are skipped below)
+#pragma unroll
+        for (int u = 0; u < U; ++u) pj[u] = load_rec(a.pos4 + j[u]);
+        if (OP != GL_RHO) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) qj[u] = load_rec(a.qty4 + j[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (e0 + u < a.k)
+                gl_term<T, Q, OP, PERIODIC, PASS>(a, pj[u], qj[u], qx, qy, qz, L, half, ball2, ih2, norm, own, mean, acc);
+    }
+}
+
 template <typename T, typename Q, int OP, bool PERIODIC>
-__global__ void __launch_bounds__(GL_WARPS * 32) k_gather_list(GlArgs<T, Q> a)
+__global__ void __launch_bounds__(GL_WARPS * 32, 4) k_gather_list(GlArgs<T, Q> a)
 {
     using OT = GlTraits<OP>;
     const int lane = threadIdx.x & 31;
@@ -128,71 +208,13 @@ __global__ void __launch_bounds__(GL_WARPS * 32) k_gather_list(GlArgs<T, Q> a)
     const uint32_t *ids = a.nn_ids + (size_t)bucket * a.K2 * 32 + lane;
 
     double acc[3] = {0, 0, 0};
-#pragma unroll 2
-    for (int e = 0; e < a.k; ++e) {
-        const uint32_t j = ids[e * 32];
-        const Rec4<T> pj = load_rec(a.pos4 + j);
-        const T dx = image_delta<T, PERIODIC>(qx, pj.a, L, half), dy = image_delta<T, PERIODIC>(qy, pj.b, L, half),
-                dz = image_delta<T, PERIODIC>(qz, pj.c, L, half);
-        const T d2 = Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
-        if (!(d2 <= ball2)) continue;                                   // smooth.h:310 (non-strict)
-        if (OP == GL_RHO) {
-            // rho_i += (W * norm) * m_j, each term rounded as the reference rounds it (smooth.h:640-645)
-            T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);
-            w *= norm;
-            acc[0] += (double)(w * pj.d);
-        } else if (!OT::grad) {
-            const Rec4<double> qj = load_rec(a.qty4 + j);
-            T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);
-            w *= norm;
-            const double wm = (double)w * qj.a;
-            acc[0] += (double)(Q)(wm * qj.b);
-            if (OT::qcols > 1) { acc[1] += (double)(Q)(wm * qj.c); acc[2] += (double)(Q)(wm * qj.d); }
-        } else {
-            // raw UNWRAPPED separation (smooth.h:736-738, :791-793), wrapped r2 in the kernel gradient
-            const Rec4<double> qj = load_rec(a.qty4 + j);
-            const T ux = qx - pj.a, uy = qy - pj.b, uz = qz - pj.c;
-            T g = (T)kern_g(a.kernel_id, d2 * ih2, d2);
-            g *= norm;
-            const T dq0 = (T)(qj.b - own[0]), dq1 = (T)(qj.c - own[1]), dq2 = (T)(qj.d - own[2]);
-            const double gm = (double)g * qj.a;
-            if (OP == GL_DIV) {
-                const T dv = ux * dq0 + uy * dq1 + uz * dq2;
-                acc[0] += (double)(Q)(gm * (double)dv);
-            } else {
-                const T c0 = uy * dq2 - uz * dq1, c1 = uz * dq0 - ux * dq2, c2 = ux * dq1 - uy * dq0;
-                acc[0] += (double)(Q)(gm * (double)c0);
-                acc[1] += (double)(Q)(gm * (double)c1);
-                acc[2] += (double)(Q)(gm * (double)c2);
-            }
-        }
-    }
+    Q mean[3] = {0, 0, 0};
+    gl_sweep<T, Q, OP, PERIODIC, 0>(a, ids, (uint32_t)p, qx, qy, qz, L, half, ball2, ih2, norm, own, mean, acc);
     if (OT::two_pass) {
-        // second sweep over the same list: sum of squared deviations from the mean (smooth.h:814-918)
-        const Q mean[3] = {(Q)acc[0], (Q)acc[1], (Q)acc[2]};
-        double s = 0;
-#pragma unroll 2
-        for (int e = 0; e < a.k; ++e) {
-            const uint32_t j = ids[e * 32];
-            const Rec4<T> pj = load_rec(a.pos4 + j);
-            const T dx = image_delta<T, PERIODIC>(qx, pj.a, L, half), dy = image_delta<T, PERIODIC>(qy, pj.b, L, half),
-                    dz = image_delta<T, PERIODIC>(qz, pj.c, L, half);
-            const T d2 = Ex<T>::add(Ex<T>::add(Ex<T>::mul(dx, dx), Ex<T>::mul(dy, dy)), Ex<T>::mul(dz, dz));
-            if (!(d2 <= ball2)) continue;
-            const Rec4<double> qj = load_rec(a.qty4 + j);
-            T w = (T)kern_w(a.kernel_id, a.wendland_self, d2 * ih2);
-            w *= norm;
-            const double wm = (double)w * qj.a;
-            Q tq = mean[0] - (Q)qj.b;
-            s += (double)(Q)(wm * (double)tq * (double)tq);
-            if (OT::qcols > 1) {
-                tq = mean[1] - (Q)qj.c;
-                s += (double)(Q)(wm * (double)tq * (double)tq);
-                tq = mean[2] - (Q)qj.d;
-                s += (double)(Q)(wm * (double)tq * (double)tq);
-            }
-        }
-        reinterpret_cast<Q *>(a.out_t)[p] = (Q)sqrt(s);                  // smooth.h:866, :917
+        mean[0] = (Q)acc[0]; mean[1] = (Q)acc[1]; mean[2] = (Q)acc[2];
+        acc[0] = acc[1] = acc[2] = 0;
+        gl_sweep<T, Q, OP, PERIODIC, 1>(a, ids, (uint32_t)p, qx, qy, qz, L, half, ball2, ih2, norm, own, mean, acc);
+        reinterpret_cast<Q *>(a.out_t)[p] = (Q)sqrt(acc[0]);            // smooth.h:866, :917
         return;
     }
     if (OP == GL_RHO) {

@@ -21,8 +21,9 @@
 //              carry inverted (+inf,-inf) bounds so no search ever opens them.
 //   REFERENCE  (only for KDTree.serialize(), export.cu) the reference's shape: inclusive range [lo,hi]
 //              split at m=(lo+hi)/2 (kd.cpp:176-199), leaf count from kdCountNodes (kd.cpp:98-111).
-// Unlike the reference (kd.cpp:168-174, split axis from the *inherited* box) the split axis is taken
-// from the tight box; neighbour sets do not depend on tree shape.
+// The device tree takes its split axis from the node's TIGHT box; the reference-shaped tree takes it, like the
+// reference (kd.cpp:165-174), from the box the node INHERITED from its parent, so that iDim / fSplit / bounds /
+// ranges of the exported KDNode records equal the reference's own.  Neighbour sets do not depend on tree shape.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -105,10 +106,14 @@ template <> __device__ inline float pos_inf<float>() { return __int_as_float(0x7
 template <> __device__ inline double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000ll); }
 
 // one thread per node of `level`: tight bounds from the list ends, split axis, split value
+// `ibox` (reference-shaped tree only): the box every node INHERITS from its parent -- the parent's inherited box
+// clipped at the parent's split value, the root's being the bounds of all particles -- which is what the reference
+// picks its split axis from (kd.cpp:165-174, 182-190); the tight bounds are what it stores afterwards (kdUpPass,
+// kd.cpp:68-96).
 template <typename T>
 __global__ void k_node_bounds(TreeShape s, int level, const uint32_t *__restrict__ L, const T *__restrict__ c,
                               T *__restrict__ box, int8_t *__restrict__ dim_out, T *__restrict__ split_out, bool leaf,
-                              int32_t *__restrict__ bucket_start)
+                              int32_t *__restrict__ bucket_start, T *__restrict__ ibox)
 {
     const int64_t n = s.n;
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -136,6 +141,20 @@ __global__ void k_node_bounds(TreeShape s, int level, const uint32_t *__restrict
     b[0] = mn[0]; b[1] = mn[1]; b[2] = mn[2]; b[3] = mx[0]; b[4] = mx[1]; b[5] = mx[2];
     if (leaf) return;
     int d = 0;
+    if (ibox) {
+        T *ib = ibox + node * 6;
+        if (level == 0) { ib[0] = mn[0]; ib[1] = mn[1]; ib[2] = mn[2]; ib[3] = mx[0]; ib[4] = mx[1]; ib[5] = mx[2]; }
+        for (int e = 1; e < 3; ++e)                                   // extents in double, as KDNode::bnd holds them
+            if ((double)ib[3 + e] - (double)ib[e] > (double)ib[3 + d] - (double)ib[d]) d = e;
+        const T sp = c[d * n + L[d * n + split_rank(s, level, lo, hi)]];
+        T *lc = ibox + 2 * node * 6, *uc = lc + 6;
+        for (int e = 0; e < 6; ++e) { lc[e] = ib[e]; uc[e] = ib[e]; }
+        lc[3 + d] = sp;                                                // kd.cpp:182-190
+        uc[d] = sp;
+        dim_out[node] = (int8_t)d;
+        split_out[node] = sp;
+        return;
+    }
     for (int e = 1; e < 3; ++e)
         if (mx[e] - mn[e] > mx[d] - mn[d]) d = e;
     dim_out[node] = (int8_t)d;
@@ -226,9 +245,11 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     }
 
     t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
-    if (!(shape.packed && want_soa && g_opt_tree_build != 2)) t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
+    if (!(shape.packed && want_soa && g_opt_tree_build == 1)) t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
     DevBuf dim(sizeof(int8_t) * 2 * t.nsplit), split(sizeof(T) * 2 * t.nsplit);
     DevBuf side(sizeof(uint8_t) * n), S(sizeof(uint32_t) * 3 * n);
+    DevBuf inherited;                                  // reference-shaped tree: split axis from the inherited boxes
+    if (!shape.packed) inherited.alloc(sizeof(T) * 6 * 2 * t.nsplit);
     PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2 * t.nsplit, s));
 
     uint32_t *L = La.as<uint32_t>(), *Ln = Lb.as<uint32_t>();
@@ -243,12 +264,12 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     // The packed device tree finishes its lowest levels per sub-tree in shared memory (tree_morton.cu: exact
     // medians by an in-CTA sort, tight bounds, tree-ordered structure of arrays) instead of one global pass +
     // prefix sum per level; the reference-shaped tree (export) runs every level here.
-    const int lseg = (shape.packed && want_soa && g_opt_tree_build != 2) ? std::min(levels, segment_levels(t.dtype)) : 0;
+    const int lseg = (shape.packed && want_soa && g_opt_tree_build == 1) ? std::min(levels, segment_levels(t.dtype)) : 0;
     const int global_levels = levels - lseg;
     for (int level = 0; level < global_levels; ++level) {
         int64_t nn = (int64_t)1 << level;
         PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
-                   dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr);
+                   dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr, inherited.as<T>());
         PNB_LAUNCH(k_mark_sides, nblk(n, BS), BS, 0, s, shape, level, L, dim.as<int8_t>(), side.as<uint8_t>());
         LeftFlag f{L, side.as<uint8_t>()};
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
@@ -261,7 +282,7 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         build_tree_segments(t, c.p, mass, L, lseg);
     } else {
         PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
-                   dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>());
+                   dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>(), (T *)nullptr);
         t.order.alloc(sizeof(uint32_t) * n);
         PNB_CUDA(cudaMemcpyAsync(t.order.p, L, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
         if (want_soa) {                                    // tree-ordered structure of arrays

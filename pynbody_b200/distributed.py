@@ -110,8 +110,34 @@ class GpuLocalTree:
 
 
 class GpuBackend:
+    native_routing = True      # owner assignment and send-buffer packing by the library's kernels (csrc/route.cu)
+
     def make_tree(self, pos, mass, boxsize):
         return GpuLocalTree(pos, mass, boxsize)
+
+    def route(self, pos, mass, domains, world):
+        """(packed [n][4] rows {x,y,z,m} destination-major and stable, original index of every row, rows per
+        destination) -- pnb_route_plan + pnb_route_pack."""
+        from . import _lib
+        L = _lib.lib()
+        n = int(pos.shape[0])
+        es = pos.element_size()
+        code = _lib.dtype_code(pos)
+        splits = domains.splits or []
+        axis = np.array([sp[0] for sp in splits], np.int32)
+        plane = np.array([sp[1] for sp in splits], np.float64)
+        child = np.array([[sp[2], sp[3]] for sp in splits], np.int32).reshape(-1)
+        owner = torch.empty(n, dtype=torch.uint8, device=pos.device)
+        counts = np.zeros(world, np.int64)
+        _lib.check(L.pnb_route_plan(pos.data_ptr(), pos.stride(0) * es, pos.stride(1) * es, n, code,
+                                    axis.ctypes.data, plane.ctypes.data, child.ctypes.data, len(splits), world,
+                                    owner.data_ptr(), counts.ctypes.data))
+        packed = torch.empty((n, 4), dtype=pos.dtype, device=pos.device)
+        src = torch.empty(n, dtype=torch.int64, device=pos.device)
+        m = mass.to(pos.dtype)
+        _lib.check(L.pnb_route_pack(pos.data_ptr(), pos.stride(0) * es, pos.stride(1) * es, m.data_ptr(), m.stride(0) * es,
+                                    n, code, owner.data_ptr(), world, packed.data_ptr(), src.data_ptr()))
+        return packed, src, [int(c) for c in counts]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -293,6 +319,18 @@ def _alltoallv(per_dest, group=None):
     return list(recv.split(rc))
 
 
+def _alltoall_rows(send, counts, group=None):
+    """The same for rows that already lie destination-major in one tensor: (received rows, rows per source)."""
+    dev = send.device
+    sc = torch.tensor(counts, dtype=torch.int64, device=dev)
+    rcounts = torch.empty_like(sc)
+    dist.all_to_all_single(rcounts, sc, group=group)
+    rc = rcounts.tolist()
+    recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=list(counts), group=group)
+    return recv, rc
+
+
 def reduce_image(img, dst=0, group=None):
     """Sum the per-rank partial frames (each rank rendered its own particles) onto rank `dst`."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -336,7 +374,15 @@ class DistributedKDTree:
         self._tick("decompose")
         self.boxsize = float(boxsize) if periodic else None
         self.requested_boxsize = boxsize
-        if self.world > 1:
+        if self.world > 1 and pos.is_cuda and getattr(self.backend, "native_routing", False) and self.world <= 256 \
+                and getattr(self.domains, "splits", None) is not None:
+            # positions and masses travel together as [n][4] rows, packed destination-major by the library
+            packed, src_idx, counts = self.backend.route(pos, mass, self.domains, self.world)
+            self._ret_counts = counts                               # what I sent to each rank (returns come back so)
+            self._ret_index = src_idx                               # original local index of each sent particle
+            recv, self._own_counts = _alltoall_rows(packed, counts, group)   # owned particles grouped by source rank
+            self.pos, self.mass = recv[:, :3].contiguous(), recv[:, 3].contiguous()
+        elif self.world > 1:
             owner = owner_of(pos, self.domains)
             # one-byte keys: the stable radix sort needs a single pass instead of eight
             key = owner.to(torch.uint8) if self.world <= 255 else owner

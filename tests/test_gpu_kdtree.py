@@ -110,7 +110,7 @@ def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype
     try:
         kd = _tree(pos, mass, boxsize)
     finally:
-        kdmain.set_option("tree_build", 1)
+        kdmain.set_option("tree_build", 2)
     L = _lib.lib()
     h = kd.kdtree.handle
     nb = L.pnb_tree_num_buckets(h)
@@ -132,6 +132,33 @@ def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype
     k = min(32, n)
     sm = _smooth(kd, pos, k)
     assert np.array_equal(sm, oracle.OracleKDTree(pos, mass, 16, boxsize, None, 0).smooth(k))
+
+
+@pytest.mark.parametrize("n,leafsize,dtype", [(100_000, 16, np.float64), (65_537, 16, np.float32), (5000, 32, np.float64),
+                                              (777, 8, np.float32), (40, 64, np.float64), (200_000, 1, np.float64)])
+def test_kdnodes_equal_the_reference_tree(n, leafsize, dtype):
+    """KDTree.kdnodes / particle_offsets against the compiled reference's own build (kd.cpp:113-238): split axis from
+    the inherited box, fSplit = coordinate of the median-rank particle, tight bounds from the up-pass, inclusive
+    [pLower, pUpper] ranges -- record for record; particle offsets as sets per leaf (quickselect leaves the order
+    inside a leaf unspecified, kd.cpp:31-66)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref (compiled reference) not built")
+    pos, vel, mass = synth.clumpy_box(n, 17 + leafsize, dtype)
+    want = ref.RefKDTree(pos, mass, leafsize, None, 4)
+    kd = _tree(pos, mass, None, leafsize=leafsize)
+    got_nodes, got_off = kd.kdnodes, kd.particle_offsets
+    assert got_nodes.shape == want.kdnodes.shape and got_nodes.dtype.itemsize == 80
+    w, g = want.kdnodes[1:], got_nodes[1:]
+    for field in ("iDim", "pLower", "pUpper", "fSplit"):
+        assert np.array_equal(g[field], w[field]), field
+    assert np.array_equal(g["bnd"]["fMin"], w["bnd"]["fMin"]) and np.array_equal(g["bnd"]["fMax"], w["bnd"]["fMax"])
+    leaves = np.flatnonzero(want.kdnodes["iDim"] == -1)
+    leaves = leaves[leaves >= 1]
+    for node in leaves[:: max(1, len(leaves) // 500)]:
+        lo, hi = int(want.kdnodes["pLower"][node]), int(want.kdnodes["pUpper"][node])
+        assert set(got_off[lo:hi + 1]) == set(want.particle_offsets[lo:hi + 1]), node
+    assert np.array_equal(np.sort(got_off), np.arange(n))
 
 
 @pytest.mark.parametrize("n,leafsize,dtype", [(5000, 16, np.float64), (5000, 32, np.float32), (777, 8, np.float64),
