@@ -81,6 +81,12 @@ int pnb_device_count(void);
  *                      every level by global passes over three per-axis sorted lists; 1: the same with the lowest levels
  *                      built per sub-tree in shared memory; 0: one Morton-key sort for the upper levels + shared-memory
  *                      kd levels (cheapest build, slower searches).  (env PNB_TREE_BUILD)
+ *   "streams"          1 (default): every host thread that calls the library works on its own non-blocking CUDA stream
+ *                      (ordered after whatever the caller had enqueued on the default stream when the call was made,
+ *                      drained before the call returns), so calls from two threads overlap on the device;
+ *                      0: everything on the default stream.  (env PNB_STREAMS)
+ *   "knn_blocks_per_sm" > 0 caps the resident blocks per SM of the (persistent) neighbour-search kernel so that kernels
+ *                      launched from another thread find room beside it; 0 (default): as many as fit.
  * PNB_ERR_VALUE for an unknown name. */
 int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */
@@ -144,6 +150,17 @@ int pnb_populate(pnb_tree *t, int propid, int k, int kernel_id, double period, i
  * pnb_mark_in_balls: flags_out[i] (FILE order, n bytes) = 1 iff particle i lies within radii[q] of
  * centres[q] (periodic) for any q < nq: the halo particles another rank's boundary queries need. */
 int pnb_set_query_mask(pnb_tree *t, const uint8_t *mask, int mem);
+/* The same with two switches for searches done in several passes over complementary subsets: `invert` selects the
+ * particles whose mask byte is ZERO; `keep_results` leaves the resident results of earlier passes (smoothing
+ * lengths, fused densities, neighbour lists) marked valid -- the caller vouches that the passes together cover
+ * every particle it later asks about.  mask == NULL removes the restriction. */
+int pnb_set_query_mask2(pnb_tree *t, const uint8_t *mask, int mem, int invert, int keep_results);
+/* pnb_mark_near_faces: flags_out[i] (FILE order, n bytes) = 1 iff the k-neighbour ball of particle i MIGHT reach a
+ * face of the cuboid [lo3, hi3) (+-inf = no face): the smallest ancestor of its bucket holding >= k particles bounds
+ * the ball radius by its diagonal; a bucket further than that from every face cannot.  Particles flagged 0 are
+ * guaranteed to find all their k neighbours inside the cuboid -- the interior of a rank's domain, searched while the
+ * halo exchange for the flagged ones is under way. */
+int pnb_mark_near_faces(pnb_tree *t, int k, const double *lo3, const double *hi3, uint8_t *flags_out, int mem);
 int pnb_mark_in_balls(pnb_tree *t, const void *centres, int64_t stride0, int64_t stride1,
                       const void *radii, int64_t rstride, int64_t nq, double period,
                       uint8_t *flags_out, int mem);

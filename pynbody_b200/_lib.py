@@ -55,6 +55,8 @@ SIGNATURES = {
     "pnb_tree_node_bounds": (_i32, [_vp, _vp]),
     "pnb_set_array": (_i32, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _i32]),
     "pnb_set_query_mask": (_i32, [_vp, _vp, _i32]),
+    "pnb_set_query_mask2": (_i32, [_vp, _vp, _i32, _i32, _i32]),
+    "pnb_mark_near_faces": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32]),
     "pnb_mark_in_balls": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _vp, _i32]),
     "pnb_route_plan": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "pnb_route_pack": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),

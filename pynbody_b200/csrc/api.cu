@@ -153,6 +153,38 @@ void cache_trim()
     c.trim_locked();
 }
 
+// ---- streams ---------------------------------------------------------------------------------------
+int g_opt_knn_blocks_per_sm = 0;    // pnb_set_option("knn_blocks_per_sm"): > 0 caps the resident blocks per SM of the search kernel
+int g_opt_streams = 1;              // pnb_set_option("streams"): 1 = one non-blocking stream per calling thread, 0 = default stream
+cudaStream_t lib_stream()
+{
+    if (!g_opt_streams) return nullptr;
+    static thread_local cudaStream_t mine[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaStream_t &s = mine[dev & 63];
+    if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); s = nullptr; }
+    return s;
+}
+ApiScope::ApiScope()
+{
+    cudaStream_t s = lib_stream();
+    if (!s) return;
+    static thread_local cudaEvent_t ev[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEvent_t &e = ev[dev & 63];
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); e = nullptr; return; }
+    // everything the caller enqueued on the default stream so far (torch's tensors) precedes our work
+    if (cudaEventRecord(e, cudaStreamLegacy) == cudaSuccess) cudaStreamWaitEvent(s, e, 0);
+    cudaGetLastError();
+}
+ApiScope::~ApiScope()
+{
+    cudaStream_t s = lib_stream();
+    if (s) { cudaStreamSynchronize(s); cudaGetLastError(); }
+}
+
 // a second, non-blocking stream per device for copies that run beside the work on the library's stream
 static cudaStream_t copy_stream()
 {
@@ -197,7 +229,14 @@ template <typename F>
 static int guarded(F &&f)
 {
     try {
-        f();
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+            ApiScope scope;
+            f();
+        } else {
+            cudaGetLastError();
+            f();
+        }
         return PNB_OK;
     } catch (const Error &e) {
         set_last_error(e.what());
@@ -312,6 +351,7 @@ static struct OptionsFromEnv {
         if (const char *e = getenv("PNB_NEIGHBOUR_LISTS")) g_opt_neighbour_lists = atoi(e);
         if (const char *e = getenv("PNB_GATHER_WALK")) g_opt_gather_walk = atoi(e);
         if (const char *e = getenv("PNB_TREE_BUILD")) g_opt_tree_build = atoi(e);
+        if (const char *e = getenv("PNB_STREAMS")) g_opt_streams = atoi(e);
     }
 } g_options_from_env;
 
@@ -491,6 +531,34 @@ static void knn_rows(Tree &t, int64_t first, int64_t count, int64_t *idx_out, vo
     }
 }
 
+// one thread per bucket: could the k-neighbour ball of any of its particles reach a face of the cuboid [lo, hi)?
+// The smallest ancestor of the bucket that holds >= k particles contains the query and k particles, so the ball
+// radius is at most that ancestor's diagonal; a bucket further than that from every face is safely interior.
+template <typename T>
+__global__ void k_near_faces(int64_t nsplit, int levels, int k, const int32_t *__restrict__ bucket_start,
+                             const T *__restrict__ box, double lx, double ly, double lz, double hx, double hy, double hz,
+                             uint8_t *__restrict__ flags_tree)
+{
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= nsplit) return;
+    const int start = bucket_start[b], cnt = bucket_start[b + 1] - start;
+    if (cnt <= 0) return;
+    int j = 0;
+    for (; j < levels; ++j) {
+        const int64_t a = b >> j;
+        const int64_t first = a << j, last = min(nsplit, (a + 1) << j);
+        if (bucket_start[last] - bucket_start[first] >= k) break;
+    }
+    const T *ab = box + ((nsplit + b) >> j) * 6;
+    const double dx = (double)ab[3] - (double)ab[0], dy = (double)ab[4] - (double)ab[1], dz = (double)ab[5] - (double)ab[2];
+    const double reach = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 + 1e-6);
+    const T *bb = box + (nsplit + b) * 6;
+    const double gap = fmin(fmin(fmin((double)bb[0] - lx, hx - (double)bb[3]), fmin((double)bb[1] - ly, hy - (double)bb[4])),
+                            fmin((double)bb[2] - lz, hz - (double)bb[5]));
+    const uint8_t near = !(gap >= reach) ? 1 : 0;          // (also set when the whole tree holds fewer than k particles)
+    for (int i = 0; i < cnt; ++i) flags_tree[start + i] = near;
+}
+
 }  // namespace pnb
 
 using namespace pnb;
@@ -514,6 +582,8 @@ int pnb_set_option(const char *name, int value)
         if (!strcmp(name, "neighbour_lists")) g_opt_neighbour_lists = value;
         else if (!strcmp(name, "gather_walk")) g_opt_gather_walk = value;
         else if (!strcmp(name, "tree_build")) g_opt_tree_build = value;
+        else if (!strcmp(name, "streams")) g_opt_streams = value;
+        else if (!strcmp(name, "knn_blocks_per_sm")) g_opt_knn_blocks_per_sm = value;
         else throw Error(PNB_ERR_VALUE, std::string("unknown option ") + name);
     });
 }
@@ -595,6 +665,7 @@ int pnb_tree_order(pnb_tree *h, int64_t *out)
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
         std::vector<uint32_t> o((size_t)t->n);
+        PNB_CUDA(cudaStreamSynchronize(t->stream));
         PNB_CUDA(cudaMemcpy(o.data(), t->order.p, sizeof(uint32_t) * (size_t)t->n, cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i < t->n; ++i) out[i] = (int64_t)o[(size_t)i];
     });
@@ -677,10 +748,10 @@ int pnb_set_array(pnb_tree *h, int id, void *ptr, int64_t stride0, int64_t strid
     });
 }
 
-__global__ void k_u8_to_tree(const uint32_t *order, const uint8_t *in_file, uint8_t *out_tree, int64_t n)
+__global__ void k_u8_to_tree(const uint32_t *order, const uint8_t *in_file, uint8_t *out_tree, int64_t n, int invert)
 {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p < n) out_tree[p] = in_file[order[p]] ? 1 : 0;
+    if (p < n) out_tree[p] = ((in_file[order[p]] != 0) != (invert != 0)) ? 1 : 0;
 }
 __global__ void k_u8_to_file(const uint32_t *order, const uint8_t *in_tree, uint8_t *out_file, int64_t n)
 {
@@ -688,31 +759,42 @@ __global__ void k_u8_to_file(const uint32_t *order, const uint8_t *in_tree, uint
     if (p < n) out_file[order[p]] = in_tree[p];
 }
 
+static void set_query_mask(Tree *t, const uint8_t *mask, int mem, int invert, int keep_results)
+{
+    if (!keep_results) { t->smooth_valid = false; t->rho_valid = false; t->nn_valid = false; }
+    if (!mask) {
+        t->query_mask.release();
+        return;
+    }
+    require_device();
+    DevBuf file_mask;
+    const uint8_t *src = mask;
+    if (mem == PNB_HOST) {
+        file_mask.alloc((size_t)t->n);
+        PNB_CUDA(cudaMemcpyAsync(file_mask.p, mask, (size_t)t->n, cudaMemcpyHostToDevice, t->stream));
+        src = file_mask.as<uint8_t>();
+    }
+    if (!t->query_mask.p) t->query_mask.alloc((size_t)t->n);
+    PNB_LAUNCH(k_u8_to_tree, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(), src,
+               t->query_mask.as<uint8_t>(), t->n, invert);
+    PNB_CUDA(cudaStreamSynchronize(t->stream));
+}
+
 int pnb_set_query_mask(pnb_tree *h, const uint8_t *mask, int mem)
 {
     PNB_NEED_TREE(h);
     Tree *t = reinterpret_cast<Tree *>(h);
     return guarded([&] {
-        if (!mask) {
-            if (t->query_mask.p) { t->query_mask.release(); t->smooth_valid = false; t->rho_valid = false; t->nn_valid = false; }
-            return;
-        }
-        t->smooth_valid = false;
-        t->rho_valid = false;
-        t->nn_valid = false;
-        require_device();
-        DevBuf file_mask;
-        const uint8_t *src = mask;
-        if (mem == PNB_HOST) {
-            file_mask.alloc((size_t)t->n);
-            PNB_CUDA(cudaMemcpyAsync(file_mask.p, mask, (size_t)t->n, cudaMemcpyHostToDevice, t->stream));
-            src = file_mask.as<uint8_t>();
-        }
-        t->query_mask.alloc((size_t)t->n);
-        PNB_LAUNCH(k_u8_to_tree, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(), src,
-                   t->query_mask.as<uint8_t>(), t->n);
-        PNB_CUDA(cudaStreamSynchronize(t->stream));
+        if (!mask && !t->query_mask.p) return;           // nothing changes: results stay valid
+        set_query_mask(t, mask, mem, 0, 0);
     });
+}
+
+int pnb_set_query_mask2(pnb_tree *h, const uint8_t *mask, int mem, int invert, int keep_results)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] { set_query_mask(t, mask, mem, invert, keep_results); });
 }
 
 int pnb_mark_in_balls(pnb_tree *h, const void *centres, int64_t stride0, int64_t stride1, const void *radii,
@@ -735,6 +817,32 @@ int pnb_mark_in_balls(pnb_tree *h, const void *centres, int64_t stride0, int64_t
             run_mark_in_balls(*t, c.p, r.p, nq, period, flags_tree.as<uint8_t>());
             PNB_CUDA(cudaStreamSynchronize(t->stream));
         }
+        uint8_t *dst = mem == PNB_DEVICE ? flags_out : flags_file.as<uint8_t>();
+        PNB_LAUNCH(k_u8_to_file, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(),
+                   flags_tree.as<uint8_t>(), dst, t->n);
+        if (mem != PNB_DEVICE)
+            PNB_CUDA(cudaMemcpyAsync(flags_out, flags_file.p, (size_t)t->n, cudaMemcpyDeviceToHost, t->stream));
+        PNB_CUDA(cudaStreamSynchronize(t->stream));
+    });
+}
+
+int pnb_mark_near_faces(pnb_tree *h, int k, const double *lo3, const double *hi3, uint8_t *flags_out, int mem)
+{
+    PNB_NEED_TREE(h);
+    Tree *t = reinterpret_cast<Tree *>(h);
+    return guarded([&] {
+        require_device();
+        if (!lo3 || !hi3 || !flags_out) throw Error(PNB_ERR_VALUE, "pointer is null");
+        if (k < 1) throw Error(PNB_ERR_VALUE, "Number of smoothing particles must be positive");
+        DevBuf flags_tree((size_t)t->n), flags_file((size_t)t->n);
+        PNB_CUDA(cudaMemsetAsync(flags_tree.p, 0, (size_t)t->n, t->stream));
+        const unsigned grid = (unsigned)((t->nsplit + 127) / 128);
+        if (t->dtype == PNB_F64)
+            PNB_LAUNCH((k_near_faces<double>), grid, 128, 0, t->stream, t->nsplit, t->levels, k, t->bucket_start.as<int32_t>(),
+                       t->box.as<double>(), lo3[0], lo3[1], lo3[2], hi3[0], hi3[1], hi3[2], flags_tree.as<uint8_t>());
+        else
+            PNB_LAUNCH((k_near_faces<float>), grid, 128, 0, t->stream, t->nsplit, t->levels, k, t->bucket_start.as<int32_t>(),
+                       t->box.as<float>(), lo3[0], lo3[1], lo3[2], hi3[0], hi3[1], hi3[2], flags_tree.as<uint8_t>());
         uint8_t *dst = mem == PNB_DEVICE ? flags_out : flags_file.as<uint8_t>();
         PNB_LAUNCH(k_u8_to_file, (unsigned)((t->n + 255) / 256), 256, 0, t->stream, t->order.as<uint32_t>(),
                    flags_tree.as<uint8_t>(), dst, t->n);

@@ -39,13 +39,34 @@ extern thread_local int64_t g_launches;
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
+// streams
+// ------------------------------------------------------------------------------------------------
+// Every host thread that calls into the library works on its OWN non-blocking stream (one per device, created on
+// first use): two threads -- e.g. the interior neighbour search of a domain and the halo pipeline of the multi-GPU
+// layer -- run their kernels side by side, and nothing serialises behind the legacy default stream any more.
+// Ordering against the caller's work (torch tensors are produced on the default stream):
+//   * on entry, ApiScope makes the thread's stream wait for everything already enqueued on the default stream;
+//   * on exit it drains the thread's stream, so outputs are complete when the call returns.
+// pnb_set_option("streams", 0) / PNB_STREAMS=0 goes back to the default stream.
+cudaStream_t lib_stream();
+struct ApiScope {
+    ApiScope();
+    ~ApiScope();
+};
+// converts to the calling thread's stream wherever a cudaStream_t is expected (Tree::stream)
+struct StreamRef {
+    operator cudaStream_t() const { return lib_stream(); }
+};
+
+// ------------------------------------------------------------------------------------------------
 // device buffer with RAII (stream-ordered allocator)
 // ------------------------------------------------------------------------------------------------
 // Device memory comes from a small caching allocator (api.cu): blocks are cudaMalloc'ed once, kept
 // on per-size free lists when released and handed out again to the next request of the same size.
-// All library work is issued on one stream, so re-use in stream order is safe without
-// synchronisation; a steady-state step performs no driver allocation at all (cudaMalloc/cudaFree
-// synchronise the device and were measured to stall for hundreds of ms).
+// A block goes back to the cache only when the stream that used it has been drained (every entry point ends
+// with ApiScope's drain, and scratch buffers released mid-call are preceded by an explicit synchronisation), so
+// the next user -- on whatever thread or stream -- finds it idle.  A steady-state step performs no driver
+// allocation at all (cudaMalloc/cudaFree synchronise the device and were measured to stall for hundreds of ms).
 void *cache_alloc(size_t bytes);
 void cache_free(void *p, size_t bytes);
 void cache_trim();
@@ -112,7 +133,7 @@ struct Tree {
     int user_leafsize = 16;
     int levels = 0;               // depth of the device tree: buckets live at heap level `levels`
     int64_t nsplit = 1;           // number of buckets = 1 << levels
-    cudaStream_t stream = nullptr;
+    StreamRef stream;             // the calling thread's stream (see ApiScope)
     cudaEvent_t mass_ready = nullptr;   // set while the masses are still on their way to the device (pnb_tree_create)
 
     // particles in tree order (T), structure of arrays
@@ -206,7 +227,7 @@ KernelParams make_kernel_params(int kernel_id, int k);
 void run_knn(Tree &t, int k, double period /* <=0: open */, bool fuse_rho, const KernelParams &kp,
              bool keep_ids, bool keep_d2);
 bool neighbour_lists_fit(const Tree &t, int k, bool with_d2);
-extern int g_opt_neighbour_lists, g_opt_gather_walk, g_opt_tree_build;     // pnb_set_option (api.cu)
+extern int g_opt_neighbour_lists, g_opt_gather_walk, g_opt_tree_build, g_opt_streams, g_opt_knn_blocks_per_sm;     // pnb_set_option (api.cu)
 // reductions over the resident neighbour lists (gather_list.cu); same arguments as run_gather
 void run_gather_lists(Tree &t, int propid, int k, double period, const KernelParams &kp,
                       const void *smooth_tree, const void *rho_tree, const void *qty_tree, int qdtype,

@@ -490,6 +490,9 @@ static void launch_knn_p(Tree &t, KnnArgs<T> &a)
     PNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    // a search running beside other work (multi-GPU: interior queries on one thread, halo pipeline on another) leaves
+    // part of each SM's shared memory to the kernels of the other thread
+    if (g_opt_knn_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt_knn_blocks_per_sm);
     const int64_t want = (t.nsplit + warps - 1) / warps;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);    // persistent: one resident wave
     DevBuf counter(sizeof(unsigned long long)), lo;

@@ -481,7 +481,7 @@ __global__ void k_finalize(const double *__restrict__ acc, int64_t n, float *__r
 inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 struct Work {
-    cudaStream_t s = nullptr;
+    cudaStream_t s = lib_stream();
     DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp;
     size_t scan_bytes = 0, sort_bytes = 0;
 };
@@ -592,7 +592,7 @@ void render(bool grid, int nx, int ny, int nz, const pnb_render_arrays *a, doubl
     if (!lut || n_lut < 1 || n_lut > 8192) throw Error(PNB_ERR_VALUE, "kernel table must hold 1..8192 samples");
     if (grid && h_power < 3) throw Error(PNB_ERR_VALUE, "Cannot render to 3D grid without 3-dimensional kernel or greater");
     if (!out) throw Error(PNB_ERR_VALUE, "output pointer is null");
-    cudaStream_t s = nullptr;
+    cudaStream_t s = lib_stream();
     StageTimer stage(2, s);
 
     Geom g;
@@ -903,7 +903,7 @@ void render_healpix(const pnb_render_arrays *a, int nside, const float *lut, int
         throw Error(PNB_ERR_VALUE, "A positive shell_radius is required to render a 3D (thin shell) healpix map");
     if (!lut || n_lut < 1 || n_lut > 8192) throw Error(PNB_ERR_VALUE, "kernel table must hold 1..8192 samples");
     if (!out) throw Error(PNB_ERR_VALUE, "output pointer is null");
-    cudaStream_t s = nullptr;
+    cudaStream_t s = lib_stream();
     StageTimer stage(2, s);
     const int64_t n = a->n, npix = (int64_t)12 * nside * nside;
     DevBuf acc(sizeof(double) * npix), lut_dev(sizeof(float) * n_lut);
@@ -955,6 +955,7 @@ template <typename F>
 int guarded_render(F &&f)
 {
     try {
+        ApiScope scope;
         f();
         return PNB_OK;
     } catch (const Error &e) {

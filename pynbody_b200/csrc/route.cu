@@ -166,6 +166,7 @@ template <typename F>
 int guarded_route(F &&f)
 {
     try {
+        ApiScope scope;
         f();
         return PNB_OK;
     } catch (const Error &e) {
@@ -191,7 +192,7 @@ int pnb_route_plan(const void *pos, int64_t stride0, int64_t stride1, int64_t n,
         check_route_args(pos, n, dtype, n_ranks);
         if (n_splits < 0 || n_splits > RT_MAX_SPLITS) throw Error(PNB_ERR_VALUE, "too many split planes");
         if (!owner_out || !counts_out) throw Error(PNB_ERR_VALUE, "output pointer is null");
-        cudaStream_t s = nullptr;
+        cudaStream_t s = lib_stream();
         Splits h;
         memset(&h, 0, sizeof(h));
         h.n = n_splits;
@@ -230,7 +231,7 @@ int pnb_route_pack(const void *pos, int64_t stride0, int64_t stride1, const void
         check_route_args(pos, n, dtype, n_ranks);
         if (!owner || !packed_out || !src_index_out) throw Error(PNB_ERR_VALUE, "pointer is null");
         if (n == 0) return;
-        cudaStream_t s = nullptr;
+        cudaStream_t s = lib_stream();
         const int64_t nb = (n + RT_BLOCK - 1) / RT_BLOCK;
         DevBuf hist(sizeof(uint32_t) * (size_t)nb * n_ranks), base(sizeof(uint64_t) * (size_t)nb * n_ranks);
         PNB_LAUNCH(k_route_block_hist, (unsigned)nb, RT_THREADS, 0, s, owner, n, n_ranks, hist.as<uint32_t>());

@@ -127,7 +127,7 @@ void select_region(const void *pos, int64_t n, int dtype, int mem, int region, c
     if (n < 0) throw Error(PNB_ERR_VALUE, "negative particle count");
     if (n == 0) return;
     if (!pos || !prm || !out) throw Error(PNB_ERR_VALUE, "null pointer");
-    cudaStream_t s = nullptr;
+    cudaStream_t s = lib_stream();
     StageTimer stage(3, s);
     const size_t bytes = (size_t)n * 3 * tsize(dtype);
     DevBuf staged, flags;
@@ -162,6 +162,7 @@ extern "C" int pnb_select_region(const void *pos, int64_t n, int dtype, int mem,
                                  int n_params, double wrap, uint8_t *out, int out_mem)
 {
     try {
+        ApiScope scope;
         select_region(pos, n, dtype, mem, region, params, n_params, wrap, out, out_mem);
         return PNB_OK;
     } catch (const Error &e) {

@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 import time
 
 import numpy as np
@@ -50,18 +51,31 @@ class GpuLocalTree:
         self.kd = KDTree(self.pos, self.mass, leafsize=32, boxsize=boxsize)
         self.boxsize = boxsize
 
-    def _mask(self, mask):
+    def _mask(self, mask, invert=False):
+        """Restrict the next pass to a subset.  Results of earlier passes stay valid (pnb_set_query_mask2 with
+        keep_results): this layer only ever asks a tree about particles it has searched on that tree."""
         from . import _lib
         h = self.kd.kdtree.require_built()
         if mask is None:
-            _lib.check(_lib.lib().pnb_set_query_mask(h, None, _lib.DEVICE))
+            _lib.check(_lib.lib().pnb_set_query_mask2(h, None, _lib.DEVICE, 0, 1))
         else:
             m = mask.to(torch.uint8).contiguous()
-            _lib.check(_lib.lib().pnb_set_query_mask(h, m.data_ptr(), _lib.DEVICE if m.is_cuda else _lib.HOST))
+            _lib.check(_lib.lib().pnb_set_query_mask2(h, m.data_ptr(), _lib.DEVICE if m.is_cuda else _lib.HOST,
+                                                      1 if invert else 0, 1))
 
-    def knn_smooth(self, k, mask=None, kernel_id=0):
+    def mark_near_faces(self, k, lo, hi):
+        """bool[n]: particles whose k-neighbour ball might reach a face of the cuboid [lo, hi) (pnb_mark_near_faces)."""
+        from . import _lib
+        flags = torch.zeros(self.n, dtype=torch.uint8, device=self.pos.device)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        _lib.check(_lib.lib().pnb_mark_near_faces(self.kd.kdtree.require_built(), int(k), lo.ctypes.data, hi.ctypes.data,
+                                                  flags.data_ptr(), _lib.DEVICE if flags.is_cuda else _lib.HOST))
+        return flags.bool()
+
+    def knn_smooth(self, k, mask=None, kernel_id=0, invert=False):
         self.kd._kernel_id = int(kernel_id)
-        self._mask(mask)
+        self._mask(mask, invert)
         sm = torch.empty(self.n, dtype=self.pos.dtype, device=self.pos.device)
         self.kd.set_array_ref("smooth", sm)
         self.kd.populate("hsm", k)
@@ -111,6 +125,7 @@ class GpuLocalTree:
 
 class GpuBackend:
     native_routing = True      # owner assignment and send-buffer packing by the library's kernels (csrc/route.cu)
+    two_phase = True           # near-face queries first; the interior search then overlaps the halo pipeline
 
     def make_tree(self, pos, mass, boxsize):
         return GpuLocalTree(pos, mass, boxsize)
@@ -426,6 +441,16 @@ class DistributedKDTree:
         v = values[self._ret_index]
         return torch.cat(_alltoallv(list(v.split(self._ret_counts)), self.group))
 
+    def _faces(self):
+        """(lo[3], hi[3]) of this rank's domain as numpy arrays, +-inf where there is no face (open outer faces, or a
+        periodic domain that spans the whole period along an axis)."""
+        lo, hi = (t.clone().to(torch.float64) for t in self.domains[self.rank])
+        if self.boxsize is not None:
+            full = (hi - lo) >= self.boxsize * (1 - 1e-12)
+            lo[full] = float("-inf")
+            hi[full] = float("inf")
+        return lo.numpy(), hi.numpy()
+
     def _boundary_distance(self):
         lo, hi = (t.to(self.dev) for t in self.domains[self.rank])
         d = torch.minimum(self.pos - lo, hi - self.pos)             # +inf along open / unsplit outer faces
@@ -438,8 +463,35 @@ class DistributedKDTree:
     def smooth(self, k, kernel_id=0):
         """Smoothing lengths (and, as a by-product, the halo for all later passes with this k)."""
         self._tick("idle")
-        sm = self.tree1.knn_smooth(k, None, kernel_id) if self.n_own >= k else None
-        self._tick("knn_owned")
+        worker = None
+        two_phase = (self.world > 1 and self.n_own >= k and getattr(self.backend, "two_phase", False)
+                     and not os.environ.get("PNB_DIST_SINGLE_PHASE"))
+        if two_phase:
+            # Phase A: only the particles whose ball MIGHT reach a face of the domain (a guaranteed bound from the
+            # tree, pnb_mark_near_faces).  Phase B -- everybody else, i.e. most of the domain, none of whom can need
+            # a halo -- then runs on a helper thread (its own CUDA stream) while this thread goes through the halo
+            # pipeline: boundary-query exchange, halo exchange, second tree, re-search.
+            near = self.tree1.mark_near_faces(k, *self._faces())
+            sm = self.tree1.knn_smooth(k, near, kernel_id)
+            self._tick("knn_near_faces")
+            from .kdtree import kdmain
+            kdmain.set_option("knn_blocks_per_sm", 8)            # leave room on every SM for the pipeline's kernels
+            box = {}
+
+            def interior():
+                try:
+                    if self.dev.type == "cuda":
+                        torch.cuda.set_device(self.dev)             # the current device is per thread
+                    box["sm"] = self.tree1.knn_smooth(k, near, kernel_id, invert=True)
+                except BaseException as e:  # noqa: BLE001
+                    box["error"] = e
+
+            worker = threading.Thread(target=interior)
+            worker.start()
+        else:
+            near = None
+            sm = self.tree1.knn_smooth(k, None, kernel_id) if self.n_own >= k else None
+            self._tick("knn_owned")
         self._sm_stage1 = sm
         self._share_costs()
         if self.world == 1:
@@ -453,6 +505,8 @@ class DistributedKDTree:
         else:
             r_ub = 2 * sm
         flagged = r_ub * (1 + 1e-6) >= self._boundary_distance()
+        if near is not None:
+            flagged &= near                                         # (phase A computed only these; the rest is interior)
         period = self.boxsize
         # boundary queries -> the ranks whose domain their ball touches
         fidx = torch.nonzero(flagged).squeeze(1)
@@ -497,9 +551,20 @@ class DistributedKDTree:
             self._mask2 = torch.zeros(self.tree2.n, dtype=torch.bool, device=self.dev)
             self._mask2[self._f2] = True
             sm2 = self.tree2.knn_smooth(k, self._mask2, kernel_id)
+        self._tick("knn_boundary")
+        if worker is not None:
+            worker.join()
+            from .kdtree import kdmain
+            kdmain.set_option("knn_blocks_per_sm", 0)
+            if "error" in box:
+                raise box["error"]
+            sm = box["sm"]                                          # every owned particle, searched on owned particles
+            self._sm_stage1 = sm
+            self.tree1._mask(None)
+            self._tick("wait_for_interior_knn")
+        if fidx.numel() > 0:
             sm = sm.clone()
             sm[fidx] = sm2[self._f2]
-        self._tick("knn_boundary")
         self._fidx = fidx
         self._interior = ~flagged
         self._sm_own, self._k = sm, k

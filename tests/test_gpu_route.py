@@ -20,7 +20,7 @@ def test_route_equals_stable_sort_by_owner(world, dtype, n):
     doms.splits = []
     _bisect(sample.t().contiguous(), None, torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64),
             list(range(world)), doms, doms.splits)
-    pos, mass = pos[:n], mass[:n] * np.arange(1, n + 1)
+    pos, mass = pos[:n], (mass[:n] * np.arange(1, n + 1)).astype(dtype)
     tp, tm = torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda()
     if n > 2:                                              # points exactly on a split plane go to the upper side
         axis, plane = doms.splits[0][0], doms.splits[0][1]
