@@ -367,7 +367,7 @@ class DistributedKDTree:
         if not self._profile:
             return
         if self.dev.type == "cuda":
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()     # (not the device: the interior search may be running beside us)
         now = time.perf_counter()
         self.timings[name] = self.timings.get(name, 0.0) + (now - self._t_last) * 1e3
         self._t_last = now
@@ -464,8 +464,12 @@ class DistributedKDTree:
         """Smoothing lengths (and, as a by-product, the halo for all later passes with this k)."""
         self._tick("idle")
         worker = None
+        # (opt-in, PNB_DIST_TWO_PHASE=1: measured SLOWER at 2 GPUs x 16.7 M particles -- 97 vs 89 ms per step,
+        # profiles/r2_scaling.md.  The interior search is a persistent kernel that fills every SM; the pipeline's NCCL
+        # and sort kernels do not find room beside it and wait for it, and confining it to a share of the SMs
+        # slows the pipeline's own searches by more than the overlap returns.)
         two_phase = (self.world > 1 and self.n_own >= k and getattr(self.backend, "two_phase", False)
-                     and not os.environ.get("PNB_DIST_SINGLE_PHASE"))
+                     and bool(os.environ.get("PNB_DIST_TWO_PHASE")))
         if two_phase:
             # Phase A: only the particles whose ball MIGHT reach a face of the domain (a guaranteed bound from the
             # tree, pnb_mark_near_faces).  Phase B -- everybody else, i.e. most of the domain, none of whom can need

@@ -52,10 +52,16 @@ def _worker(rank, world, port, n, k, dtype_name, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dtype", [(2, np.float64), (3, np.float32)])
-def test_distributed_device_path_equals_the_oracle(world, dtype, tmp_path):
+@pytest.mark.parametrize("world,dtype,two_phase", [(2, np.float64, False), (3, np.float32, False), (2, np.float64, True)])
+def test_distributed_device_path_equals_the_oracle(world, dtype, two_phase, tmp_path, monkeypatch):
+    """two_phase: the opt-in variant that searches near-face particles first and the interior on a helper thread
+    (its own CUDA stream) beside the halo pipeline -- multi-pass query masks, pnb_mark_near_faces, per-thread streams."""
     from oracle import oracle
     n, k = 60_000, 32
+    if two_phase:
+        monkeypatch.setenv("PNB_DIST_TWO_PHASE", "1")
+    else:
+        monkeypatch.delenv("PNB_DIST_TWO_PHASE", raising=False)
     mp.spawn(_worker, args=(world, _free_port(), n, k, np.dtype(dtype).name, str(tmp_path)), nprocs=world, join=True)
     pos, vel, mass = _particles(n, dtype)
     o = oracle.OracleKDTree(pos, mass, 16, 1.0, None, 1)
