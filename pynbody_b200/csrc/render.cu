@@ -7,24 +7,29 @@
 // On the GPU the same sums are evaluated as a tile-binned GATHER:
 //   1. footprint pass: per particle (and per periodic image) the cull tests and the inclusive-exclusive
 //      pixel rectangle [xa,xb) x [ya,yb) (x [za,zb)) are computed with the reference's double
-//      arithmetic and C integer truncation (_render.pyx:297-346, 436-480); the number of 16x16-pixel
+//      arithmetic and C integer truncation (_render.pyx:297-346, 436-480); the number of 64x32-pixel
 //      (4x8x8-voxel) tiles it overlaps is counted;
 //   2. a prefix sum and a second footprint pass emit (tile, particle) pairs, which one radix sort
 //      groups by tile;
-//   3. a record pass writes one 64-byte record per pair (position relative to the tile origin, 1/kernel
-//      support, weight, rectangle clipped to the tile) in sorted order, so that a tile's particles are
-//      contiguous;
+//   3. a record pass writes one 32-byte record per pair (float position relative to the tile origin,
+//      1/kernel support, weight, rectangle clipped to the tile) in sorted order, so that a tile's particles
+//      are contiguous;
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
-//      balance for clustered data), streams the records through shared memory with TMA bulk copies
-//      (cp.async.bulk + mbarrier, double buffered), and each of its 256 threads accumulates ONE pixel
-//      of the current tile in a register.  Pixels are flushed with one double-precision atomicAdd per
-//      (pixel, slice) -- 256 per tile switch instead of one per particle-pixel pair.
+//      balance for clustered data) and streams the records through shared memory with TMA bulk copies
+//      (cp.async.bulk + mbarrier, double buffered).  IMAGE tiles are 64 x 32 pixels: warp w owns rows
+//      4w .. 4w+3 and lane l columns l and l+32, i.e. EIGHT pixels per thread in registers -- a record's row
+//      test is warp-uniform, its column terms (dx^2 + dz^2) are formed once for the 4 rows, its row terms once
+//      for the 2 columns, and the per-record decode is paid once per 8 pixels (round 1: 32 x 16 tiles, two
+//      pixels per thread: 54 ms for the C3 image; the per-record overhead was half of the instructions).
+//      GRID tiles are 4 x 8 x 8 voxels, one per thread.  Pixels are flushed with one double-precision
+//      atomicAdd per (pixel, slice).
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
 // evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
-// coordinates (absolute error < 4e-4 of an index step) and falls back to the reference's exact double
-// expression whenever the float value lies within 2e-3 of an integer, so the selected table entry is
-// the reference's in every case.
+// coordinates (absolute error < 2e-3 of an index step for 64-pixel tiles) and falls back to the reference's
+// exact double expression -- recomputed from the particle's own arrays, the records carry no doubles --
+// whenever the float value lies within 4e-3 of an integer, so the selected table entry is the reference's in
+// every case.
 //
 // Perspective images (z_camera != 0) rescale the pixel grid per particle (_render.pyx:281-295); they go
 // through an exact per-particle scatter kernel with double atomics instead of the tile path.
@@ -39,12 +44,12 @@ namespace pnb {
 
 namespace {
 
-constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, two pixels (rows 2w and 2w + 1 of warp w) per thread
+constexpr int TILE_X = 64, TILE_Y = 32;          // image tile: 64 x 32 pixels, 8 per thread (rows 4w..4w+3 of warp w, columns l and l+32)
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
-constexpr int64_t MAX_PAIRS = (int64_t)96 << 20;  // pairs handled per sort/render batch (6 GiB of records)
-constexpr float BORDER = 2e-3f;
+constexpr int64_t MAX_PAIRS = (int64_t)192 << 20; // pairs handled per sort/render batch (6 GiB of records)
+constexpr float BORDER = 4e-3f;
 
 struct Geom {
     int nx, ny, nz, grid;
@@ -78,14 +83,13 @@ struct Images {
 };
 
 struct alignas(16) Rec {
-    double xi, yi, zd, kmax2;     // zd: image -> dz = (z - z0) * use_z ; grid -> z
     float xr, yr, zr, inv;        // tile-relative position; image: zr = dz^2; inv = ns / kmax2 (<0: exact path only)
     float wq;                     // weight / h^dim
     uint32_t box;                 // lxa | wx << 8 | lya << 16 | wy << 24   (rectangle clipped to the tile)
     uint32_t boxz;                // lza | wz << 8
     uint32_t tile;
 };
-static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
+static_assert(sizeof(Rec) == 32, "record must be 32 bytes");
 
 __device__ __forceinline__ int c_int(double v)
 {
@@ -247,15 +251,12 @@ __global__ void k_make_records(Geom g, Cols c, int64_t i0, Images im, int64_t np
     const double h = f.h;
     const float hk = (g.h_power == 2) ? (float)(h * h) : (float)(h * h * h);        // :309-312
     const double kmax2 = (h * h) * (g.max_d * g.max_d);                             // :313
-    R.xi = f.xi; R.yi = f.yi; R.kmax2 = kmax2;
     R.xr = (float)(f.xi - (g.x1 + g.pdx * px0));
     R.yr = (float)(f.yi - (g.y1 + g.pdy * py0));
     if (!g.grid) {
         const double dz = (f.zi - g.z0) * g.use_z;                                  // :314
-        R.zd = dz;
         R.zr = (float)(dz * dz);
     } else {
-        R.zd = f.zi;
         R.zr = (float)(f.zi - (g.z1 + g.pdz * pz0));
     }
     const bool single = g.max_d * h / g.pdx < 1 && g.max_d * h / g.pdy < 1;
@@ -301,25 +302,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// the reference's table lookup index (_render.pyx:186-193) in exact double arithmetic
+// the reference's table lookup index (_render.pyx:186-193) in exact double arithmetic, from the particle's own
+// arrays (taken by the few pixel evaluations whose float index lies next to a bin edge, and by sub-pixel kernels)
+struct ExactCtx {            // what the exact path reads; lives in global memory so that the render kernel does not
+    Geom g;                  // have to spill its parameters to the stack to pass them on
+    Cols c;
+    Images im;
+    int64_t i0;
+};
 template <bool GRID>
-__device__ __forceinline__ unsigned exact_index(const Geom &g, const Rec &R, int px, int py, int pz)
+__device__ __noinline__ unsigned exact_index(const ExactCtx *__restrict__ ctx, uint32_t payload, int px, int py, int pz)
 {
-    const double ddx = R.xi - (g.pdx * (double)px + g.xs);
-    const double ddy = R.yi - (g.pdy * (double)py + g.ys);
+    const Geom &g = ctx->g;
+    const Cols &c = ctx->c;
+    const Images &im = ctx->im;
+    const int64_t i0 = ctx->i0;
+    const int img = (int)(payload >> IMAGE_SHIFT);
+    const int64_t i = i0 + (payload & ((1u << IMAGE_SHIFT) - 1u));
+    const double xi = ld_pos(c.x, c.pos_f64, i, im.ox[img]), yi = ld_pos(c.y, c.pos_f64, i, im.oy[img]);
+    const double zi = ld_pos(c.z, c.pos_f64, i, GRID ? im.oz[img] : 0.0f);
+    double h = c.h[i];
+    if (!GRID && h < g.min_smooth) h = g.min_smooth;                                // :297
+    const double kmax2 = (h * h) * (g.max_d * g.max_d);                             // :313
+    const double ddx = xi - (g.pdx * (double)px + g.xs);
+    const double ddy = yi - (g.pdy * (double)py + g.ys);
     double d2;
     if (GRID) {
-        const double ddz = R.zd - (g.pdz * (double)pz + g.zs);
+        const double ddz = zi - (g.pdz * (double)pz + g.zs);
         d2 = ddx * ddx + ddy * ddy + ddz * ddz;
     } else {
-        d2 = ddx * ddx + ddy * ddy + R.zd * R.zd;
+        const double dz = (zi - g.z0) * g.use_z;                                    // :314
+        d2 = ddx * ddx + ddy * ddy + dz * dz;
     }
-    const double t = g.ns * (d2 / R.kmax2);
+    const double t = g.ns * (d2 / kmax2);
     return (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ recs, int64_t npairs, Geom g,
+__global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ recs, const uint32_t *__restrict__ payloads,
+                                                      int64_t npairs, Geom g, const ExactCtx *__restrict__ ctx,
                                                       const float *__restrict__ lut, double *__restrict__ acc)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -338,50 +359,58 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int c) {
-        const int64_t b = first + (int64_t)c * CHUNK;
+    auto issue = [&](int ch) {
+        const int64_t b = first + (int64_t)ch * CHUNK;
         const uint32_t bytes = (uint32_t)(min((int64_t)CHUNK, last - b) * sizeof(Rec));
-        mbar_expect_tx(&bar[c & 1], bytes);
-        tma_load_bulk(buf + (c & 1) * CHUNK, recs + b, bytes, &bar[c & 1]);
+        mbar_expect_tx(&bar[ch & 1], bytes);
+        tma_load_bulk(buf + (ch & 1) * CHUNK, recs + b, bytes, &bar[ch & 1]);
     };
     if (tid == 0) issue(0);
 
-    // Image tiles are 32 x 16 pixels: a warp is one row of 32 pixels (lane = x) and takes rows 2w and 2w + 1, so the
-    // row test of a record's rectangle is warp-uniform -- rows outside cost the warp three instructions instead of
-    // idling its lanes through the pixel arithmetic.  Grid tiles are 4 x 8 x 8 voxels, one per thread.
-    constexpr int NPIX = GRID ? 1 : 2;
+    // pixels of this thread inside a tile.  Image: rows NR*w .. NR*w+NR-1 of warp w (a record's row test is
+    // warp-uniform), columns lane and lane + 32.  Grid: one voxel of the 4 x 8 x 8 tile.
+    constexpr int NR = GRID ? 1 : 4, NCOL = GRID ? 1 : 2;
     int lx, ly, lz = 0;
     if (GRID) { lz = tid & (GTZ - 1); ly = (tid >> 3) & (GTY - 1); lx = tid >> 6; }
-    else { lx = tid & 31; ly = tid >> 5; }
-    const float cx = (float)(g.pdx * (lx + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
-    float cy[NPIX];
+    else { lx = tid & 31; ly = (tid >> 5) * NR; }
+    float cxs[NCOL], cys[NR];
 #pragma unroll
-    for (int q = 0; q < NPIX; ++q) cy[q] = (float)(g.pdy * (NPIX * ly + q + 0.5));
+    for (int j = 0; j < NCOL; ++j) cxs[j] = (float)(g.pdx * (lx + 32 * j + 0.5));
+#pragma unroll
+    for (int q = 0; q < NR; ++q) cys[q] = (float)(g.pdy * (ly + q + 0.5));
+    const float cz = (float)(g.pdz * (lz + 0.5));
     const float nsf = (float)g.ns;
+    const unsigned ns = (unsigned)g.ns;
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
-    float a[NPIX];
+    float a[NR][NCOL];
 #pragma unroll
-    for (int q = 0; q < NPIX; ++q) a[q] = 0.0f;
+    for (int q = 0; q < NR; ++q)
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) a[q][j] = 0.0f;
     uint32_t cur = 0xffffffffu;
     int px = 0, py = 0, pz = 0;                        // first pixel of this thread in the current tile
     auto flush = [&]() {
 #pragma unroll
-        for (int q = 0; q < NPIX; ++q) {
-            if (a[q] != 0.0f) {
-                const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)(py + q) * g.nx + px;
-                atomicAdd(&acc[pix], (double)a[q]);
+        for (int q = 0; q < NR; ++q)
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                if (a[q][j] != 0.0f) {
+                    const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz
+                                             : (int64_t)(py + q) * g.nx + (px + 32 * j);
+                    atomicAdd(&acc[pix], (double)a[q][j]);
+                }
+                a[q][j] = 0.0f;
             }
-            a[q] = 0.0f;
-        }
     };
 
-    for (int c = 0; c < nchunks; ++c) {
-        if (tid == 0 && c + 1 < nchunks) issue(c + 1);       // buffer (c+1)&1 was released by the barrier below
-        mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
-        const Rec *chunk = buf + (c & 1) * CHUNK;
-        const int cnt = (int)min((int64_t)CHUNK, last - (first + (int64_t)c * CHUNK));
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (tid == 0 && ch + 1 < nchunks) issue(ch + 1);      // buffer (ch+1)&1 was released by the barrier below
+        mbar_wait(&bar[ch & 1], (uint32_t)((ch >> 1) & 1));
+        const Rec *chunk = buf + (ch & 1) * CHUNK;
+        const int64_t chunk0 = first + (int64_t)ch * CHUNK;
+        const int cnt = (int)min((int64_t)CHUNK, last - chunk0);
         for (int r = 0; r < cnt; ++r) {
             const Rec &R = chunk[r];
             if (R.tile != cur) {                               // block-uniform
@@ -392,43 +421,62 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                     pz = tz * GTZ + lz; py = (q % g.tiles_y) * GTY + ly; px = (q / g.tiles_y) * GTX + lx;
                 } else {
                     const int ty = cur / g.tiles_x;
-                    py = ty * TILE_Y + NPIX * ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
+                    py = ty * TILE_Y + ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
                 }
             }
             const uint32_t box = R.box;
             // rows of this thread inside the record's rectangle (image: the same for the whole warp)
-            const int row0 = GRID ? ly : NPIX * ly;
-            const unsigned rel = (unsigned)(row0 - (int)((box >> 16) & 0xff)), wy = box >> 24;
-            if (!(rel < wy) && !(NPIX > 1 && rel + 1u < wy)) continue;
-            bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
-            if (GRID) in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
-            if (!in_xz) continue;
-            const float ddx = R.xr - cx;
-            float d2xz = ddx * ddx;
-            if (GRID) { const float ddz = R.zr - cz; d2xz += ddz * ddz; }
-            else d2xz += R.zr;
+            const unsigned rel = (unsigned)(ly - (int)((box >> 16) & 0xff)), wy = box >> 24;
+            bool any_row = false;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) any_row |= rel + (unsigned)q < wy;
+            if (!any_row) continue;
+            const unsigned relx = (unsigned)(lx - (int)(box & 0xff)), wx = (box >> 8) & 0xff;
+            bool incol[NCOL];
+            bool any_col = false;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) { incol[j] = relx + 32u * j < wx; any_col |= incol[j]; }
+            if (GRID) any_col &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+            if (!any_col) continue;
+            float d2xz[NCOL];
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+                const float ddx = R.xr - cxs[j];
+                d2xz[j] = ddx * ddx;
+                if (GRID) { const float ddz = R.zr - cz; d2xz[j] += ddz * ddz; }
+                else d2xz[j] += R.zr;
+            }
             // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
             // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
             // indices past its end need no test
             const float inv = R.inv, wq = R.wq;
-            const unsigned ns = (unsigned)g.ns;
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
-                for (int q = 0; q < NPIX; ++q) {
+                for (int q = 0; q < NR; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
-                    const float ddy = R.yr - cy[q];
-                    const float d2 = ddy * ddy + d2xz;
-                    const float t = fminf(d2 * inv, nsf + 2.0f);
-                    unsigned idx = (unsigned)t;
-                    const float fr = t - (float)idx;
-                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
-                    a[q] += slut[idx] * wq;
+                    const float ddy = R.yr - cys[q];
+                    const float d2y = ddy * ddy;
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) {
+                        if (!incol[j]) continue;
+                        const float d2 = d2y + d2xz[j];
+                        const float t = fminf(d2 * inv, nsf + 2.0f);
+                        unsigned idx = (unsigned)t;
+                        const float fr = t - (float)idx;
+                        if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f)
+                            idx = min(exact_index<GRID>(ctx, payloads[chunk0 + r], px + 32 * j, py + q, pz), ns);
+                        a[q][j] += slut[idx] * wq;
+                    }
                 }
             } else {                                           // tiny kernels: exact index only
 #pragma unroll
-                for (int q = 0; q < NPIX; ++q) {
+                for (int q = 0; q < NR; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
-                    a[q] += slut[min(exact_index<GRID>(g, R, px, py + q, pz), ns)] * wq;
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) {
+                        if (!incol[j]) continue;
+                        a[q][j] += slut[min(exact_index<GRID>(ctx, payloads[chunk0 + r], px + 32 * j, py + q, pz), ns)] * wq;
+                    }
                 }
             }
         }
@@ -482,7 +530,7 @@ inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); 
 
 struct Work {
     cudaStream_t s = lib_stream();
-    DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp;
+    DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp, ctx;
     size_t scan_bytes = 0, sort_bytes = 0;
 };
 
@@ -534,13 +582,20 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, im, P, wk.keys2.as<uint32_t>(),
                wk.vals2.as<uint32_t>(), wk.recs.as<Rec>());
     const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * ((size_t)g.ns + 3);
+    ExactCtx hctx;
+    hctx.g = g; hctx.c = c; hctx.im = im; hctx.i0 = i0;
+    if (!wk.ctx.p) wk.ctx.alloc(sizeof(ExactCtx));
+    PNB_CUDA(cudaMemcpyAsync(wk.ctx.p, &hctx, sizeof(ExactCtx), cudaMemcpyHostToDevice, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
     KernelTimer timer(2, s);
     if (g.grid) {
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+        PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), wk.vals2.as<uint32_t>(), P, g,
+                   wk.ctx.as<ExactCtx>(), lut_dev, acc);
     } else {
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), wk.vals2.as<uint32_t>(), P, g,
+                   wk.ctx.as<ExactCtx>(), lut_dev, acc);
     }
     timer.stop();
     kernel_ms += pnb_last_kernel_ms(2);
