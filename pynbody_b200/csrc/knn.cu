@@ -409,27 +409,81 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                                                      PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
         }
 
-        // then the sibling sub-tree at every level on the way up (smooth.h:209-241)
+        // then the sibling sub-tree at every level on the way up (smooth.h:209-241).  Inside a sub-tree the walk is
+        // depth-first with the NEARER child first (the reference goes lower child first): both children of a node are
+        // tested together (their bounds are adjacent in memory), the warp votes on which one lies nearer to most of
+        // its queries, and one bit per level remembers that the other child is still to come.  Near buckets tighten
+        // every lane's k-th distance early, so later buckets yield fewer candidates that have to be inserted only to
+        // be pushed out again (CPU model of the walk, scripts/knn_walk_model.py: -10 % buckets visited, -18 % insert
+        // rounds).  The result does not depend on the order (exact ties at the k-th distance aside).
         int64_t cell = tv.nsplit + bucket;
         while (cell != 1) {
             int64_t cp = cell ^ 1;
-            const int64_t stop = next_node(cp);
-            for (;;) {
-                Box6<T> b = load_box(tv.box, cp);
+            int depth = 0;
+            uint32_t pend = 0, pend_right = 0;      // bit d: the node at depth d has a child left to visit / it is the right one
+            T sx, sy, sz;
+            bool pass;
+            {
+                const Box6<T> b = load_box(tv.box, cp);
                 STAT(5, 1);    // nodes tested
-                T sx, sy, sz;
-                T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
+                const T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
                 // (top * slack overflows to +inf while the queue still holds its initial huge keys; empty
                 // nodes have inverted bounds and an infinite gap)
-                bool pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
+                pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
+            }
+            for (;;) {
+                bool descend = false;
                 if (__any_sync(FULL, pass)) {
-                    if (cp < tv.nsplit) { cp = 2 * cp; continue; }
-                    const bool amb = pass && shift_is_ambiguous<T, PERIODIC>(b, sx, sy, sz, L);
-                    knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
-                                                             PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
+                    if (cp >= tv.nsplit) {
+                        bool amb = false;
+                        if (PERIODIC) amb = pass && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, cp), sx, sy, sz, L);
+                        knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
+                                                                 PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
+                    } else {
+                        const Box6<T> bl = load_box(tv.box, 2 * cp), br = load_box(tv.box, 2 * cp + 1);
+                        STAT(5, 2);
+                        T lx_, ly_, lz_, rx_, ry_, rz_;
+                        const T gl = box_gap2<T, PERIODIC>(bl, qx, qy, qz, L, lx_, ly_, lz_);
+                        const T gr = box_gap2<T, PERIODIC>(br, qx, qy, qz, L, rx_, ry_, rz_);
+                        const T bound = q.top * Ex<T>::slack();
+                        const bool pl = active && gl <= bound && gl < Ex<T>::inf();
+                        const bool pr = active && gr <= bound && gr < Ex<T>::inf();
+                        const unsigned vl = __ballot_sync(FULL, pl), vr = __ballot_sync(FULL, pr);
+                        if (vl | vr) {
+                            const unsigned nearer_r = __ballot_sync(FULL, active && gr < gl);
+                            const unsigned nearer_l = __ballot_sync(FULL, active && gl < gr);
+                            const bool right_first = vr && (!vl || __popc(nearer_r) > __popc(nearer_l));
+                            if (vl && vr) {
+                                pend |= 1u << depth;
+                                if (right_first) pend_right &= ~(1u << depth); else pend_right |= 1u << depth;
+                            }
+                            cp = 2 * cp + (right_first ? 1 : 0);
+                            ++depth;
+                            pass = right_first ? pr : pl;
+                            sx = right_first ? rx_ : lx_; sy = right_first ? ry_ : ly_; sz = right_first ? rz_ : lz_;
+                            descend = true;
+                        }
+                    }
                 }
-                cp = next_node(cp);
-                if (cp == stop) break;
+                if (descend) continue;
+                // back up to the nearest level that still owes a child; re-test it against the tighter bound
+                bool found = false;
+                while (depth > 0) {
+                    --depth;
+                    cp >>= 1;
+                    if ((pend >> depth) & 1u) {
+                        pend &= ~(1u << depth);
+                        cp = 2 * cp + ((pend_right >> depth) & 1u);
+                        ++depth;
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) break;
+                const Box6<T> b = load_box(tv.box, cp);
+                STAT(5, 1);
+                const T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
+                pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
             }
             cell >>= 1;
         }

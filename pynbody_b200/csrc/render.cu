@@ -11,9 +11,9 @@
 //      (4x8x8-voxel) tiles it overlaps is counted;
 //   2. a prefix sum and a second footprint pass emit (tile, particle) pairs, which one radix sort
 //      groups by tile;
-//   3. a record pass writes one 32-byte record per pair (float position relative to the tile origin,
-//      1/kernel support, weight, rectangle clipped to the tile) in sorted order, so that a tile's particles
-//      are contiguous;
+//   3. a record pass writes one 64-byte record per pair (float position relative to the tile origin,
+//      1/kernel support, weight, rectangle clipped to the tile; the doubles of the exact path) in sorted
+//      order, so that a tile's particles are contiguous;
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
 //      balance for clustered data) and streams the records through shared memory with TMA bulk copies
 //      (cp.async.bulk + mbarrier, double buffered).  IMAGE tiles are 64 x 32 pixels: warp w owns rows
@@ -26,10 +26,9 @@
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
 // evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
-// coordinates (absolute error < 2e-3 of an index step for 64-pixel tiles) and falls back to the reference's
-// exact double expression -- recomputed from the particle's own arrays, the records carry no doubles --
-// whenever the float value lies within 4e-3 of an integer, so the selected table entry is the reference's in
-// every case.
+// coordinates and falls back to the reference's exact double expression whenever the float value lies within
+// twice its own error bound of an integer (a per-record bound: 3e-4 of an index step for a typical 10-pixel
+// kernel, 3e-3 for the smallest ones), so the selected table entry is the reference's in every case.
 //
 // Perspective images (z_camera != 0) rescale the pixel grid per particle (_render.pyx:281-295); they go
 // through an exact per-particle scatter kernel with double atomics instead of the tile path.
@@ -48,8 +47,7 @@ constexpr int TILE_X = 64, TILE_Y = 32;          // image tile: 64 x 32 pixels, 
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
-constexpr int64_t MAX_PAIRS = (int64_t)192 << 20; // pairs handled per sort/render batch (6 GiB of records)
-constexpr float BORDER = 4e-3f;
+constexpr int64_t MAX_PAIRS = (int64_t)96 << 20;  // pairs handled per sort/render batch (6 GiB of records)
 
 struct Geom {
     int nx, ny, nz, grid;
@@ -83,13 +81,14 @@ struct Images {
 };
 
 struct alignas(16) Rec {
+    double xi, yi, zd, kmax2;     // exact path only.  zd: image -> dz = (z - z0) * use_z ; grid -> z
     float xr, yr, zr, inv;        // tile-relative position; image: zr = dz^2; inv = ns / kmax2 (<0: exact path only)
     float wq;                     // weight / h^dim
     uint32_t box;                 // lxa | wx << 8 | lya << 16 | wy << 24   (rectangle clipped to the tile)
     uint32_t boxz;                // lza | wz << 8
     uint32_t tile;
 };
-static_assert(sizeof(Rec) == 32, "record must be 32 bytes");
+static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
 
 __device__ __forceinline__ int c_int(double v)
 {
@@ -251,12 +250,15 @@ __global__ void k_make_records(Geom g, Cols c, int64_t i0, Images im, int64_t np
     const double h = f.h;
     const float hk = (g.h_power == 2) ? (float)(h * h) : (float)(h * h * h);        // :309-312
     const double kmax2 = (h * h) * (g.max_d * g.max_d);                             // :313
+    R.xi = f.xi; R.yi = f.yi; R.kmax2 = kmax2;
     R.xr = (float)(f.xi - (g.x1 + g.pdx * px0));
     R.yr = (float)(f.yi - (g.y1 + g.pdy * py0));
     if (!g.grid) {
         const double dz = (f.zi - g.z0) * g.use_z;                                  // :314
+        R.zd = dz;
         R.zr = (float)(dz * dz);
     } else {
+        R.zd = f.zi;
         R.zr = (float)(f.zi - (g.z1 + g.pdz * pz0));
     }
     const bool single = g.max_d * h / g.pdx < 1 && g.max_d * h / g.pdy < 1;
@@ -302,45 +304,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// the reference's table lookup index (_render.pyx:186-193) in exact double arithmetic, from the particle's own
-// arrays (taken by the few pixel evaluations whose float index lies next to a bin edge, and by sub-pixel kernels)
-struct ExactCtx {            // what the exact path reads; lives in global memory so that the render kernel does not
-    Geom g;                  // have to spill its parameters to the stack to pass them on
-    Cols c;
-    Images im;
-    int64_t i0;
-};
+// the reference's table lookup index (_render.pyx:186-193) in exact double arithmetic
 template <bool GRID>
-__device__ __noinline__ unsigned exact_index(const ExactCtx *__restrict__ ctx, uint32_t payload, int px, int py, int pz)
+__device__ __forceinline__ unsigned exact_index(const Geom &g, const Rec &R, int px, int py, int pz)
 {
-    const Geom &g = ctx->g;
-    const Cols &c = ctx->c;
-    const Images &im = ctx->im;
-    const int64_t i0 = ctx->i0;
-    const int img = (int)(payload >> IMAGE_SHIFT);
-    const int64_t i = i0 + (payload & ((1u << IMAGE_SHIFT) - 1u));
-    const double xi = ld_pos(c.x, c.pos_f64, i, im.ox[img]), yi = ld_pos(c.y, c.pos_f64, i, im.oy[img]);
-    const double zi = ld_pos(c.z, c.pos_f64, i, GRID ? im.oz[img] : 0.0f);
-    double h = c.h[i];
-    if (!GRID && h < g.min_smooth) h = g.min_smooth;                                // :297
-    const double kmax2 = (h * h) * (g.max_d * g.max_d);                             // :313
-    const double ddx = xi - (g.pdx * (double)px + g.xs);
-    const double ddy = yi - (g.pdy * (double)py + g.ys);
+    const double ddx = R.xi - (g.pdx * (double)px + g.xs);
+    const double ddy = R.yi - (g.pdy * (double)py + g.ys);
     double d2;
     if (GRID) {
-        const double ddz = zi - (g.pdz * (double)pz + g.zs);
+        const double ddz = R.zd - (g.pdz * (double)pz + g.zs);
         d2 = ddx * ddx + ddy * ddy + ddz * ddz;
     } else {
-        const double dz = (zi - g.z0) * g.use_z;                                    // :314
-        d2 = ddx * ddx + ddy * ddy + dz * dz;
+        d2 = ddx * ddx + ddy * ddy + R.zd * R.zd;
     }
-    const double t = g.ns * (d2 / kmax2);
+    const double t = g.ns * (d2 / R.kmax2);
     return (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ recs, const uint32_t *__restrict__ payloads,
-                                                      int64_t npairs, Geom g, const ExactCtx *__restrict__ ctx,
+__global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ recs, int64_t npairs, Geom g,
                                                       const float *__restrict__ lut, double *__restrict__ acc)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -381,6 +363,13 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     const float cz = (float)(g.pdz * (lz + 0.5));
     const float nsf = (float)g.ns;
     const unsigned ns = (unsigned)g.ns;
+    // How far the float index t = ns * d2 / kmax2 can be from the exact one: the tile-relative coordinates are rounded
+    // to float (half an ulp of at most tile extent + 2h), which moves t by < 6e-6 * (tile extent / h + 2) per axis;
+    // the remaining float operations add < 6e-5.  Within twice that bound of an integer the exact expression decides.
+    // With 1/h = max_d * sqrt(inv / ns) the bound is linear in sqrt(inv): border = border_a * sqrt(inv) + border_b.
+    const float extent = GRID ? (float)(GTX * g.pdx + GTY * g.pdy + GTZ * g.pdz) : (float)(TILE_X * g.pdx + TILE_Y * g.pdy);
+    const float border_a = 2.0f * 6e-6f * extent * (float)g.max_d / sqrtf(nsf);
+    const float border_b = 2.0f * (6e-6f * (GRID ? 6.0f : 4.0f) + 6e-5f);
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
@@ -450,6 +439,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
             // indices past its end need no test
             const float inv = R.inv, wq = R.wq;
+            const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
                 for (int q = 0; q < NR; ++q) {
@@ -463,8 +453,8 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                         const float t = fminf(d2 * inv, nsf + 2.0f);
                         unsigned idx = (unsigned)t;
                         const float fr = t - (float)idx;
-                        if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f)
-                            idx = min(exact_index<GRID>(ctx, payloads[chunk0 + r], px + 32 * j, py + q, pz), ns);
+                        if (fabsf(fr - 0.5f) > 0.5f - border && t < nsf + 1.0f)
+                            idx = min(exact_index<GRID>(g, R, px + 32 * j, py + q, pz), ns);
                         a[q][j] += slut[idx] * wq;
                     }
                 }
@@ -475,7 +465,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
 #pragma unroll
                     for (int j = 0; j < NCOL; ++j) {
                         if (!incol[j]) continue;
-                        a[q][j] += slut[min(exact_index<GRID>(ctx, payloads[chunk0 + r], px + 32 * j, py + q, pz), ns)] * wq;
+                        a[q][j] += slut[min(exact_index<GRID>(g, R, px + 32 * j, py + q, pz), ns)] * wq;
                     }
                 }
             }
@@ -530,7 +520,7 @@ inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); 
 
 struct Work {
     cudaStream_t s = lib_stream();
-    DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp, ctx;
+    DevBuf counts, offsets, keys, vals, keys2, vals2, recs, scan_tmp, sort_tmp;
     size_t scan_bytes = 0, sort_bytes = 0;
 };
 
@@ -582,20 +572,13 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
     PNB_LAUNCH(k_make_records, nblk(P, BS), BS, 0, s, g, c, i0, im, P, wk.keys2.as<uint32_t>(),
                wk.vals2.as<uint32_t>(), wk.recs.as<Rec>());
     const size_t smem = 2 * CHUNK * sizeof(Rec) + 16 + sizeof(float) * ((size_t)g.ns + 3);
-    ExactCtx hctx;
-    hctx.g = g; hctx.c = c; hctx.im = im; hctx.i0 = i0;
-    if (!wk.ctx.p) wk.ctx.alloc(sizeof(ExactCtx));
-    PNB_CUDA(cudaMemcpyAsync(wk.ctx.p, &hctx, sizeof(ExactCtx), cudaMemcpyHostToDevice, s));
-    PNB_CUDA(cudaStreamSynchronize(s));
     KernelTimer timer(2, s);
     if (g.grid) {
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), wk.vals2.as<uint32_t>(), P, g,
-                   wk.ctx.as<ExactCtx>(), lut_dev, acc);
+        PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     } else {
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), wk.vals2.as<uint32_t>(), P, g,
-                   wk.ctx.as<ExactCtx>(), lut_dev, acc);
+        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     }
     timer.stop();
     kernel_ms += pnb_last_kernel_ms(2);
