@@ -16,13 +16,16 @@
 //      order, so that a tile's particles are contiguous;
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
 //      balance for clustered data) and streams the records through shared memory with TMA bulk copies
-//      (cp.async.bulk + mbarrier, double buffered).  IMAGE tiles are 64 x 32 pixels: warp w owns rows
-//      4w .. 4w+3 and lane l columns l and l+32, i.e. EIGHT pixels per thread in registers -- a record's row
-//      test is warp-uniform, its column terms (dx^2 + dz^2) are formed once for the 4 rows, its row terms once
-//      for the 2 columns, and the per-record decode is paid once per 8 pixels (round 1: 32 x 16 tiles, two
-//      pixels per thread: 54 ms for the C3 image; the per-record overhead was half of the instructions).
-//      GRID tiles are 4 x 8 x 8 voxels, one per thread.  Pixels are flushed with one double-precision
-//      atomicAdd per (pixel, slice).
+//      (cp.async.bulk + mbarrier, double buffered).
+//      IMAGE tiles are 64 x 64 pixels held as floats in shared memory.  Every WARP takes its own records of
+//      the slice and sweeps the record's clipped rectangle -- lanes across 32 columns, rows in a loop -- adding
+//      into the tile with shared-memory float atomics: a record is decoded once by one warp instead of being
+//      examined by all eight, and lanes idle only in the last 32-column chunk of a rectangle.  (Round 1 gave
+//      every thread fixed pixels of a 32 x 16 tile and showed each record to all 256 threads: 54 ms for the C3
+//      image, 58.6 G warp instructions, a third of them useful; giving each thread 8 fixed pixels of a 64 x 32
+//      tile kept the instruction count and lost issue efficiency: 84 ms.)  When the slice moves on to the next
+//      tile the CTA adds its tile to the image with one double-precision atomicAdd per touched pixel.
+//      GRID tiles are 4 x 8 x 8 voxels, one voxel per thread in a register.
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
 // evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
@@ -43,7 +46,7 @@ namespace pnb {
 
 namespace {
 
-constexpr int TILE_X = 64, TILE_Y = 32;          // image tile: 64 x 32 pixels, 8 per thread (rows 4w..4w+3 of warp w, columns l and l+32)
+constexpr int TILE_X = 64, TILE_Y = 64;          // image tile: 64 x 64 pixels, accumulated in shared memory (k_render_image_tiles)
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
@@ -475,6 +478,117 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     flush();
 }
 
+// ---- image tiles: record-parallel warps, tile in shared memory -------------------------------------------
+__global__ void __launch_bounds__(256) k_render_image_tiles(const Rec *__restrict__ recs, int64_t npairs, Geom g,
+                                                            const float *__restrict__ lut, double *__restrict__ acc)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    Rec *buf = reinterpret_cast<Rec *>(smem);                                  // [2][CHUNK]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * CHUNK * sizeof(Rec));
+    float *tile = reinterpret_cast<float *>(smem + 2 * CHUNK * sizeof(Rec) + 16);        // [TILE_Y][TILE_X]
+    float *slut = tile + TILE_X * TILE_Y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t first = (int64_t)blockIdx.x * SEG;
+    const int64_t last = min(npairs, first + (int64_t)SEG);
+    const int nchunks = (int)((last - first + CHUNK - 1) / CHUNK);
+
+    for (int i = tid; i < g.ns + 3; i += 256) slut[i] = i < g.ns ? lut[i] : 0.0f;
+    for (int i = tid; i < TILE_X * TILE_Y; i += 256) tile[i] = 0.0f;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int ch) {
+        const int64_t b = first + (int64_t)ch * CHUNK;
+        const uint32_t bytes = (uint32_t)(min((int64_t)CHUNK, last - b) * sizeof(Rec));
+        mbar_expect_tx(&bar[ch & 1], bytes);
+        tma_load_bulk(buf + (ch & 1) * CHUNK, recs + b, bytes, &bar[ch & 1]);
+    };
+    if (tid == 0) issue(0);
+
+    const float nsf = (float)g.ns;
+    const unsigned ns = (unsigned)g.ns;
+    const float pdxf = (float)g.pdx, pdyf = (float)g.pdy;
+    // float-index error bound (see k_render_tiles); the pixel-centre offsets are formed in float here, which adds
+    // one more rounding of at most the tile extent
+    const float extent = (float)(TILE_X * g.pdx + TILE_Y * g.pdy);
+    const float border_a = 2.0f * 9e-6f * extent * (float)g.max_d / sqrtf(nsf);
+    const float border_b = 2.0f * (6e-6f * 4.0f + 6e-5f);
+
+    uint32_t cur = 0xffffffffu;                        // tile the shared-memory accumulator belongs to
+    auto flush = [&]() {                               // block-wide; callers synchronise around it
+        if (cur == 0xffffffffu) return;
+        const int ty = cur / g.tiles_x, tx = cur - ty * g.tiles_x;
+        for (int i = tid; i < TILE_X * TILE_Y; i += 256) {
+            const float v = tile[i];
+            if (v != 0.0f) {
+                const int py = ty * TILE_Y + i / TILE_X, px = tx * TILE_X + (i & (TILE_X - 1));
+                atomicAdd(&acc[(int64_t)py * g.nx + px], (double)v);
+                tile[i] = 0.0f;
+            }
+        }
+    };
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (tid == 0 && ch + 1 < nchunks) issue(ch + 1);      // buffer (ch+1)&1 was released by the barrier below
+        mbar_wait(&bar[ch & 1], (uint32_t)((ch >> 1) & 1));
+        const Rec *chunk = buf + (ch & 1) * CHUNK;
+        const int cnt = (int)min((int64_t)CHUNK, last - (first + (int64_t)ch * CHUNK));
+        int r0 = 0;
+        while (r0 < cnt) {                                 // runs of records of one tile (the list is sorted by tile)
+            const uint32_t t = chunk[r0].tile;
+            int r1 = cnt;
+            if (chunk[cnt - 1].tile != t) {
+                r1 = r0 + 1;
+                while (chunk[r1].tile == t) ++r1;
+            }
+            if (t != cur) {
+                __syncthreads();
+                flush();
+                cur = t;
+                __syncthreads();
+            }
+            const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
+            for (int r = r0 + warp; r < r1; r += 8) {          // one record per warp at a time
+                const Rec &R = chunk[r];
+                const uint32_t box = R.box;
+                const int lxa = box & 0xff, wx = (box >> 8) & 0xff, lya = (box >> 16) & 0xff, wy = box >> 24;
+                const float inv = R.inv, wq = R.wq, xr = R.xr, yr = R.yr, zr = R.zr;
+                const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
+                for (int c0 = 0; c0 < wx; c0 += 32) {
+                    const int col = lxa + c0 + lane;
+                    const bool incol = c0 + lane < wx;
+                    const float ddx = xr - pdxf * ((float)col + 0.5f);
+                    const float d2xz = ddx * ddx + zr;
+                    float *tp = tile + lya * TILE_X + col;
+                    for (int row = lya; row < lya + wy; ++row, tp += TILE_X) {
+                        const float ddy = yr - pdyf * ((float)row + 0.5f);
+                        const float d2 = ddy * ddy + d2xz;
+                        unsigned idx;
+                        if (inv > 0.0f) {
+                            const float tt = fminf(d2 * inv, nsf + 2.0f);
+                            idx = (unsigned)tt;
+                            const float fr = tt - (float)idx;
+                            if (incol && fabsf(fr - 0.5f) > 0.5f - border && tt < nsf + 1.0f)
+                                idx = min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns);
+                        } else {                                   // sub-pixel kernels: exact index only
+                            idx = incol ? min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns) : ns;
+                        }
+                        // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
+                        // weight poisons the same pixels (w * 0 = NaN); the table is followed by zeros
+                        if (incol) atomicAdd(tp, slut[idx] * wq);
+                    }
+                }
+            }
+            r0 = r1;
+        }
+        __syncthreads();
+    }
+    flush();
+}
+
 // ---- exact per-particle scatter (perspective images; also the cross-check path) ------------------------
 __global__ void k_render_scatter(Geom g, Cols c, float ox, float oy, const float *__restrict__ lut,
                                  double *__restrict__ acc)
@@ -577,8 +691,9 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     } else {
-        PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+        const size_t smem_img = smem + sizeof(float) * TILE_X * TILE_Y;
+        PNB_CUDA(cudaFuncSetAttribute(k_render_image_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
+        PNB_LAUNCH(k_render_image_tiles, nblk(P, SEG), 256, smem_img, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     }
     timer.stop();
     kernel_ms += pnb_last_kernel_ms(2);
