@@ -17,14 +17,16 @@
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
 //      balance for clustered data) and streams the records through shared memory with TMA bulk copies
 //      (cp.async.bulk + mbarrier, double buffered).
-//      IMAGE tiles are 64 x 64 pixels held as floats in shared memory.  Every WARP takes its own records of
-//      the slice and sweeps the record's clipped rectangle -- lanes across 32 columns, rows in a loop -- adding
-//      into the tile with shared-memory float atomics: a record is decoded once by one warp instead of being
-//      examined by all eight, and lanes idle only in the last 32-column chunk of a rectangle.  (Round 1 gave
-//      every thread fixed pixels of a 32 x 16 tile and showed each record to all 256 threads: 54 ms for the C3
-//      image, 58.6 G warp instructions, a third of them useful; giving each thread 8 fixed pixels of a 64 x 32
-//      tile kept the instruction count and lost issue efficiency: 84 ms.)  When the slice moves on to the next
-//      tile the CTA adds its tile to the image with one double-precision atomicAdd per touched pixel.
+//      IMAGE tiles are 64 x 64 pixels held as floats in shared memory; warp w owns the band of rows 8w .. 8w+7.
+//      For every record a warp looks at one word (the clipped rectangle) and, if the rectangle reaches into its
+//      band, sweeps just that part: lanes across 32 columns at a time, its rows in a loop, plain read-add-write
+//      of pixels nobody else touches.  Lanes idle only in the last 32-column chunk of a rectangle, and a record
+//      costs a warp that has nothing to do with it a handful of instructions.  (Round 1 gave every thread fixed
+//      pixels of a 32 x 16 tile: 54 ms for the C3 image, 58.6 G warp instructions, a third of them useful.  Two
+//      variants measured slower: 8 fixed pixels per thread on 64 x 32 tiles -- same instruction count, worse issue
+//      efficiency, 84 ms; one record per warp with shared-memory float atomics -- those are CAS loops
+//      (ATOMS.CAST.SPIN), 71 ms.)  When the slice moves on to the next tile the CTA adds its tile to the image
+//      with one double-precision atomicAdd per touched pixel.
 //      GRID tiles are 4 x 8 x 8 voxels, one voxel per thread in a register.
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
@@ -517,6 +519,7 @@ __global__ void __launch_bounds__(256) k_render_image_tiles(const Rec *__restric
     const float border_a = 2.0f * 9e-6f * extent * (float)g.max_d / sqrtf(nsf);
     const float border_b = 2.0f * (6e-6f * 4.0f + 6e-5f);
 
+    constexpr int BAND = TILE_Y / 8;                   // rows of the tile owned by one warp
     uint32_t cur = 0xffffffffu;                        // tile the shared-memory accumulator belongs to
     auto flush = [&]() {                               // block-wide; callers synchronise around it
         if (cur == 0xffffffffu) return;
@@ -551,19 +554,23 @@ __global__ void __launch_bounds__(256) k_render_image_tiles(const Rec *__restric
                 __syncthreads();
             }
             const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
-            for (int r = r0 + warp; r < r1; r += 8) {          // one record per warp at a time
+            for (int r = r0; r < r1; ++r) {
                 const Rec &R = chunk[r];
                 const uint32_t box = R.box;
-                const int lxa = box & 0xff, wx = (box >> 8) & 0xff, lya = (box >> 16) & 0xff, wy = box >> 24;
+                // rows of the record's rectangle inside this warp's band (warp-uniform)
+                const int lya = (box >> 16) & 0xff, wy = box >> 24;
+                const int ra = max(lya, warp * BAND), rb = min(lya + wy, warp * BAND + BAND);
+                if (ra >= rb) continue;
+                const int lxa = box & 0xff, wx = (box >> 8) & 0xff;
                 const float inv = R.inv, wq = R.wq, xr = R.xr, yr = R.yr, zr = R.zr;
                 const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
                 for (int c0 = 0; c0 < wx; c0 += 32) {
                     const int col = lxa + c0 + lane;
-                    const bool incol = c0 + lane < wx;
+                    if (c0 + lane >= wx) continue;
                     const float ddx = xr - pdxf * ((float)col + 0.5f);
                     const float d2xz = ddx * ddx + zr;
-                    float *tp = tile + lya * TILE_X + col;
-                    for (int row = lya; row < lya + wy; ++row, tp += TILE_X) {
+                    float *tp = tile + ra * TILE_X + col;
+                    for (int row = ra; row < rb; ++row, tp += TILE_X) {
                         const float ddy = yr - pdyf * ((float)row + 0.5f);
                         const float d2 = ddy * ddy + d2xz;
                         unsigned idx;
@@ -571,14 +578,14 @@ __global__ void __launch_bounds__(256) k_render_image_tiles(const Rec *__restric
                             const float tt = fminf(d2 * inv, nsf + 2.0f);
                             idx = (unsigned)tt;
                             const float fr = tt - (float)idx;
-                            if (incol && fabsf(fr - 0.5f) > 0.5f - border && tt < nsf + 1.0f)
+                            if (fabsf(fr - 0.5f) > 0.5f - border && tt < nsf + 1.0f)
                                 idx = min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns);
                         } else {                                   // sub-pixel kernels: exact index only
-                            idx = incol ? min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns) : ns;
+                            idx = min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns);
                         }
                         // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
                         // weight poisons the same pixels (w * 0 = NaN); the table is followed by zeros
-                        if (incol) atomicAdd(tp, slut[idx] * wq);
+                        *tp += slut[idx] * wq;
                     }
                 }
             }
