@@ -7,7 +7,7 @@
 // On the GPU the same sums are evaluated as a tile-binned GATHER:
 //   1. footprint pass: per particle (and per periodic image) the cull tests and the inclusive-exclusive
 //      pixel rectangle [xa,xb) x [ya,yb) (x [za,zb)) are computed with the reference's double
-//      arithmetic and C integer truncation (_render.pyx:297-346, 436-480); the number of 64x32-pixel
+//      arithmetic and C integer truncation (_render.pyx:297-346, 436-480); the number of 32x16-pixel
 //      (4x8x8-voxel) tiles it overlaps is counted;
 //   2. a prefix sum and a second footprint pass emit (tile, particle) pairs, which one radix sort
 //      groups by tile;
@@ -15,19 +15,17 @@
 //      1/kernel support, weight, rectangle clipped to the tile; the doubles of the exact path) in sorted
 //      order, so that a tile's particles are contiguous;
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
-//      balance for clustered data) and streams the records through shared memory with TMA bulk copies
-//      (cp.async.bulk + mbarrier, double buffered).
-//      IMAGE tiles are 64 x 64 pixels held as floats in shared memory; warp w owns the band of rows 8w .. 8w+7.
-//      For every record a warp looks at one word (the clipped rectangle) and, if the rectangle reaches into its
-//      band, sweeps just that part: lanes across 32 columns at a time, its rows in a loop, plain read-add-write
-//      of pixels nobody else touches.  Lanes idle only in the last 32-column chunk of a rectangle, and a record
-//      costs a warp that has nothing to do with it a handful of instructions.  (Round 1 gave every thread fixed
-//      pixels of a 32 x 16 tile: 54 ms for the C3 image, 58.6 G warp instructions, a third of them useful.  Two
-//      variants measured slower: 8 fixed pixels per thread on 64 x 32 tiles -- same instruction count, worse issue
-//      efficiency, 84 ms; one record per warp with shared-memory float atomics -- those are CAS loops
-//      (ATOMS.CAST.SPIN), 71 ms.)  When the slice moves on to the next tile the CTA adds its tile to the image
-//      with one double-precision atomicAdd per touched pixel.
-//      GRID tiles are 4 x 8 x 8 voxels, one voxel per thread in a register.
+//      balance for clustered data), streams the records through shared memory with TMA bulk copies
+//      (cp.async.bulk + mbarrier, double buffered), and its 256 threads accumulate the pixels of the current
+//      tile in registers: image tiles are 32 x 16 pixels, a warp is one 32-pixel row segment and owns two
+//      adjacent rows, so a record's row test is warp-uniform; grid tiles are 4 x 8 x 8 voxels, one per thread.
+//      Pixels are flushed with one double-precision atomicAdd per (pixel, slice).
+//      Three re-designs of the image kernel were built, verified against the goldens and measured SLOWER than
+//      this one (54 ms for the C3 image; profiles/r2_render_variants.md): 8 fixed pixels per thread on 64 x 32
+//      tiles (84 ms: same 58 G warp instructions, issue efficiency 87 -> 60 %); one record per warp adding into
+//      a shared-memory tile with float atomics (71 ms: those are CAS loops, ATOMS.CAST.SPIN); warps owning
+//      row bands of a shared-memory tile (73 ms: 46 G instructions but the warps of a CTA wait for the busiest
+//      band at every chunk barrier).
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
 // evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
@@ -48,7 +46,7 @@ namespace pnb {
 
 namespace {
 
-constexpr int TILE_X = 64, TILE_Y = 64;          // image tile: 64 x 64 pixels, accumulated in shared memory (k_render_image_tiles)
+constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, two pixels (rows 2w and 2w + 1 of warp w) per thread
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
@@ -346,65 +344,59 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int ch) {
-        const int64_t b = first + (int64_t)ch * CHUNK;
+    auto issue = [&](int c) {
+        const int64_t b = first + (int64_t)c * CHUNK;
         const uint32_t bytes = (uint32_t)(min((int64_t)CHUNK, last - b) * sizeof(Rec));
-        mbar_expect_tx(&bar[ch & 1], bytes);
-        tma_load_bulk(buf + (ch & 1) * CHUNK, recs + b, bytes, &bar[ch & 1]);
+        mbar_expect_tx(&bar[c & 1], bytes);
+        tma_load_bulk(buf + (c & 1) * CHUNK, recs + b, bytes, &bar[c & 1]);
     };
     if (tid == 0) issue(0);
 
-    // pixels of this thread inside a tile.  Image: rows NR*w .. NR*w+NR-1 of warp w (a record's row test is
-    // warp-uniform), columns lane and lane + 32.  Grid: one voxel of the 4 x 8 x 8 tile.
-    constexpr int NR = GRID ? 1 : 4, NCOL = GRID ? 1 : 2;
+    // Image tiles are 32 x 16 pixels: a warp is one row of 32 pixels (lane = x) and takes rows 2w and 2w + 1, so the
+    // row test of a record's rectangle is warp-uniform -- rows outside cost the warp three instructions instead of
+    // idling its lanes through the pixel arithmetic.  Grid tiles are 4 x 8 x 8 voxels, one per thread.
+    constexpr int NPIX = GRID ? 1 : 2;
     int lx, ly, lz = 0;
     if (GRID) { lz = tid & (GTZ - 1); ly = (tid >> 3) & (GTY - 1); lx = tid >> 6; }
-    else { lx = tid & 31; ly = (tid >> 5) * NR; }
-    float cxs[NCOL], cys[NR];
+    else { lx = tid & 31; ly = tid >> 5; }
+    const float cx = (float)(g.pdx * (lx + 0.5)), cz = (float)(g.pdz * (lz + 0.5));
+    float cy[NPIX];
 #pragma unroll
-    for (int j = 0; j < NCOL; ++j) cxs[j] = (float)(g.pdx * (lx + 32 * j + 0.5));
-#pragma unroll
-    for (int q = 0; q < NR; ++q) cys[q] = (float)(g.pdy * (ly + q + 0.5));
-    const float cz = (float)(g.pdz * (lz + 0.5));
+    for (int q = 0; q < NPIX; ++q) cy[q] = (float)(g.pdy * (NPIX * ly + q + 0.5));
     const float nsf = (float)g.ns;
-    const unsigned ns = (unsigned)g.ns;
     // How far the float index t = ns * d2 / kmax2 can be from the exact one: the tile-relative coordinates are rounded
     // to float (half an ulp of at most tile extent + 2h), which moves t by < 6e-6 * (tile extent / h + 2) per axis;
-    // the remaining float operations add < 6e-5.  Within twice that bound of an integer the exact expression decides.
-    // With 1/h = max_d * sqrt(inv / ns) the bound is linear in sqrt(inv): border = border_a * sqrt(inv) + border_b.
+    // the remaining float operations add < 6e-5.  Within twice that bound of an integer the exact expression decides
+    // (round 1 used a fixed 2e-3: 0.4 % of the pixel evaluations, i.e. one in eight 32-pixel rows, took the exact
+    // path; for a typical 10-pixel kernel the bound is 2.5e-4).  With 1/h = max_d * sqrt(inv / ns) the bound is linear
+    // in sqrt(inv): border = border_a * sqrt(inv) + border_b.
     const float extent = GRID ? (float)(GTX * g.pdx + GTY * g.pdy + GTZ * g.pdz) : (float)(TILE_X * g.pdx + TILE_Y * g.pdy);
     const float border_a = 2.0f * 6e-6f * extent * (float)g.max_d / sqrtf(nsf);
     const float border_b = 2.0f * (6e-6f * (GRID ? 6.0f : 4.0f) + 6e-5f);
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
-    float a[NR][NCOL];
+    float a[NPIX];
 #pragma unroll
-    for (int q = 0; q < NR; ++q)
-#pragma unroll
-        for (int j = 0; j < NCOL; ++j) a[q][j] = 0.0f;
+    for (int q = 0; q < NPIX; ++q) a[q] = 0.0f;
     uint32_t cur = 0xffffffffu;
     int px = 0, py = 0, pz = 0;                        // first pixel of this thread in the current tile
     auto flush = [&]() {
 #pragma unroll
-        for (int q = 0; q < NR; ++q)
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
-                if (a[q][j] != 0.0f) {
-                    const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz
-                                             : (int64_t)(py + q) * g.nx + (px + 32 * j);
-                    atomicAdd(&acc[pix], (double)a[q][j]);
-                }
-                a[q][j] = 0.0f;
+        for (int q = 0; q < NPIX; ++q) {
+            if (a[q] != 0.0f) {
+                const int64_t pix = GRID ? ((int64_t)px * g.ny + py) * g.nz + pz : (int64_t)(py + q) * g.nx + px;
+                atomicAdd(&acc[pix], (double)a[q]);
             }
+            a[q] = 0.0f;
+        }
     };
 
-    for (int ch = 0; ch < nchunks; ++ch) {
-        if (tid == 0 && ch + 1 < nchunks) issue(ch + 1);      // buffer (ch+1)&1 was released by the barrier below
-        mbar_wait(&bar[ch & 1], (uint32_t)((ch >> 1) & 1));
-        const Rec *chunk = buf + (ch & 1) * CHUNK;
-        const int64_t chunk0 = first + (int64_t)ch * CHUNK;
-        const int cnt = (int)min((int64_t)CHUNK, last - chunk0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + 1 < nchunks) issue(c + 1);       // buffer (c+1)&1 was released by the barrier below
+        mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+        const Rec *chunk = buf + (c & 1) * CHUNK;
+        const int cnt = (int)min((int64_t)CHUNK, last - (first + (int64_t)c * CHUNK));
         for (int r = 0; r < cnt; ++r) {
             const Rec &R = chunk[r];
             if (R.tile != cur) {                               // block-uniform
@@ -415,181 +407,46 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                     pz = tz * GTZ + lz; py = (q % g.tiles_y) * GTY + ly; px = (q / g.tiles_y) * GTX + lx;
                 } else {
                     const int ty = cur / g.tiles_x;
-                    py = ty * TILE_Y + ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
+                    py = ty * TILE_Y + NPIX * ly; px = (cur - ty * g.tiles_x) * TILE_X + lx;
                 }
             }
             const uint32_t box = R.box;
             // rows of this thread inside the record's rectangle (image: the same for the whole warp)
-            const unsigned rel = (unsigned)(ly - (int)((box >> 16) & 0xff)), wy = box >> 24;
-            bool any_row = false;
-#pragma unroll
-            for (int q = 0; q < NR; ++q) any_row |= rel + (unsigned)q < wy;
-            if (!any_row) continue;
-            const unsigned relx = (unsigned)(lx - (int)(box & 0xff)), wx = (box >> 8) & 0xff;
-            bool incol[NCOL];
-            bool any_col = false;
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) { incol[j] = relx + 32u * j < wx; any_col |= incol[j]; }
-            if (GRID) any_col &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
-            if (!any_col) continue;
-            float d2xz[NCOL];
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
-                const float ddx = R.xr - cxs[j];
-                d2xz[j] = ddx * ddx;
-                if (GRID) { const float ddz = R.zr - cz; d2xz[j] += ddz * ddz; }
-                else d2xz[j] += R.zr;
-            }
+            const int row0 = GRID ? ly : NPIX * ly;
+            const unsigned rel = (unsigned)(row0 - (int)((box >> 16) & 0xff)), wy = box >> 24;
+            if (!(rel < wy) && !(NPIX > 1 && rel + 1u < wy)) continue;
+            bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
+            if (GRID) in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+            if (!in_xz) continue;
+            const float ddx = R.xr - cx;
+            float d2xz = ddx * ddx;
+            if (GRID) { const float ddz = R.zr - cz; d2xz += ddz * ddz; }
+            else d2xz += R.zr;
             // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
             // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
             // indices past its end need no test
             const float inv = R.inv, wq = R.wq;
             const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
+            const unsigned ns = (unsigned)g.ns;
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
-                for (int q = 0; q < NR; ++q) {
+                for (int q = 0; q < NPIX; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
-                    const float ddy = R.yr - cys[q];
-                    const float d2y = ddy * ddy;
-#pragma unroll
-                    for (int j = 0; j < NCOL; ++j) {
-                        if (!incol[j]) continue;
-                        const float d2 = d2y + d2xz[j];
-                        const float t = fminf(d2 * inv, nsf + 2.0f);
-                        unsigned idx = (unsigned)t;
-                        const float fr = t - (float)idx;
-                        if (fabsf(fr - 0.5f) > 0.5f - border && t < nsf + 1.0f)
-                            idx = min(exact_index<GRID>(g, R, px + 32 * j, py + q, pz), ns);
-                        a[q][j] += slut[idx] * wq;
-                    }
+                    const float ddy = R.yr - cy[q];
+                    const float d2 = ddy * ddy + d2xz;
+                    const float t = fminf(d2 * inv, nsf + 2.0f);
+                    unsigned idx = (unsigned)t;
+                    const float fr = t - (float)idx;
+                    if (fabsf(fr - 0.5f) > 0.5f - border && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
+                    a[q] += slut[idx] * wq;
                 }
             } else {                                           // tiny kernels: exact index only
 #pragma unroll
-                for (int q = 0; q < NR; ++q) {
+                for (int q = 0; q < NPIX; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
-#pragma unroll
-                    for (int j = 0; j < NCOL; ++j) {
-                        if (!incol[j]) continue;
-                        a[q][j] += slut[min(exact_index<GRID>(g, R, px + 32 * j, py + q, pz), ns)] * wq;
-                    }
+                    a[q] += slut[min(exact_index<GRID>(g, R, px, py + q, pz), ns)] * wq;
                 }
             }
-        }
-        __syncthreads();
-    }
-    flush();
-}
-
-// ---- image tiles: record-parallel warps, tile in shared memory -------------------------------------------
-__global__ void __launch_bounds__(256) k_render_image_tiles(const Rec *__restrict__ recs, int64_t npairs, Geom g,
-                                                            const float *__restrict__ lut, double *__restrict__ acc)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    Rec *buf = reinterpret_cast<Rec *>(smem);                                  // [2][CHUNK]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * CHUNK * sizeof(Rec));
-    float *tile = reinterpret_cast<float *>(smem + 2 * CHUNK * sizeof(Rec) + 16);        // [TILE_Y][TILE_X]
-    float *slut = tile + TILE_X * TILE_Y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t first = (int64_t)blockIdx.x * SEG;
-    const int64_t last = min(npairs, first + (int64_t)SEG);
-    const int nchunks = (int)((last - first + CHUNK - 1) / CHUNK);
-
-    for (int i = tid; i < g.ns + 3; i += 256) slut[i] = i < g.ns ? lut[i] : 0.0f;
-    for (int i = tid; i < TILE_X * TILE_Y; i += 256) tile[i] = 0.0f;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int ch) {
-        const int64_t b = first + (int64_t)ch * CHUNK;
-        const uint32_t bytes = (uint32_t)(min((int64_t)CHUNK, last - b) * sizeof(Rec));
-        mbar_expect_tx(&bar[ch & 1], bytes);
-        tma_load_bulk(buf + (ch & 1) * CHUNK, recs + b, bytes, &bar[ch & 1]);
-    };
-    if (tid == 0) issue(0);
-
-    const float nsf = (float)g.ns;
-    const unsigned ns = (unsigned)g.ns;
-    const float pdxf = (float)g.pdx, pdyf = (float)g.pdy;
-    // float-index error bound (see k_render_tiles); the pixel-centre offsets are formed in float here, which adds
-    // one more rounding of at most the tile extent
-    const float extent = (float)(TILE_X * g.pdx + TILE_Y * g.pdy);
-    const float border_a = 2.0f * 9e-6f * extent * (float)g.max_d / sqrtf(nsf);
-    const float border_b = 2.0f * (6e-6f * 4.0f + 6e-5f);
-
-    constexpr int BAND = TILE_Y / 8;                   // rows of the tile owned by one warp
-    uint32_t cur = 0xffffffffu;                        // tile the shared-memory accumulator belongs to
-    auto flush = [&]() {                               // block-wide; callers synchronise around it
-        if (cur == 0xffffffffu) return;
-        const int ty = cur / g.tiles_x, tx = cur - ty * g.tiles_x;
-        for (int i = tid; i < TILE_X * TILE_Y; i += 256) {
-            const float v = tile[i];
-            if (v != 0.0f) {
-                const int py = ty * TILE_Y + i / TILE_X, px = tx * TILE_X + (i & (TILE_X - 1));
-                atomicAdd(&acc[(int64_t)py * g.nx + px], (double)v);
-                tile[i] = 0.0f;
-            }
-        }
-    };
-
-    for (int ch = 0; ch < nchunks; ++ch) {
-        if (tid == 0 && ch + 1 < nchunks) issue(ch + 1);      // buffer (ch+1)&1 was released by the barrier below
-        mbar_wait(&bar[ch & 1], (uint32_t)((ch >> 1) & 1));
-        const Rec *chunk = buf + (ch & 1) * CHUNK;
-        const int cnt = (int)min((int64_t)CHUNK, last - (first + (int64_t)ch * CHUNK));
-        int r0 = 0;
-        while (r0 < cnt) {                                 // runs of records of one tile (the list is sorted by tile)
-            const uint32_t t = chunk[r0].tile;
-            int r1 = cnt;
-            if (chunk[cnt - 1].tile != t) {
-                r1 = r0 + 1;
-                while (chunk[r1].tile == t) ++r1;
-            }
-            if (t != cur) {
-                __syncthreads();
-                flush();
-                cur = t;
-                __syncthreads();
-            }
-            const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
-            for (int r = r0; r < r1; ++r) {
-                const Rec &R = chunk[r];
-                const uint32_t box = R.box;
-                // rows of the record's rectangle inside this warp's band (warp-uniform)
-                const int lya = (box >> 16) & 0xff, wy = box >> 24;
-                const int ra = max(lya, warp * BAND), rb = min(lya + wy, warp * BAND + BAND);
-                if (ra >= rb) continue;
-                const int lxa = box & 0xff, wx = (box >> 8) & 0xff;
-                const float inv = R.inv, wq = R.wq, xr = R.xr, yr = R.yr, zr = R.zr;
-                const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
-                for (int c0 = 0; c0 < wx; c0 += 32) {
-                    const int col = lxa + c0 + lane;
-                    if (c0 + lane >= wx) continue;
-                    const float ddx = xr - pdxf * ((float)col + 0.5f);
-                    const float d2xz = ddx * ddx + zr;
-                    float *tp = tile + ra * TILE_X + col;
-                    for (int row = ra; row < rb; ++row, tp += TILE_X) {
-                        const float ddy = yr - pdyf * ((float)row + 0.5f);
-                        const float d2 = ddy * ddy + d2xz;
-                        unsigned idx;
-                        if (inv > 0.0f) {
-                            const float tt = fminf(d2 * inv, nsf + 2.0f);
-                            idx = (unsigned)tt;
-                            const float fr = tt - (float)idx;
-                            if (fabsf(fr - 0.5f) > 0.5f - border && tt < nsf + 1.0f)
-                                idx = min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns);
-                        } else {                                   // sub-pixel kernels: exact index only
-                            idx = min(exact_index<false>(g, R, tx * TILE_X + col, ty * TILE_Y + row, 0), ns);
-                        }
-                        // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
-                        // weight poisons the same pixels (w * 0 = NaN); the table is followed by zeros
-                        *tp += slut[idx] * wq;
-                    }
-                }
-            }
-            r0 = r1;
         }
         __syncthreads();
     }
@@ -698,9 +555,8 @@ void render_range(Work &wk, const Geom &g, const Cols &c, int64_t i0, int64_t i1
         PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PNB_LAUNCH((k_render_tiles<true>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     } else {
-        const size_t smem_img = smem + sizeof(float) * TILE_X * TILE_Y;
-        PNB_CUDA(cudaFuncSetAttribute(k_render_image_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_img));
-        PNB_LAUNCH(k_render_image_tiles, nblk(P, SEG), 256, smem_img, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
+        PNB_CUDA(cudaFuncSetAttribute(k_render_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNB_LAUNCH((k_render_tiles<false>), nblk(P, SEG), 256, smem, s, wk.recs.as<Rec>(), P, g, lut_dev, acc);
     }
     timer.stop();
     kernel_ms += pnb_last_kernel_ms(2);
