@@ -29,9 +29,10 @@
 //
 // LUT index parity: the reference indexes its 201-entry table with (unsigned)(ns * (d2 / kmax2))
 // evaluated in double.  The inner loop evaluates the same quantity in float from tile-relative
-// coordinates and falls back to the reference's exact double expression whenever the float value lies within
-// twice its own error bound of an integer (a per-record bound: 3e-4 of an index step for a typical 10-pixel
-// kernel, 3e-3 for the smallest ones), so the selected table entry is the reference's in every case.
+// coordinates (absolute error < 9e-4 of an index step) and falls back to the reference's exact double
+// expression whenever the float value lies within 2e-3 of an integer, so the selected table entry is
+// the reference's in every case.  (A per-record bound -- 2.5e-4 for a typical 10-pixel kernel -- sends five
+// times fewer evaluations through the exact path but costs a square root per record and thread: 57.6 vs 54.1 ms.)
 //
 // Perspective images (z_camera != 0) rescale the pixel grid per particle (_render.pyx:281-295); they go
 // through an exact per-particle scatter kernel with double atomics instead of the tile path.
@@ -50,6 +51,7 @@ constexpr int TILE_X = 32, TILE_Y = 16;          // image tile: 32 x 16 pixels, 
 constexpr int GTX = 4, GTY = 8, GTZ = 8;        // grid tile: 4 x 8 x 8 voxels (z fastest in memory)
 constexpr int SEG = 1024;                       // (tile, particle) pairs per CTA
 constexpr int CHUNK = 64;                       // records per TMA transfer
+constexpr float BORDER = 2e-3f;
 constexpr int64_t MAX_PAIRS = (int64_t)96 << 20;  // pairs handled per sort/render batch (6 GiB of records)
 
 struct Geom {
@@ -364,15 +366,6 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
 #pragma unroll
     for (int q = 0; q < NPIX; ++q) cy[q] = (float)(g.pdy * (NPIX * ly + q + 0.5));
     const float nsf = (float)g.ns;
-    // How far the float index t = ns * d2 / kmax2 can be from the exact one: the tile-relative coordinates are rounded
-    // to float (half an ulp of at most tile extent + 2h), which moves t by < 6e-6 * (tile extent / h + 2) per axis;
-    // the remaining float operations add < 6e-5.  Within twice that bound of an integer the exact expression decides
-    // (round 1 used a fixed 2e-3: 0.4 % of the pixel evaluations, i.e. one in eight 32-pixel rows, took the exact
-    // path; for a typical 10-pixel kernel the bound is 2.5e-4).  With 1/h = max_d * sqrt(inv / ns) the bound is linear
-    // in sqrt(inv): border = border_a * sqrt(inv) + border_b.
-    const float extent = GRID ? (float)(GTX * g.pdx + GTY * g.pdy + GTZ * g.pdz) : (float)(TILE_X * g.pdx + TILE_Y * g.pdy);
-    const float border_a = 2.0f * 6e-6f * extent * (float)g.max_d / sqrtf(nsf);
-    const float border_b = 2.0f * (6e-6f * (GRID ? 6.0f : 4.0f) + 6e-5f);
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
@@ -426,7 +419,6 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
             // indices past its end need no test
             const float inv = R.inv, wq = R.wq;
-            const float border = fminf(border_a * sqrtf(fmaxf(inv, 0.0f)) + border_b, 0.25f);
             const unsigned ns = (unsigned)g.ns;
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
@@ -437,7 +429,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                     const float t = fminf(d2 * inv, nsf + 2.0f);
                     unsigned idx = (unsigned)t;
                     const float fr = t - (float)idx;
-                    if (fabsf(fr - 0.5f) > 0.5f - border && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
+                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
                     a[q] += slut[idx] * wq;
                 }
             } else {                                           // tiny kernels: exact index only
