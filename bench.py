@@ -561,6 +561,12 @@ def run_ours_distributed(args):
     allst = [torch.empty_like(st) for _ in range(world)]
     dist.all_gather(allst, st)
 
+    # C4: the gradient operators on the decomposed box (halo exchange #2 carries rho and the velocities)
+    stages = {}
+    for op in ("div", "curl", "mean"):
+        d.sph_op(op, vel, K_NEIGHBOURS, 1)
+        stages["v_%s_ms" % op] = round(timed(lambda: d.sph_op(op, vel, K_NEIGHBOURS, 1), 2) / 2, 3)
+
     # C5-style image: every rank renders the particles it owns, frames are summed over NVLink
     render = {}
     if not args.no_render:
@@ -568,16 +574,18 @@ def run_ours_distributed(args):
         from pynbody_b200.sph import _render, kernels
         k2 = kernels.create_kernel(KERNEL).projection()
         wrap = [-1.0, 0.0, 1.0]
-        res = args.render_res
         opos, omass, osm, orho = d.owned()
+        res = args.render_res
         def once():
             img = _render.render_image(res, res, opos[:, 0], opos[:, 1], opos[:, 2], osm, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5,
                                        orho, omass, orho, 0.0, float("inf"), float("-inf"), float("inf"), 0.0, k2, wrap, wrap)
             return reduce_image(img)
-        once()
-        ms = timed(once, 2) / 2
-        render["image"] = {"resolution": res, "mode": "projected density, 3x3 periodic images, per-rank frames summed with an NCCL reduce",
-                           "ms": ms, "mpix_per_s": res * res / (ms * 1e-3) / 1e6}
+        for res in sorted({args.render_res, 4096}):
+            once()
+            ms = timed(once, 2) / 2
+            render["image" if res == args.render_res else "image_%d" % res] = {
+                "resolution": res, "mode": "projected density, 3x3 periodic images, per-rank frames summed with an NCCL reduce",
+                "ms": ms, "mpix_per_s": res * res / (ms * 1e-3) / 1e6}
     if rank == 0:
         peak, peak_src = load_peaks()
         knn_ms = kdmain.last_kernel_ms(0)
@@ -599,7 +607,7 @@ def run_ours_distributed(args):
                              "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                              "peak_source": peak_src, "kernel_ms": knn_ms,
                              "note": "per-kernel roofline is reported by the N=1 run; see DESIGN.md"},
-                "render": render}
+                "stages_ms": stages, "render": render}
         print(json.dumps(line))
     dist.destroy_process_group()
 

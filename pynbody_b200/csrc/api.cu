@@ -124,9 +124,15 @@ void cache_free(void *p, size_t bytes)
     BlockCache &c = block_cache();
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.limit == 0) {
+        // idle blocks kept at most: PNB_CACHE_LIMIT_GB if set, else a quarter of the device's memory (torch's own
+        // caching allocator in the same process cannot reclaim what sits here; pnb_release_cached_memory() returns it)
         size_t free_b = 0, total_b = 0;
         c.limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 : (size_t)16 << 30;
         cudaGetLastError();
+        if (const char *e = getenv("PNB_CACHE_LIMIT_GB")) {
+            const double gb = atof(e);
+            if (gb >= 0) c.limit = (size_t)(gb * 1073741824.0) + 1;
+        }
     }
     // A process that keeps changing its particle count would otherwise pile up idle blocks of ever new size
     // classes: past the limit everything idle goes back to the driver (the next step re-allocates what it needs).
@@ -605,6 +611,7 @@ pnb_tree *pnb_tree_create(const void *pos, int64_t pos_stride0, int64_t pos_stri
         if (leafsize < 1) throw Error(PNB_ERR_VALUE, "leafsize must be positive");
         t = new Tree();
         t->dtype = dtype; t->n = n; t->user_leafsize = leafsize;
+        PNB_CUDA(cudaGetDevice(&t->device));
         StageTimer timer(0, t->stream);
         const size_t ts = tsize(dtype);
         DevBuf cols(ts * 3 * n), mass_dev;
@@ -638,6 +645,13 @@ void pnb_tree_destroy(pnb_tree *h) { delete reinterpret_cast<Tree *>(h); }
 #define PNB_NEED_TREE(h)                                                     \
     do {                                                                     \
         if (!(h)) { set_last_error("tree handle is null"); return PNB_ERR_VALUE; } \
+        int dev_ = -1;                                                       \
+        const int tdev_ = reinterpret_cast<const Tree *>(h)->device;         \
+        if (tdev_ >= 0 && cudaGetDevice(&dev_) == cudaSuccess && dev_ != tdev_) {                                     \
+            set_last_error("the tree lives on CUDA device " + std::to_string(tdev_) + " but the calling thread's current " \
+                           "device is " + std::to_string(dev_) + ": call pnb_set_device first");                     \
+            return PNB_ERR_VALUE;                                            \
+        }                                                                    \
     } while (0)
 
 int64_t pnb_tree_num_particles(const pnb_tree *h) { PNB_NEED_TREE(h); return reinterpret_cast<const Tree *>(h)->n; }

@@ -129,6 +129,7 @@ void shape_seg_of_node(const TreeShape &s, int level, int64_t j, int64_t &lo, in
 struct Tree {
     TreeShape shape;
     int dtype = PNB_F64;          // PNB_F32 / PNB_F64: dtype of pos/mass/smooth/rho ("T")
+    int device = -1;              // CUDA device the tree's buffers live on; entry points reject calls from another device
     int64_t n = 0;
     int user_leafsize = 16;
     int levels = 0;               // depth of the device tree: buckets live at heap level `levels`

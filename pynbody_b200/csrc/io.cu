@@ -33,7 +33,17 @@ struct Staging {
         if (!ok) cudaGetLastError();
     }
 };
-Staging &staging() { static thread_local Staging s; return s; }
+// one set of pinned buffers and events per (thread, device): events are bound to the device that was current
+// when they were created (a thread that calls pnb_set_device() in between must not reuse another device's)
+Staging &staging()
+{
+    static thread_local Staging *per_dev[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    Staging *&s = per_dev[dev & 63];
+    if (!s) s = new Staging();
+    return *s;
+}
 
 bool is_pinned(const void *p)
 {

@@ -889,7 +889,9 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             else vf = vf * ((const float *)a.mass)[i];
             if (isd || a.rho_f64) { vd = (isd ? vd : (double)vf) / ldv(a.rho, a.rho_f64, i); isd = true; }
             else vf = vf / ((const float *)a.rho)[i];
-            atomicAdd(&acc[ipix], isd ? vd : (double)vf);
+            // The reference's ip == 0 case on the first ring gives pixel index (size_t)-1: it writes 4 bytes BEFORE its
+            // image there (an out-of-bounds write on the host).  That contribution is dropped here.
+            if (ipix < (size_t)12 * nside * nside) atomicAdd(&acc[ipix], isd ? vd : (double)vf);
         }
         __syncwarp();
     }

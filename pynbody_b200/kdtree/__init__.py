@@ -81,25 +81,20 @@ class KDTree:
 
     @classmethod
     def deserialize(cls, pos, mass, serialized_state, num_threads=None, boxsize=None):
-        """Reconstruct a KDTree from a serialized state (pynbody/kdtree/__init__.py:140-163)."""
+        """A KDTree for ``pos`` from what :meth:`serialize` returned (pynbody/kdtree/__init__.py:140-163).  The
+        serialized node records are checked against the particle set and kept as this tree's ``kdnodes`` /
+        ``particle_offsets``; the device tree itself is rebuilt from the positions (milliseconds; neighbour sets do not
+        depend on the tree's shape)."""
+        leafsize, saved_boxsize, kdnodes, particle_offsets, kernel_id = serialized_state
+        if None not in (boxsize, saved_boxsize) and abs(boxsize - saved_boxsize) > 1e-6:
+            warnings.warn("Boxsize in serialized state does not match boxsize passed to deserialize")
         self = object.__new__(cls)
         self._set_num_threads(num_threads)
-        leafsize, boxsize_s, kdnodes, particle_offsets, kernel_id = serialized_state
-        if boxsize is not None and boxsize_s is not None and abs(boxsize - boxsize_s) > 1e-6:
-            warnings.warn("Boxsize in serialized state does not match boxsize passed to deserialize")
-        self.kdtree = kdmain.init(pos, mass, leafsize)
         self.leafsize = leafsize
-        nodes = kdmain.get_node_count(self.kdtree)
-        if len(kdnodes) != nodes:
-            raise ValueError("Number of nodes in serialized state does not match number of nodes in kdtree")
-        if len(particle_offsets) != len(pos):
-            raise ValueError("Number of particle offsets in serialized state does not match number of particles")
-        self._kdnodes = kdnodes
-        self._particle_offsets = particle_offsets
-        self.boxsize = boxsize
-        self._pos = pos
-        self._kernel_id = kernel_id
-        kdmain.import_prebuilt(self.kdtree, kdnodes, particle_offsets, 0)
+        self.kdtree = kdmain.init(pos, mass, leafsize)
+        kdmain.import_prebuilt(self.kdtree, kdnodes, particle_offsets, 0)     # ValueError on a size mismatch
+        self._kdnodes, self._particle_offsets = kdnodes, particle_offsets
+        self.boxsize, self._pos, self._kernel_id = boxsize, pos, kernel_id
         return self
 
     def _period(self):
@@ -168,30 +163,30 @@ class KDTree:
     def get_array_ref(self, name):
         return kdmain.get_arrayref(self.kdtree, self.array_name_to_id(name))
 
+    # operation name -> (property id for 1-D input, property id for N x 3 input); None = shape not accepted
+    _OPERATIONS = {"hsm": (PROPID_HSM, PROPID_HSM), "rho": (PROPID_RHO, PROPID_RHO),
+                   "qty_mean": (PROPID_QTYMEAN_1D, PROPID_QTYMEAN_ND), "qty_disp": (PROPID_QTYDISP_1D, PROPID_QTYDISP_ND),
+                   "qty_div": (None, PROPID_QTYDIV), "qty_curl": (None, PROPID_QTYCURL)}
+
     def smooth_operation_to_id(self, name):
-        """Name of a smoothing operation -> property id (pynbody/kdtree/__init__.py:275-320)."""
-        if name == "hsm":
-            return self.PROPID_HSM
-        elif name == "rho":
-            return self.PROPID_RHO
-        elif name in ("qty_mean", "qty_disp"):
-            input_array = self.get_array_ref("qty")
-            one, nd = ((self.PROPID_QTYMEAN_1D, self.PROPID_QTYMEAN_ND) if name == "qty_mean"
-                       else (self.PROPID_QTYDISP_1D, self.PROPID_QTYDISP_ND))
-            if len(input_array.shape) == 1:
-                return one
-            elif len(input_array.shape) == 2:
-                if input_array.shape[1] != 3:
-                    raise ValueError("Currently only able to smooth 3D or 1D arrays")
-                return nd
-            raise ValueError("Currently only able to smooth 3D or 1D arrays")
-        elif name in ("qty_div", "qty_curl"):
-            input_array = self.get_array_ref("qty")
-            if len(input_array.shape) != 2 or input_array.shape[1] != 3:
-                raise ValueError("Can only compute %s of 3D arrays" % ("divergence" if name == "qty_div" else "curl"))
-            return self.PROPID_QTYDIV if name == "qty_div" else self.PROPID_QTYCURL
-        else:
+        """Property id of a smoothing operation, chosen by the shape of the registered ``qty`` array
+        (pynbody/kdtree/__init__.py:275-320: same names, same ValueErrors)."""
+        if name not in self._OPERATIONS:
             raise ValueError("Unknown smoothing request %s" % name)
+        one, nd = self._OPERATIONS[name]
+        if one == nd:
+            return one
+        shape = tuple(self.get_array_ref("qty").shape)
+        is_nd = len(shape) == 2 and shape[1] == 3
+        if name in ("qty_div", "qty_curl"):
+            if not is_nd:
+                raise ValueError("Can only compute %s of 3D arrays" % ("divergence" if name == "qty_div" else "curl"))
+            return nd
+        if len(shape) == 1:
+            return one
+        if not is_nd:
+            raise ValueError("Currently only able to smooth 3D or 1D arrays")
+        return nd
 
     def set_kernel(self, kernel=None):
         """Set the kernel for smoothing operations (pynbody/kdtree/__init__.py:322-334)."""
@@ -221,56 +216,38 @@ class KDTree:
             out.units = array.units if units is None else units
         return out
 
-    def sph_mean(self, array, nsmooth=64):
-        """SPH mean of an array (pynbody/kdtree/__init__.py:377-419)."""
-        output = self._output_like(array)
+    def _sph_reduce(self, array, mode, label, nsmooth, scalar_out=False, per_length=False):
+        """One SPH reduction of ``array`` over each particle's neighbours: registers input and output, runs
+        ``populate(mode)`` and returns the output (pynbody/kdtree/__init__.py:377-534).  ``scalar_out``: one value per
+        particle; ``per_length``: the result carries the units of ``array`` divided by those of the positions."""
+        units = None
+        if per_length and hasattr(array, "units") and hasattr(self._pos, "units"):
+            units = array.units / self._pos.units
+        output = self._output_like(array, shape=(len(array),) if scalar_out else None, units=units)
         self.set_array_ref("qty", array)
         self.set_array_ref("qty_sm", output)
-        logger.info("Smoothing array with %d nearest neighbours" % nsmooth)
+        logger.info("%s of array with %d nearest neighbours" % (label, nsmooth))
         start = time.time()
-        self.populate("qty_mean", nsmooth)
-        logger.info("SPH smooth done in %5.3g s" % (time.time() - start))
+        self.populate(mode, nsmooth)
+        logger.info("%s done in %5.3g s" % (label, time.time() - start))
         return output
+
+    def sph_mean(self, array, nsmooth=64):
+        """SPH mean of a 1-D or N x 3 array (pynbody/kdtree/__init__.py:377-419)."""
+        return self._sph_reduce(array, "qty_mean", "SPH mean", nsmooth)
 
     def sph_dispersion(self, array, nsmooth=64):
-        """SPH dispersion of an array (pynbody/kdtree/__init__.py:421-470).
-
-        As in the reference the output is allocated with the input's shape; for N x 3 input the
-        single dispersion per particle lands in column 0 (smDispQtyND writes through a 1-D accessor).
-        """
-        output = self._output_like(array)
-        self.set_array_ref("qty", array)
-        self.set_array_ref("qty_sm", output)
-        logger.info("Getting dispersion of array with %d nearest neighbours" % nsmooth)
-        start = time.time()
-        self.populate("qty_disp", nsmooth)
-        logger.info("SPH dispersion done in %5.3g s" % (time.time() - start))
-        return output
-
-    def _sph_differential_operator(self, array, op, nsmooth=64):
-        if op == "div":
-            op_label = "divergence"
-            output = self._output_like(array, shape=(len(array),),
-                                       units=(array.units / self._pos.units) if hasattr(array, "units") and hasattr(self._pos, "units") else None)
-        elif op == "curl":
-            op_label = "curl"
-            output = self._output_like(array,
-                                       units=(array.units / self._pos.units) if hasattr(array, "units") and hasattr(self._pos, "units") else None)
-        else:
-            raise ValueError("Can only compute curl or divergence")
-        self.set_array_ref("qty", array)
-        self.set_array_ref("qty_sm", output)
-        logger.info("Getting %s of array with %d nearest neighbours" % (op_label, nsmooth))
-        start = time.time()
-        self.populate("qty_%s" % op, nsmooth)
-        logger.info(f"SPH {op_label} done in {time.time() - start:5.3g} s")
-        return output
+        """SPH dispersion (pynbody/kdtree/__init__.py:421-470).  As in the reference the output has the input's shape;
+        for N x 3 input the single dispersion per particle lands in column 0 (smDispQtyND writes through a 1-D accessor)."""
+        return self._sph_reduce(array, "qty_disp", "SPH dispersion", nsmooth)
 
     def sph_curl(self, array, nsmooth=64):
-        return self._sph_differential_operator(array, "curl", nsmooth)
+        """SPH curl of an N x 3 array (pynbody/kdtree/__init__.py:472-534)."""
+        return self._sph_reduce(array, "qty_curl", "SPH curl", nsmooth, per_length=True)
 
     def sph_divergence(self, array, nsmooth=64):
-        return self._sph_differential_operator(array, "div", nsmooth)
+        """SPH divergence of an N x 3 array (pynbody/kdtree/__init__.py:472-534)."""
+        return self._sph_reduce(array, "qty_div", "SPH divergence", nsmooth, scalar_out=True, per_length=True)
 
     def __del__(self):
         if hasattr(self, "kdtree"):
