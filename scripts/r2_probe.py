@@ -10,7 +10,8 @@ from pynbody_b200.kdtree import KDTree, kdmain
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dtype = np.float32 if (len(sys.argv) > 2 and sys.argv[2] == "f32") else np.float64
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-ops = len(sys.argv) > 4 and sys.argv[4] == "ops"
+ops = len(sys.argv) > 4 and sys.argv[4] in ("ops", "walk")
+walk = len(sys.argv) > 4 and sys.argv[4] == "walk"
 k = 64
 pos, vel, mass = synth.zeldovich_box_device(side, 2, dtype)
 n = pos.shape[0]
@@ -31,5 +32,10 @@ for rep in range(reps):
         for name, fn in (("mean", kd.sph_mean), ("disp", kd.sph_dispersion), ("div", kd.sph_divergence), ("curl", kd.sph_curl)):
             fn(vel, k)
             line += f" | {name} {kdmain.last_device_ms(1):.2f} (kernel {kdmain.last_kernel_ms(1):.2f})"
+    if walk:      # foreign smooth array: the tree-walking fixed-radius gather (gather.cu)
+        sm2 = sm.clone(); sm2[0] *= 1.0000001
+        kd.set_array_ref("smooth", sm2)
+        kd.populate("rho", k)
+        line += f" | rho by tree walk {kdmain.last_device_ms(1):.2f} (kernel {kdmain.last_kernel_ms(1):.2f})"
     print(line, flush=True)
     del kd

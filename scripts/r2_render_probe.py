@@ -24,3 +24,9 @@ if len(sys.argv) > 4:
     g = _render.to_3d_grid(256, 256, 256, pos[:, 0], pos[:, 1], pos[:, 2], sm, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, rho, mass, rho,
                            0.0, float("inf"), k3, wrap, wrap, wrap)
     print("grid ms:", _render.last_render_ms(), flush=True)
+    c = pos - 0.5
+    r2 = (c * c).sum(dim=1)
+    shell = torch.nonzero((r2 > 0.09) & (r2 < 0.25)).squeeze(1)
+    hp = _render.render_spherical_image_core(rho[shell], mass[shell], rho[shell], c[shell][:, 0].contiguous(), c[shell][:, 1].contiguous(),
+                                             c[shell][:, 2].contiguous(), sm[shell], 256, k2)
+    print("healpix nside 256,", int(shell.numel()), "particles, ms:", _render.last_render_ms(), flush=True)
