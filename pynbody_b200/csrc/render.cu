@@ -803,6 +803,9 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
     if (thetamax > PI) thetamax = PI;
     const size_t irmin = hp_ring_num_from_z(nside, cos(thetamin)), irmax = hp_ring_num_from_z(nside, cos(thetamax));
     const double cos_radius = cos(radius);
+    const float radiusf = (float)radius, distancef = (float)distance, nsf = (float)a.ns;
+    const float inv_kmax2f = (float)(1.0 / kernel_max_2);
+    const double ns_over_kmax2 = (double)a.ns / kernel_max_2;
     // The disc is found ring by ring as healpix.c does it, 32 rings at a time with one ring per lane; the
     // pixels of those rings are then numbered consecutively and dealt out to the lanes, so that all lanes
     // are busy whatever the width of a ring (a disc of the usual size has ~12 pixels per ring).
@@ -860,27 +863,65 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             size_t ip = (size_t)R.ip_lo + (size_t)(f - first);
             if (ip > n_in_ring) ip -= n_in_ring;
             const size_t ipix = hp_pixel_index(nside, R.iring, ip);
-            double dot;
-            if (pixvec && ip >= 1) {             // (ip = 0 happens at phi ~ 0: the reference then takes the direction
-                                                 // of "pixel 0" of the ring but the index before the ring's first)
+            // Fast path (the pixel's centre vector comes from the table): the angle between the two unit vectors is
+            // taken from their chord -- c^2 = |v - p|^2 in double without cancellation, angle = 2 asin(c / 2) in float
+            // (relative error < 5e-7) -- instead of a double-precision acos(v . p) per pixel, and the table index
+            // t = ns d2 / kmax2 is formed in float.  The reference's double expressions decide whenever the float
+            // result is not safe: angle within 1e-5 of the disc radius, t within 5e-4 of an integer, nearly antipodal
+            // directions.  For the thin-shell kernel cos(angle) = 1 - c^2/2 is used directly (no transcendental at all).
+            unsigned idx = 0;
+            bool exact = !(pixvec && ip >= 1);
+            double dot = 0.0;
+            if (!exact) {
                 const double4 pv = pixvec[ipix];
+                const double ex = v0 - pv.x, ey = v1 - pv.y, ez = v2 - pv.z;
+                const double chord2 = ex * ex + ey * ey + ez * ez;
                 dot = v0 * pv.x + v1 * pv.y + v2 * pv.z;
-            } else {
-                double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
-                if (phi >= twopi) phi -= twopi;
-                double sphi, cphi;
-                sincos(phi, &sphi, &cphi);
-                dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
+                if (a.projected) {
+                    const float chord = sqrtf((float)chord2);
+                    const float distf = 2.0f * asinf(fminf(0.5f * chord, 1.0f));
+                    if (chord > 1.9f || fabsf(distf - radiusf) <= 1e-5f * radiusf) exact = true;
+                    else {
+                        if (distf > radiusf) continue;
+                        const float off = distancef * distf;
+                        const float tf = nsf * (off * off) * inv_kmax2f;
+                        idx = (unsigned)fminf(tf, nsf + 2.0f);
+                        const float fr = tf - (float)idx;
+                        if (fabsf(fr - 0.5f) > 0.5f - 5e-4f && tf < nsf + 1.0f) exact = true;
+                    }
+                } else {
+                    const double cosd = 1.0 - 0.5 * chord2;
+                    if (fabs(cosd - cos_radius) <= 1e-12) exact = true;
+                    else {
+                        if (cosd < cos_radius) continue;
+                        const double d2 = shell_2 + distance2 - two_rs_d * cosd;
+                        const double td = d2 * ns_over_kmax2;
+                        const double tc = td < 0.0 ? 0.0 : (td > 4.0e9 ? 4.0e9 : td);
+                        idx = (unsigned)tc;
+                        const double fr = tc - (double)idx;
+                        if (fabs(fr - 0.5) > 0.5 - 1e-7 && td < (double)a.ns + 1.0) exact = true;
+                    }
+                }
             }
-            if (dot > 1.0) dot = 1.0;
-            if (dot < -1.0) dot = -1.0;
-            const double dist = acos(dot);
-            if (!(dist <= radius)) continue;
-            double d2;
-            if (a.projected) { const double off = distance * dist; d2 = off * off; }
-            else d2 = shell_2 + distance2 - two_rs_d * cos(dist);
-            const double t = a.ns * (d2 / kernel_max_2);
-            const unsigned idx = (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
+            if (exact) {
+                if (!(pixvec && ip >= 1)) {      // (ip = 0 happens at phi ~ 0: the reference then takes the direction
+                                                 // of "pixel 0" of the ring but the index before the ring's first)
+                    double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
+                    if (phi >= twopi) phi -= twopi;
+                    double sphi, cphi;
+                    sincos(phi, &sphi, &cphi);
+                    dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
+                }
+                if (dot > 1.0) dot = 1.0;
+                if (dot < -1.0) dot = -1.0;
+                const double dist = acos(dot);
+                if (!(dist <= radius)) continue;
+                double d2;
+                if (a.projected) { const double off = distance * dist; d2 = off * off; }
+                else d2 = shell_2 + distance2 - two_rs_d * cos(dist);
+                const double t = a.ns * (d2 / kernel_max_2);
+                idx = (t >= 4294967296.0 || t != t) ? 0xffffffffu : (unsigned)t;
+            }
             const float kern = idx < (unsigned)a.ns ? lut[idx] / h_to_kdim : 0.0f;
             bool isd = a.qty_f64;
             double vd = isd ? qty_i * (double)kern : 0.0;
