@@ -704,6 +704,7 @@ struct HpArgs {
 struct HpRing {                 // one ring of a particle's disc (healpix.c:120-200)
     double st, ct;              // sin / cos of the ring's colatitude
     unsigned ip_lo, n_in_ring, shift, iring;
+    unsigned long long base;    // index of the ring's pixel "0" (= hp_pixel_index(nside, iring, 0)); pixel ip is base + ip
 };
 
 __device__ __forceinline__ double ldv(const void *p, int f64, int64_t i)
@@ -804,6 +805,9 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
     const size_t irmin = hp_ring_num_from_z(nside, cos(thetamin)), irmax = hp_ring_num_from_z(nside, cos(thetamax));
     const double cos_radius = cos(radius);
     const float radiusf = (float)radius, distancef = (float)distance, nsf = (float)a.ns;
+    // the particle's mass and density, loaded once (they enter every pixel's weight chain in their own element type)
+    const double mass_d = ldv(a.mass, a.mass_f64, i), rho_d = ldv(a.rho, a.rho_f64, i);
+    const float mass_f = (float)mass_d, rho_f = (float)rho_d;
     const float inv_kmax2f = (float)(1.0 / kernel_max_2);
     const double ns_over_kmax2 = (double)a.ns / kernel_max_2;
     // The disc is found ring by ring as healpix.c does it, 32 rings at a time with one ring per lane; the
@@ -837,6 +841,7 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             sincos(theta, &wr[lane].st, &wr[lane].ct);
             wr[lane].ip_lo = (unsigned)ip_lo; wr[lane].n_in_ring = (unsigned)n_in_ring;
             wr[lane].shift = (unsigned)shift; wr[lane].iring = (unsigned)iring;
+            wr[lane].base = (unsigned long long)hp_pixel_index(nside, iring, 0);
             count = (int)(ip_hi - ip_lo + 1);
         }
         int incl = count;                               // inclusive prefix sum over the lanes
@@ -862,7 +867,7 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             const size_t n_in_ring = R.n_in_ring, shift = R.shift;
             size_t ip = (size_t)R.ip_lo + (size_t)(f - first);
             if (ip > n_in_ring) ip -= n_in_ring;
-            const size_t ipix = hp_pixel_index(nside, R.iring, ip);
+            const size_t ipix = (size_t)(R.base + ip);
             // Fast path (the pixel's centre vector comes from the table): the angle between the two unit vectors is
             // taken from their chord -- c^2 = |v - p|^2 in double without cancellation, angle = 2 asin(c / 2) in float
             // (relative error < 5e-7) -- instead of a double-precision acos(v . p) per pixel, and the table index
@@ -926,10 +931,10 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             bool isd = a.qty_f64;
             double vd = isd ? qty_i * (double)kern : 0.0;
             float vf = isd ? 0.0f : (float)qty_i * kern;
-            if (isd || a.mass_f64) { vd = (isd ? vd : (double)vf) * ldv(a.mass, a.mass_f64, i); isd = true; }
-            else vf = vf * ((const float *)a.mass)[i];
-            if (isd || a.rho_f64) { vd = (isd ? vd : (double)vf) / ldv(a.rho, a.rho_f64, i); isd = true; }
-            else vf = vf / ((const float *)a.rho)[i];
+            if (isd || a.mass_f64) { vd = (isd ? vd : (double)vf) * mass_d; isd = true; }
+            else vf = vf * mass_f;
+            if (isd || a.rho_f64) { vd = (isd ? vd : (double)vf) / rho_d; isd = true; }
+            else vf = vf / rho_f;
             // The reference's ip == 0 case on the first ring gives pixel index (size_t)-1: it writes 4 bytes BEFORE its
             // image there (an out-of-bounds write on the host).  That contribution is dropped here.
             if (ipix < (size_t)12 * nside * nside) atomicAdd(&acc[ipix], isd ? vd : (double)vf);
