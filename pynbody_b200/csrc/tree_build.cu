@@ -163,15 +163,28 @@ __global__ void k_node_bounds(TreeShape s, int level, const uint32_t *__restrict
 
 // one thread per list position: the particle at rank p of its node's split-axis list goes to the
 // lower child iff p <= split rank
+constexpr int LEVEL_ITEMS = 4;       // list entries per thread in the per-level passes: four independent load chains in flight
+
 __global__ void k_mark_sides(TreeShape s, int level, const uint32_t *__restrict__ L, const int8_t *__restrict__ dim,
                              uint8_t *__restrict__ side)
 {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= s.n) return;
-    int64_t lo, hi, node;
-    seg_of_pos(s, level, p, lo, hi, node);
-    int d = dim[node];
-    side[L[(int64_t)d * s.n + p]] = (uint8_t)(p > split_rank(s, level, lo, hi));
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * LEVEL_ITEMS + threadIdx.x;
+    uint32_t id[LEVEL_ITEMS];
+    uint8_t sd[LEVEL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < LEVEL_ITEMS; ++k) {
+        const int64_t p = base + (int64_t)k * blockDim.x;
+        id[k] = 0xffffffffu;
+        if (p >= s.n) continue;
+        int64_t lo, hi, node;
+        seg_of_pos(s, level, p, lo, hi, node);
+        const int d = dim[node];
+        id[k] = L[(int64_t)d * s.n + p];
+        sd[k] = (uint8_t)(p > split_rank(s, level, lo, hi));
+    }
+#pragma unroll
+    for (int k = 0; k < LEVEL_ITEMS; ++k)
+        if (id[k] != 0xffffffffu) side[id[k]] = sd[k];
 }
 
 struct LeftFlag {
@@ -186,20 +199,39 @@ __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__
                             const int8_t *__restrict__ dim, const uint32_t *__restrict__ S, uint32_t *__restrict__ Lnew)
 {
     const int64_t n = s.n;
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= 3 * n) return;
-    int64_t d = (i >= n) + (i >= 2 * n), p = i - d * n;
-    int64_t lo, hi, node;
-    seg_of_pos(s, level, p, lo, hi, node);
-    int64_t m = split_rank(s, level, lo, hi);
-    uint32_t id = L[i];
-    if (s.packed && dim[node] == d) {                // the list of the split axis is partitioned as it stands
-        Lnew[i] = id;
-        return;
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * LEVEL_ITEMS + threadIdx.x;
+    // phase 1: the independent loads of all items (list entry, node's split axis, prefix sums)
+    uint32_t id[LEVEL_ITEMS], sv[LEVEL_ITEMS], sl[LEVEL_ITEMS];
+    int64_t lo_[LEVEL_ITEMS], m_[LEVEL_ITEMS], p_[LEVEL_ITEMS];
+    int dd[LEVEL_ITEMS];
+    bool keep[LEVEL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < LEVEL_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * blockDim.x;
+        dd[k] = -1;
+        if (i >= 3 * n) continue;
+        const int64_t d = (i >= n) + (i >= 2 * n), p = i - d * n;
+        int64_t lo, hi, node;
+        seg_of_pos(s, level, p, lo, hi, node);
+        dd[k] = (int)d; p_[k] = p; lo_[k] = lo; m_[k] = split_rank(s, level, lo, hi);
+        id[k] = L[i];
+        keep[k] = s.packed && dim[node] == d;                 // the list of the split axis is partitioned as it stands
+        sv[k] = S[i];
+        sl[k] = S[d * n + lo];
     }
-    uint32_t left_before = S[i] - S[d * n + lo];     // modular arithmetic: exact because < 2^32
-    int64_t dest = side[id] ? (m + 1) + (p - lo) - (int64_t)left_before : lo + (int64_t)left_before;
-    Lnew[d * n + dest] = id;
+    // phase 2: the dependent gathers of the side flags
+    uint8_t sd[LEVEL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < LEVEL_ITEMS; ++k) sd[k] = (dd[k] >= 0 && !keep[k]) ? side[id[k]] : 0;
+#pragma unroll
+    for (int k = 0; k < LEVEL_ITEMS; ++k) {
+        if (dd[k] < 0) continue;
+        const int64_t i = base + (int64_t)k * blockDim.x;
+        if (keep[k]) { Lnew[i] = id[k]; continue; }
+        const uint32_t left_before = sv[k] - sl[k];           // modular arithmetic: exact because < 2^32
+        const int64_t dest = sd[k] ? (m_[k] + 1) + (p_[k] - lo_[k]) - (int64_t)left_before : lo_[k] + (int64_t)left_before;
+        Lnew[(int64_t)dd[k] * n + dest] = id[k];
+    }
 }
 
 template <typename T>
@@ -270,12 +302,12 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         int64_t nn = (int64_t)1 << level;
         PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
                    dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr, inherited.as<T>());
-        PNB_LAUNCH(k_mark_sides, nblk(n, BS), BS, 0, s, shape, level, L, dim.as<int8_t>(), side.as<uint8_t>());
+        PNB_LAUNCH(k_mark_sides, nblk(n, BS * LEVEL_ITEMS), BS, 0, s, shape, level, L, dim.as<int8_t>(), side.as<uint8_t>());
         LeftFlag f{L, side.as<uint8_t>()};
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
         PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
         g_launches += 2;
-        PNB_LAUNCH(k_partition, nblk(3 * n, BS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
+        PNB_LAUNCH(k_partition, nblk(3 * n, BS * LEVEL_ITEMS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
         uint32_t *tmp = L; L = Ln; Ln = tmp;
     }
     if (lseg > 0) {

@@ -131,6 +131,45 @@ struct SegArgs {
     T *box;                           // [2*nsplit][6]
 };
 
+// ---- the sorting network of one level, 4 slots per thread -------------------------------------------------------
+// Slot e = 4 * tid + r lives in register r of thread tid: compare-exchange partners at strides 1 and 2 are in the same
+// thread, at strides 4 .. 64 in another lane of the same warp (one shuffle per register), at strides >= 128 in another
+// warp (those stages go through shared memory).  `up` for a pair: ascending iff bit k2 of the slot index inside its
+// node is clear (node size m; for k2 == m every pair is ascending).  Equal keys never swap.
+template <typename T>
+__device__ __forceinline__ void cex(T &ka, int &ia, T &kb, int &ib, bool up)
+{
+    const bool sw = up ? (ka > kb) : (ka < kb);
+    if (sw) { const T t = ka; ka = kb; kb = t; const int u = ia; ia = ib; ib = u; }
+}
+template <typename T>
+__device__ __forceinline__ void reg_stages(T (&K)[4], int (&I)[4], int e0, int k2, int jstart, int mmask)
+{
+    for (int j = jstart; j >= 4; j >>= 1) {
+        const int lm = j >> 2;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = e0 + r;
+            const bool up = ((e & mmask) & k2) == 0, upper = (e & j) != 0;
+            const T kb = __shfl_xor_sync(0xffffffffu, K[r], lm);
+            const int ib = __shfl_xor_sync(0xffffffffu, I[r], lm);
+            const bool take_min = up != upper;
+            const bool sw = take_min ? (kb < K[r]) : (kb > K[r]);
+            if (sw) { K[r] = kb; I[r] = ib; }
+        }
+    }
+    if (jstart >= 2) {
+        const bool up0 = ((e0 & mmask) & k2) == 0, up1 = (((e0 + 1) & mmask) & k2) == 0;
+        cex(K[0], I[0], K[2], I[2], up0);
+        cex(K[1], I[1], K[3], I[3], up1);
+    }
+    {
+        const bool up0 = ((e0 & mmask) & k2) == 0, up2 = (((e0 + 2) & mmask) & k2) == 0;
+        cex(K[0], I[0], K[1], I[1], up0);
+        cex(K[2], I[2], K[3], I[3], up2);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__((32 << SegCfg<T>::LSEG) / 4) k_build_segment(SegArgs<T> a)
 {
@@ -143,56 +182,63 @@ __global__ void __launch_bounds__((32 << SegCfg<T>::LSEG) / 4) k_build_segment(S
     T *py = px + SEG, *pz = py + SEG, *sk = pz + SEG;
     U *sbox = reinterpret_cast<U *>(sk + SEG);       // [MAXSUB][6]
     uint16_t *perm = reinterpret_cast<uint16_t *>(sbox + MAXSUB * 6);
-    uint8_t *axis = reinterpret_cast<uint8_t *>(perm + SEG);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int segn = 32 << a.lseg;                   // slots of this segment (<= SEG)
     const int64_t base = (int64_t)blockIdx.x * segn;
     const int cnt = (int)max((int64_t)0, min((int64_t)segn, a.n - base));
     const int ltop = a.levels - a.lseg;              // depth of the segment roots
     const T inf = Ord<T>::inf();
+    const int e0 = 4 * tid;                          // this thread's slots: e0 .. e0 + 3
 
-    for (int i = tid; i < segn; i += NT) {
+    for (int i = tid; i < SEG; i += NT) {
         if (i < cnt) {
             const uint32_t id = a.ids[base + i];
             px[i] = a.cols[id]; py[i] = a.cols[a.n + id]; pz[i] = a.cols[2 * a.n + id];
         } else {
             px[i] = py[i] = pz[i] = inf;             // padding sorts to the end and is skipped by the bounds
         }
-        perm[i] = (uint16_t)i;
     }
+    T K[4];
+    int I[4];                                        // local particle held by each slot (>= cnt: padding)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) I[r] = e0 + r;
     __syncthreads();
 
     for (int l = 0; l <= a.lseg; ++l) {
         const int m = segn >> l;                     // slots per node of this level
         const int nsub = 1 << l;
         const bool leaf = l == a.lseg;
-        // 1. tight bounds of every node of the level (leaf level: straight to global memory)
+        const int node_of_thread = e0 >> (5 + a.lseg - l);
+        // 1. tight bounds of every node of the level: per thread, then across the lanes that share the node
         if (!leaf) {
             for (int i = tid; i < nsub * 6; i += NT) sbox[i] = (i % 6) < 3 ? ~(U)0 : (U)0;
             __syncthreads();
         }
-        for (int g = warp; g < segn / 32; g += NT / 32) {
-            const int li = perm[g * 32 + lane];
-            const bool valid = li < cnt;
-            T mn[3], mx[3];
-            mn[0] = valid ? px[li] : inf; mn[1] = valid ? py[li] : inf; mn[2] = valid ? pz[li] : inf;
-            mx[0] = valid ? px[li] : -inf; mx[1] = valid ? py[li] : -inf; mx[2] = valid ? pz[li] : -inf;
+        T mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
+        for (int r = 0; r < 4; ++r) {
+            const int li = I[r];
+            if (li < cnt) {
+                const T x = px[li], y = py[li], z = pz[li];
+                mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z);
+                mx[0] = fmax(mx[0], x); mx[1] = fmax(mx[1], y); mx[2] = fmax(mx[2], z);
+            }
+        }
+        const int group = min(32, m >> 2);            // lanes per node inside a warp (a power of two >= 8)
+        for (int o = group >> 1; o; o >>= 1)
 #pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-                    mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
-                }
+            for (int d = 0; d < 3; ++d) {
+                mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+                mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+            }
+        if (e0 < segn && (lane & (group - 1)) == 0) {
             if (leaf) {
-                if (lane < 6) {
-                    const int64_t node = a.nsplit + (int64_t)blockIdx.x * (segn / 32) + g;
-                    const T v = lane == 0 ? mn[0] : lane == 1 ? mn[1] : lane == 2 ? mn[2] : lane == 3 ? mx[0] : lane == 4 ? mx[1] : mx[2];
-                    a.box[node * 6 + lane] = v;
-                }
-            } else if (lane == 0) {
-                U *b = sbox + (g >> (a.lseg - l)) * 6;
+                const int64_t node = a.nsplit + (int64_t)blockIdx.x * (segn / 32) + (e0 >> 5);
+                T *b = a.box + node * 6;
+                b[0] = mn[0]; b[1] = mn[1]; b[2] = mn[2]; b[3] = mx[0]; b[4] = mx[1]; b[5] = mx[2];
+            } else {
+                U *b = sbox + node_of_thread * 6;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     atomicMin(&b[d], (U)Ord<T>::enc(mn[d]));
@@ -202,53 +248,60 @@ __global__ void __launch_bounds__((32 << SegCfg<T>::LSEG) / 4) k_build_segment(S
         }
         if (leaf) break;
         __syncthreads();
-        // 2. node bounds out, split axis = longest extent of the tight box
-        for (int s = tid; s < nsub; s += NT) {
-            T mn[3], mx[3];
+        // 2. node bounds out (one thread per node), split axis = longest extent of the tight box
+        int axis = 0;
+        if (e0 < segn) {
+            T bmn[3], bmx[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { mn[d] = Ord<T>::dec(sbox[s * 6 + d]); mx[d] = Ord<T>::dec(sbox[s * 6 + 3 + d]); }
-            const int64_t node = ((int64_t)1 << (ltop + l)) + (int64_t)blockIdx.x * nsub + s;
-            T *b = a.box + node * 6;
-            b[0] = mn[0]; b[1] = mn[1]; b[2] = mn[2]; b[3] = mx[0]; b[4] = mx[1]; b[5] = mx[2];
-            int d = 0;
-            if (mx[1] - mn[1] > mx[d] - mn[d]) d = 1;
-            if (mx[2] - mn[2] > mx[d] - mn[d]) d = 2;
-            axis[s] = (uint8_t)d;
+            for (int d = 0; d < 3; ++d) { bmn[d] = Ord<T>::dec(sbox[node_of_thread * 6 + d]); bmx[d] = Ord<T>::dec(sbox[node_of_thread * 6 + 3 + d]); }
+            if (bmx[1] - bmn[1] > bmx[axis] - bmn[axis]) axis = 1;
+            if (bmx[2] - bmn[2] > bmx[axis] - bmn[axis]) axis = 2;
+            if ((e0 & (m - 1)) == 0) {
+                const int64_t node = ((int64_t)1 << (ltop + l)) + (int64_t)blockIdx.x * nsub + node_of_thread;
+                T *b = a.box + node * 6;
+                b[0] = bmn[0]; b[1] = bmn[1]; b[2] = bmn[2]; b[3] = bmx[0]; b[4] = bmx[1]; b[5] = bmx[2];
+            }
         }
-        __syncthreads();
         // 3. sort every node's slots by the coordinate along its axis: the lower half is the lower child
-        for (int i = tid; i < segn; i += NT) {
-            const int d = axis[i >> (5 + a.lseg - l)], li = perm[i];
-            sk[i] = d == 0 ? px[li] : d == 1 ? py[li] : pz[li];
-        }
-        __syncthreads();
-        for (int k2 = 2; k2 <= m; k2 <<= 1)
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const T *pc = axis == 0 ? px : axis == 1 ? py : pz;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) K[r] = (e0 < segn && I[r] < SEG) ? pc[I[r]] : inf;
+        const int mmask = m - 1;
+        for (int k2 = 2; k2 <= min(m, 128); k2 <<= 1) reg_stages<T>(K, I, e0, k2, k2 >> 1, mmask);
+        for (int k2 = 256; k2 <= m; k2 <<= 1) {
+            __syncthreads();                              // (sbox and the previous round's reads are done with)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { sk[e0 + r] = K[r]; perm[e0 + r] = (uint16_t)I[r]; }
+            __syncthreads();
+            for (int j = k2 >> 1; j >= 128; j >>= 1) {
                 for (int t = tid; t < segn / 2; t += NT) {
                     const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const int p = i | j;
-                    const bool up = ((i & (m - 1)) & k2) == 0;
+                    const bool up = ((i & mmask) & k2) == 0;
                     const T ka = sk[i], kb = sk[p];
                     if ((ka > kb) == up && ka != kb) {
                         sk[i] = kb; sk[p] = ka;
                         const uint16_t t16 = perm[i]; perm[i] = perm[p]; perm[p] = t16;
                     }
                 }
-                // pairs with j <= 32 stay inside the 64-slot blocks a warp owns (t -> i maps aligned runs of 32
-                // pair indices onto aligned runs of 64 slots): a block barrier is needed only around wider strides
-                const int jn = j > 1 ? (j >> 1) : k2;
-                if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
+                __syncthreads();
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { K[r] = sk[e0 + r]; I[r] = perm[e0 + r]; }
+            reg_stages<T>(K, I, e0, k2, 64, mmask);
+        }
         __syncthreads();
     }
-    __syncthreads();
     // tree-ordered structure of arrays
-    for (int i = tid; i < cnt; i += NT) {
-        const int li = perm[i];
-        const uint32_t id = a.ids[base + li];
-        a.x[base + i] = px[li]; a.y[base + i] = py[li]; a.z[base + i] = pz[li];
-        a.order[base + i] = id;
-        if (a.mass) a.m[base + i] = a.mass[id];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = e0 + r, li = I[r];
+        if (e < cnt) {
+            const uint32_t id = a.ids[base + li];
+            a.x[base + e] = px[li]; a.y[base + e] = py[li]; a.z[base + e] = pz[li];
+            a.order[base + e] = id;
+            if (a.mass) a.m[base + e] = a.mass[id];
+        }
     }
 }
 
@@ -279,7 +332,7 @@ template <typename T>
 size_t segment_smem()
 {
     constexpr int SEG = 32 << SegCfg<T>::LSEG;
-    return (size_t)SEG * 4 * sizeof(T) + (size_t)(SEG / 64) * 6 * sizeof(typename Ord<T>::U) + (size_t)SEG * 2 + SEG / 64 + 16;
+    return (size_t)SEG * 4 * sizeof(T) + (size_t)(SEG / 64) * 6 * sizeof(typename Ord<T>::U) + (size_t)SEG * 2 + 16;
 }
 
 // The lower `lseg` levels of the device tree, one CTA per sub-tree: `ids` lists the particles (file indices) so
