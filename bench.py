@@ -51,12 +51,15 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def source_hash():
-    """Hash of the sources the dominant kernels are compiled from; ncu-derived constants are only quoted for
-    the sources they were captured on."""
+KERNEL_SOURCES = {"k_knn": ("knn.cu", "traverse.cuh"), "k_render_tiles": ("render.cu",)}
+
+
+def source_hash(kernel="k_knn"):
+    """Hash of the sources a kernel is compiled from; ncu-derived constants are only quoted for the sources they
+    were captured on."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("knn.cu", "traverse.cuh", "tree_morton.cu", "render.cu"):
+    for f in KERNEL_SOURCES[kernel]:
         with open(os.path.join(ROOT, "pynbody_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -64,12 +67,13 @@ def source_hash():
 
 def load_ncu(key):
     """A per-launch figure from the committed ncu capture (profiles/r2_ncu_constants.json: DRAM bytes, issue-slot
-    utilisation, warp instructions per particle), or None when the capture was taken on other sources --
-    stale constants are not printed."""
+    utilisation, warp instructions per particle; keys are "<kernel>:<dtype>:<n_side>:<what>"), or None when the capture
+    was taken on other sources of that kernel -- stale constants are not printed."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as f:
             d = json.load(f)
-        if d.get("source_hash") != source_hash():
+        kernel = key.split(":")[0]
+        if d.get("source_hashes", {}).get(kernel) != source_hash(kernel):
             return None
         return d.get(key)
     except Exception:
@@ -88,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -451,7 +455,7 @@ def run_ours(args):
                      "neighbour_interactions_per_s": n * K_NEIGHBOURS / (knn_kernel_ms * 1e-3),
                      "ncu_issue_active_pct": load_ncu(f"k_knn:{args.dtype}:{args.n_side}:issue_active_pct"),
                      "ncu_warp_inst_per_particle": load_ncu(f"k_knn:{args.dtype}:{args.n_side}:warp_inst_per_particle"),
-                     "ncu_source_hash": source_hash(),
+                     "ncu_source_hash": source_hash("k_knn"),
                      "note": "irregular tree search: bound by instruction issue (on-chip neighbour-queue updates), not by "
                              "HBM bytes (SURVEY.md 8d); traffic / issue-slot figures come from the committed ncu capture "
                              "(profiles/r2_ncu_constants.json) and are null unless it was taken on these very sources"},

@@ -43,3 +43,19 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_ncu_constants_are_quoted_only_for_the_sources_they_were_captured_on(tmp_path, monkeypatch):
+    """roofline.traffic & co. come from a committed ncu capture; bench.py must refuse to print them once the kernel
+    sources have changed (a stale constant is worse than a null)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    const = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")))
+    key = "k_knn:f64:256:dram_bytes"
+    assert key in const and const[key] > 0
+    if const["source_hashes"]["k_knn"] == bench.source_hash("k_knn"):
+        assert bench.load_ncu(key) == const[key]
+    else:
+        assert bench.load_ncu(key) is None
+    monkeypatch.setattr(bench, "source_hash", lambda kernel="k_knn": "0" * 16)
+    assert bench.load_ncu(key) is None
