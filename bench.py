@@ -218,11 +218,20 @@ def run_reference(args):
     if rank != 0:
         return
     dtype = np.float64 if args.dtype == "f64" else np.float32
-    res = cpu_arm(args.n_side, dtype, args.steps, CPU_BUDGET_S, 0 if args.no_render else args.render_res)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if world > 1:
+        # the N-GPU arm searches ONE global box of ~N x n_side^3 particles: so does this arm, on the host cores (same
+        # recipe and size; the GPU arm draws its Gaussian field on the device, so the realisation differs).  One pass
+        # of 134 M particles takes minutes: no render leg here.
+        res = cpu_arm(global_side(args, world), dtype, args.steps, CPU_BUDGET_S, 0)
+        cfg = distributed_config(args, world)
+    else:
+        res = cpu_arm(args.n_side, dtype, args.steps, CPU_BUDGET_S, 0 if args.no_render else args.render_res)
+        cfg = workload_config(args)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args),
+            "config": cfg,
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "steps_timed": res["passes"], "gpu_launches": 0}
@@ -231,6 +240,24 @@ def run_reference(args):
         line["render"] = {"image": {"resolution": args.render_res, "ms": r["seconds"] * 1e3, "mpix_per_s": r["value"],
                                     "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}}}
     print(json.dumps(line))
+
+
+def global_side(args, world):
+    """Side of the ONE global box the N-GPU arms run: about N x n_side^3 particles (weak scaling)."""
+    return int(round((world * args.n_side ** 3) ** (1.0 / 3.0)))
+
+
+def distributed_config(args, world):
+    side = global_side(args, world)
+    n_total = side ** 3
+    cfg = workload_config(args)
+    cfg["workload"] = (f"C4/C5-style: ONE global {n_total}-particle ({side}^3) clustered Zel'dovich-like periodic box "
+                       f"decomposed over {world} GPUs (~{n_total // world} particles per GPU), sim['rho'] = domain decomposition + "
+                       f"tree build + smooth + rho, k={K_NEIGHBOURS}, WendlandC2, {args.dtype}")
+    cfg["parallelism"] = (f"spatial domains x{world} (coordinate bisection), NCCL all-to-all particle routing + need-based halo "
+                          f"exchange + masked re-search; image = per-rank frames + NCCL reduce")
+    cfg["global_particles"] = n_total
+    return cfg
 
 
 def workload_config(args):
@@ -492,7 +519,7 @@ def run_ours_distributed(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dtype = np.float64 if args.dtype == "f64" else np.float32
     tsz = np.dtype(dtype).itemsize
-    side = int(round((world * args.n_side ** 3) ** (1.0 / 3.0)))
+    side = global_side(args, world)
     n_total = side ** 3
     pos, vel, mass = synth.zeldovich_box_device(side, 2, dtype, "cuda", rank, world)
     n_local = int(pos.shape[0])
@@ -593,14 +620,7 @@ def run_ours_distributed(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         knn_ms = kdmain.last_kernel_ms(0)
-        cfg = workload_config(args)
-        cfg["workload"] = (f"C4/C5-style: ONE global {n_total}-particle ({side}^3) clustered Zel'dovich-like periodic box "
-                           f"decomposed over {world} GPUs (~{n_total // world} particles per GPU), sim['rho'] = domain decomposition + "
-                           f"tree build + smooth + rho, k={K_NEIGHBOURS}, WendlandC2, {args.dtype}")
-        cfg["parallelism"] = (f"spatial domains x{world} (coordinate bisection), NCCL all-to-all particle routing + need-based halo "
-                              f"exchange + masked re-search; image = per-rank frames + NCCL reduce")
-        cfg["global_particles"] = n_total
-        cfg["per_rank_owned_boundary_halo"] = [[int(v) for v in s.tolist()] for s in allst]
+        cfg = distributed_config(args, world)          # (identical to the reference arm's config for the same N)
         line = {"metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": cfg,
@@ -611,6 +631,7 @@ def run_ours_distributed(args):
                              "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                              "peak_source": peak_src, "kernel_ms": knn_ms,
                              "note": "per-kernel roofline is reported by the N=1 run; see DESIGN.md"},
+                "per_rank_owned_boundary_halo": [[int(v) for v in st_.tolist()] for st_ in allst],
                 "stages_ms": stages, "render": render}
         print(json.dumps(line))
     dist.destroy_process_group()
