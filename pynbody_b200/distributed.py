@@ -258,11 +258,16 @@ def decompose(pos, boxsize, group=None, sample_per_rank=8192, seed=0):
         mn = torch.full((3,), float("inf"), dtype=dt, device=dev)
         mx = -mn
     if world > 1:
+        staged = dev.type == "cuda" and _staged(group)             # (gloo: device tensors cross through host memory)
+        if staged:
+            samp, mn, mx = samp.cpu(), mn.cpu(), mx.cpu()
         allsamp = [torch.empty_like(samp) for _ in range(world)]
         dist.all_gather(allsamp, samp, group=group)
         samp = torch.cat(allsamp)
         dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        if staged:
+            samp = samp.to(dev)
     samp = samp[~torch.isnan(samp[:, 0])].t().contiguous()          # [3][m]: one contiguous row per axis
     mn, mx = mn.cpu(), mx.cpu()
     periodic = boxsize is not None and boxsize > 0 and bool(((mx - mn) <= boxsize).all())
@@ -320,10 +325,18 @@ def _box_gap2(x, lo, hi, period):
 # ------------------------------------------------------------------------------------------------
 # collectives
 # ------------------------------------------------------------------------------------------------
+def _staged(group):
+    """True when device tensors have to cross the collective through host memory: the gloo backend (CPU tests, and the
+    single-GPU multi-rank test of the device kernels) has no all-to-all for CUDA tensors.  NCCL moves them directly."""
+    return dist.get_backend(group) == "gloo"
+
+
 def _alltoallv(per_dest, group=None):
     """Variable-size all-to-all: per_dest[r] goes to rank r; returns the list received from each rank."""
     world = dist.get_world_size(group)
     dev = per_dest[0].device
+    if dev.type == "cuda" and _staged(group):
+        return [t.to(dev) for t in _alltoallv([t.cpu() for t in per_dest], group)]
     counts = torch.tensor([t.shape[0] for t in per_dest], dtype=torch.int64, device=dev)
     rcounts = torch.empty_like(counts)
     dist.all_to_all_single(rcounts, counts, group=group)
@@ -337,6 +350,9 @@ def _alltoallv(per_dest, group=None):
 def _alltoall_rows(send, counts, group=None):
     """The same for rows that already lie destination-major in one tensor: (received rows, rows per source)."""
     dev = send.device
+    if dev.type == "cuda" and _staged(group):
+        recv, rc = _alltoall_rows(send.cpu(), counts, group)
+        return recv.to(dev), rc
     sc = torch.tensor(counts, dtype=torch.int64, device=dev)
     rcounts = torch.empty_like(sc)
     dist.all_to_all_single(rcounts, sc, group=group)
@@ -589,7 +605,7 @@ class DistributedKDTree:
         ms = getattr(self.tree1, "last_knn_ms", lambda: None)()
         if self.world == 1 or ms is None or not os.environ.get("PNB_DIST_COST_FEEDBACK"):
             return
-        mine = torch.tensor([ms / max(self.n_own, 1)], dtype=torch.float64, device=self.dev)
+        mine = torch.tensor([ms / max(self.n_own, 1)], dtype=torch.float64)     # (a host tensor: any backend gathers it)
         allc = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allc, mine, group=self.group)
         costs = [float(c.item()) for c in allc]
