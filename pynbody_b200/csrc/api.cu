@@ -124,21 +124,23 @@ void cache_free(void *p, size_t bytes)
     BlockCache &c = block_cache();
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.limit == 0) {
-        // idle blocks kept at most: PNB_CACHE_LIMIT_GB if set, else a quarter of the device's memory (torch's own
-        // caching allocator in the same process cannot reclaim what sits here; pnb_release_cached_memory() returns it)
+        // idle blocks kept at most: PNB_CACHE_LIMIT_GB if set, else HALF of the device's memory -- the working set of one
+        // step must fit or every step pays for cudaMalloc / cudaFree again (10^9 particles on 8 GPUs: 34 GB of neighbour
+        // lists + 15 GB of build and search buffers per rank; with a limit of a quarter the step took 719 instead of
+        // ~560 ms).  torch's own caching allocator in the same process cannot reclaim what sits here;
+        // pnb_release_cached_memory() returns it.
         size_t free_b = 0, total_b = 0;
-        c.limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 4 : (size_t)16 << 30;
+        c.limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 2 : (size_t)32 << 30;
         cudaGetLastError();
         if (const char *e = getenv("PNB_CACHE_LIMIT_GB")) {
             const double gb = atof(e);
             if (gb >= 0) c.limit = (size_t)(gb * 1073741824.0) + 1;
         }
     }
-    // A process that keeps changing its particle count would otherwise pile up idle blocks of ever new size
-    // classes: past the limit everything idle goes back to the driver (the next step re-allocates what it needs).
+    // Past the limit the block that is being released goes back to the driver; the blocks already cached stay (dropping
+    // the whole cache, as round 1 did, makes the NEXT step re-allocate everything).
     if (c.cached_bytes + bytes > c.limit) {
         cudaDeviceSynchronize();
-        c.trim_locked();
         cudaFree(p);
         return;
     }
