@@ -127,7 +127,7 @@ void cache_free(void *p, size_t bytes)
         // idle blocks kept at most: PNB_CACHE_LIMIT_GB if set, else HALF of the device's memory -- the working set of one
         // step must fit or every step pays for cudaMalloc / cudaFree again (10^9 particles on 8 GPUs: 34 GB of neighbour
         // lists + 15 GB of build and search buffers per rank; with a limit of a quarter the step took 719 instead of
-        // ~560 ms).  torch's own caching allocator in the same process cannot reclaim what sits here;
+        // 497 ms).  torch's own caching allocator in the same process cannot reclaim what sits here;
         // pnb_release_cached_memory() returns it.
         size_t free_b = 0, total_b = 0;
         c.limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 2 : (size_t)32 << 30;
