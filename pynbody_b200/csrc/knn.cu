@@ -48,7 +48,8 @@ __device__ unsigned long long g_stats[8];
 #define STAT(i, v)
 #endif
 
-constexpr int KNN_WARPS = 2;
+constexpr int KNN_WARPS = 2;          // k > 128: warps per block (several blocks per SM)
+constexpr int KNN_MAX_WARPS = 20;     // k <= 128: ONE block per SM with as many warps as its shared memory holds
 constexpr int MAXLOG = 10;              // k <= 1024
 
 template <typename T>
@@ -85,7 +86,47 @@ struct Queue {
     uint32_t top_hi, top_lo;  // double: exact high word; low word if lo_known
     bool lo_known;
     int etop;               // the root winner's leaf
+    uint32_t hb, wb;        // k <= 128: 32-bit shared-window addresses of this lane's leaf 0 / winner byte 0; both regions
+                            // are aligned to their size, so any leaf or node address is one logic operation away from
+                            // the leaf index (queue_replace_max_fast)
 };
+
+// ---- internal nodes of the tournament --------------------------------------------------------------------------
+// The node at height l (1 = parents of leaves) above leaves [a 2^l, (a+1) 2^l) sits at
+//   k <= 128 (depth known at compile time): in-order position (a << l) | (1 << (l-1))
+//   otherwise:                               heap position (K2 >> l) + a
+template <int LOGC>
+__device__ __forceinline__ int wpos(int K2, int l, int a)
+{
+    return LOGC >= 0 ? ((a << l) | (1 << (l - 1))) : ((K2 >> l) + a);
+}
+// byte offset of the winner byte at position pos from the lane's byte 0 (Queue::W).  Generic depth: [pos][lane].
+// Compile-time depth: four consecutive positions of one lane share a 32-bit word, [pos / 4][lane][pos % 4], so lane l
+// only ever touches bank l and the byte accesses of a replacement are free of bank conflicts whatever leaves the
+// lanes are working on ([pos][lane] put four lanes into each word: 1.7 G conflicts in 7 G wavefronts, ncu).
+template <int LOGC>
+__device__ __forceinline__ int wofs(int pos)
+{
+    return LOGC >= 0 ? (((pos >> 2) << 7) | (pos & 3)) : pos * 32;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
+// shared memory through 32-bit window addresses (no generic-address arithmetic in the insert path)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 // is d2 strictly below the current k-th distance?  (exact)
 template <typename W_t>
@@ -97,6 +138,15 @@ __device__ __forceinline__ bool below_top(Queue<double, W_t> &q, double d2)
     if (h != q.top_hi) return h < q.top_hi;         // non-negative doubles order like their bit patterns
     if (!q.lo_known) { q.top_lo = q.lo[q.etop * 32]; q.lo_known = true; }   // equal high words: rare
     return (uint32_t)__double2loint(d2) < q.top_lo;
+}
+// phase-A filter, evaluated by every lane for the query of lane i: can d2 be below that query's k-th distance?
+// (double: decided on the high words -- one shuffle instead of two, an integer compare; an upper bound of the exact test)
+template <typename W_t>
+__device__ __forceinline__ bool maybe_below(const Queue<float, W_t> &q, float d2, int i) { return d2 < __shfl_sync(FULL, q.top, i); }
+template <typename W_t>
+__device__ __forceinline__ bool maybe_below(const Queue<double, W_t> &q, double d2, int i)
+{
+    return (uint32_t)__double2hiint(d2) <= __shfl_sync(FULL, q.top_hi, i);
 }
 template <typename W_t>
 __device__ __forceinline__ float top_exact(Queue<float, W_t> &q) { return q.top; }
@@ -207,6 +257,124 @@ __device__ __forceinline__ void queue_replace_max(Queue<double, W_t> &q, double 
     q.etop = ce;
 }
 
+// ---- k <= 128: the same replacement with the address arithmetic stripped to one instruction per access ----------
+// Round-2 profile of the insert round (profiles/r2_knn_summary.txt): 140 SASS instructions, a third of them address
+// arithmetic (heap-position shifts per level, the shared window base rematerialised in every round).  Here the lane's
+// leaves live at hb | e*128 and its winner bytes at wb | pos*32 with pos in in-order layout, both regions aligned to
+// their size: the path node at height l is (e32 & ~mask_l) | wb (+ a constant folded into the access), its sibling is
+// that address with bit l flipped.
+template <int LOGC>
+struct PathAddr {
+    // swizzled offset of position p (compile-time): wofs<LOGC>(p)
+    static __device__ __forceinline__ constexpr uint32_t sw(uint32_t p) { return ((p >> 2) << 7) | (p & 3u); }
+    uint32_t t[LOGC > 0 ? LOGC : 1];         // t[l-1]: lane's winner byte 0 | swizzled first leaf under the path node at height l
+    __device__ __forceinline__ PathAddr(uint32_t wb, uint32_t e)
+    {
+        const uint32_t S = ((e & ~3u) << 5) | (e & 3u);                 // sw(e)
+#pragma unroll
+        for (int l = 1; l <= LOGC; ++l) t[l - 1] = (S & ~sw((1u << l) - 1u)) | wb;
+    }
+    // (the constants are folded into the accesses' immediate offsets)
+    __device__ __forceinline__ uint32_t own(int l) const { return t[l - 1] + sw(1u << (l - 1)); }
+    __device__ __forceinline__ uint32_t sibling(int l) const { return (t[l - 1] ^ sw(1u << l)) + sw(1u << (l - 1)); }   // l < LOGC
+};
+
+template <int LOGC, bool WITH_IDX>
+__device__ __forceinline__ void queue_replace_max_fast(Queue<float, uint8_t> &q, float v, uint32_t id)
+{
+    const uint32_t e = (uint32_t)q.etop;
+    const uint32_t leaf = q.hb | (e << 7);
+    sts_u32(leaf, __float_as_uint(v));
+    if (WITH_IDX) q.hi[e * 32] = id;
+    const PathAddr<LOGC> pa(q.wb, e);
+    uint32_t si[LOGC > 0 ? LOGC : 1];
+    float sv[LOGC > 0 ? LOGC : 1];
+    si[0] = e ^ 1u;
+#pragma unroll
+    for (int l = 1; l < LOGC; ++l) si[l] = lds_u8(pa.sibling(l));
+    if (LOGC > 0) sv[0] = __uint_as_float(lds_u32(leaf ^ 128u));
+#pragma unroll
+    for (int l = 1; l < LOGC; ++l) sv[l] = __uint_as_float(lds_u32(q.hb + (si[l] << 7)));
+    float cv = v;
+    uint32_t ce = e;
+#pragma unroll
+    for (int l = 0; l < LOGC; ++l) {
+        if (sv[l] > cv) { cv = sv[l]; ce = si[l]; }
+        sts_u8(pa.own(l + 1), ce);
+    }
+    q.top = cv;
+    q.etop = (int)ce;
+}
+
+template <int LOGC, bool WITH_IDX>
+__device__ __forceinline__ void queue_replace_max_fast(Queue<double, uint8_t> &q, double v, uint32_t id)
+{
+    const uint32_t e = (uint32_t)q.etop;
+    const uint32_t vhi = (uint32_t)__double2hiint(v), vlo = (uint32_t)__double2loint(v);
+    const uint32_t leaf = q.hb | (e << 7);
+    sts_u32(leaf, vhi);
+    q.lo[e * 32] = vlo;
+    if (WITH_IDX) q.hi[e * 32] = id;
+    const PathAddr<LOGC> pa(q.wb, e);
+    uint32_t si[LOGC > 0 ? LOGC : 1], win[LOGC > 0 ? LOGC : 1], sk[LOGC > 0 ? LOGC : 1];
+    si[0] = e ^ 1u;
+#pragma unroll
+    for (int l = 1; l < LOGC; ++l) si[l] = lds_u8(pa.sibling(l));
+    if (LOGC > 0) sk[0] = lds_u32(leaf ^ 128u);
+#pragma unroll
+    for (int l = 1; l < LOGC; ++l) sk[l] = lds_u32(q.hb + (si[l] << 7));
+    // replay on the high words alone, without branches; equal high words anywhere on the path (rare) send the lane
+    // through the exact replay below
+    uint32_t ck = vhi, ce = e;
+    bool tie = false;
+#pragma unroll
+    for (int l = 0; l < LOGC; ++l) {
+        const bool gt = sk[l] > ck;
+        tie |= sk[l] == ck;
+        ck = gt ? sk[l] : ck;
+        ce = gt ? si[l] : ce;
+        win[l] = ce;
+    }
+    q.lo_known = false;                             // (fetched on demand: below_top on equal high words, top_exact)
+    if (tie) {
+        uint32_t clo = vlo;
+        bool clo_known = true;
+        ck = vhi; ce = e;
+#pragma unroll
+        for (int l = 0; l < LOGC; ++l) {
+            bool gt = sk[l] > ck;
+            if (sk[l] == ck) {                      // decide on the exact 64-bit values
+                if (!clo_known) { clo = q.lo[ce * 32]; clo_known = true; }
+                gt = q.lo[si[l] * 32] > clo;
+            }
+            if (gt) { ck = sk[l]; ce = si[l]; clo_known = false; }
+            win[l] = ce;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < LOGC; ++l) sts_u8(pa.own(l + 1), win[l]);
+    q.top_hi = ck;
+    q.top = __hiloint2double((int)ck, -1);          // upper bound for pruning (kept in registers: deriving it from top_hi
+                                                    // at the points of use makes nvcc guard every warp vote with BRA.DIV)
+    q.etop = (int)ce;
+}
+
+// depth known at compile time (k <= 128): the stripped path; otherwise the generic one
+template <typename T, typename W_t, int LOGC, bool WITH_IDX>
+struct Replace {
+    static_assert(LOGC < 0, "compile-time depths use the in-order winner layout (queue_replace_max_fast)");
+    static __device__ __forceinline__ void run(Queue<T, W_t> &q, T v, uint32_t id) { queue_replace_max<W_t, LOGC, WITH_IDX>(q, v, id); }
+};
+template <typename T, bool WITH_IDX> struct Replace<T, uint8_t, 5, WITH_IDX> {
+    static __device__ __forceinline__ void run(Queue<T, uint8_t> &q, T v, uint32_t id) { queue_replace_max_fast<5, WITH_IDX>(q, v, id); }
+};
+template <typename T, bool WITH_IDX> struct Replace<T, uint8_t, 6, WITH_IDX> {
+    static __device__ __forceinline__ void run(Queue<T, uint8_t> &q, T v, uint32_t id) { queue_replace_max_fast<6, WITH_IDX>(q, v, id); }
+};
+template <typename T, bool WITH_IDX> struct Replace<T, uint8_t, 7, WITH_IDX> {
+    static __device__ __forceinline__ void run(Queue<T, uint8_t> &q, T v, uint32_t id) { queue_replace_max_fast<7, WITH_IDX>(q, v, id); }
+};
+
 // ---- start of a search: the first k candidates go straight into the leaves, then the tree is built once ----
 __device__ __forceinline__ void leaf_store(Queue<float, uint8_t> &q, int e, float d2) { q.hd[e * 32] = d2; }
 __device__ __forceinline__ void leaf_store(Queue<float, uint16_t> &q, int e, float d2) { q.hd[e * 32] = d2; }
@@ -242,18 +410,21 @@ template <typename T, typename W_t, int LOGC>
 __device__ __forceinline__ void queue_build(Queue<T, W_t> &q)
 {
     const int K2 = LOGC >= 0 ? (1 << LOGC) : q.K2;
+    const int LOG = LOGC >= 0 ? LOGC : q.LOG;
     if (K2 == 1) { set_top_from_leaf(q, 0); return; }
 #pragma unroll 4
-    for (int node = K2 - 1; node >= K2 / 2; --node) {      // parents of leaves
-        const int a = 2 * node - K2, b = a + 1;
-        q.W[node * 32] = (W_t)(leaf_greater(q, b, a) ? b : a);
+    for (int a = 0; a < K2 / 2; ++a) {                      // parents of leaves
+        const int x = 2 * a, y = x + 1;
+        q.W[wofs<LOGC>(wpos<LOGC>(K2, 1, a))] = (W_t)(leaf_greater(q, y, x) ? y : x);
     }
+    for (int l = 2; l <= LOG; ++l) {
 #pragma unroll 4
-    for (int node = K2 / 2 - 1; node >= 1; --node) {
-        const int a = (int)q.W[2 * node * 32], b = (int)q.W[(2 * node + 1) * 32];
-        q.W[node * 32] = (W_t)(leaf_greater(q, b, a) ? b : a);
+        for (int a = 0; a < (K2 >> l); ++a) {
+            const int x = (int)q.W[wofs<LOGC>(wpos<LOGC>(K2, l - 1, 2 * a))], y = (int)q.W[wofs<LOGC>(wpos<LOGC>(K2, l - 1, 2 * a + 1))];
+            q.W[wofs<LOGC>(wpos<LOGC>(K2, l, a))] = (W_t)(leaf_greater(q, y, x) ? y : x);
+        }
     }
-    set_top_from_leaf(q, (int)q.W[32]);
+    set_top_from_leaf(q, (int)q.W[wofs<LOGC>(wpos<LOGC>(K2, LOG, 0))]);
 }
 
 template <typename T, typename W_t, int LOGC, bool WITH_IDX>
@@ -261,8 +432,10 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
                                                  Queue<T, W_t> &q, T *tile, int lane, bool wide, T qx, T qy, T qz,
                                                  int &filled, int k, bool active)
 {
-    const int start = tv.bucket_start[bucket];
-    const int cnt = tv.bucket_start[bucket + 1] - start;
+    // every builder makes bucket j the ranks [32 j, 32 j + 32) cut at n (bucket_start[j] = min(n, 32 j)): computed, not
+    // loaded -- a dependent global load less in front of every candidate tile
+    const int start = (int)min(tv.n, (int64_t)32 * bucket);
+    const int cnt = (int)min(tv.n, (int64_t)32 * (bucket + 1)) - start;
     __syncwarp();                                   // previous tile fully consumed
     if (lane < cnt) {
         tile[lane] = tv.x[start + lane];
@@ -298,13 +471,14 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
         const T cx = lane < cnt ? tile[lane] : (T)0, cy = lane < cnt ? tile[32 + lane] : (T)0,
                 cz = lane < cnt ? tile[64 + lane] : (T)0;
         unsigned todo = __ballot_sync(FULL, pass);
+        const bool valid = lane < cnt;
         while (todo) {
             const int i = __ffs(todo) - 1;
             todo &= todo - 1;
             const T ux = __shfl_sync(FULL, sx, i), uy = __shfl_sync(FULL, sy, i), uz = __shfl_sync(FULL, sz, i);
-            const T ut = __shfl_sync(FULL, top0, i);
             const T d2 = dist2<T>(ux, uy, uz, cx, cy, cz);
-            const unsigned row = __ballot_sync(FULL, lane < cnt && (sizeof(T) == 8 ? d2 <= ut : d2 < ut));   // (double: an upper bound)
+            const bool mb = maybe_below(q, d2, i);                 // (contains a shuffle: every lane takes part)
+            const unsigned row = __ballot_sync(FULL, valid & mb);
             if (lane == i) mask = row;
         }
     } else {                                        // some lane's shift is ambiguous here: image per particle
@@ -332,7 +506,7 @@ __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t 
             mask &= mask - 1;
             const T d2 = wide ? dist2_nearest<T>(qx, qy, qz, tile[j], tile[32 + j], tile[64 + j], tv.period)
                               : dist2<T>(sx, sy, sz, tile[j], tile[32 + j], tile[64 + j]);
-            if (below_top(q, d2)) { queue_replace_max<W_t, LOGC, WITH_IDX>(q, d2, (uint32_t)(start + j)); ins = true; }
+            if (below_top(q, d2)) { Replace<T, W_t, LOGC, WITH_IDX>::run(q, d2, (uint32_t)(start + j)); ins = true; }
         }
 #ifdef KNN_STATS
         unsigned b = __ballot_sync(FULL, ins);
@@ -357,7 +531,7 @@ __device__ __forceinline__ float init_top(float) { return 3.0e38f; }
 __device__ __forceinline__ double init_top(double) { return __hiloint2double(0x7fe00000, 0); }
 
 template <typename T, typename W_t, int LOGC, bool WITH_IDX, bool FUSE_RHO, bool PERIODIC>
-__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
+__global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 32, 1) k_knn(KnnArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename KeyOf<T>::type Key;
@@ -366,15 +540,34 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
     const int warps = blockDim.x >> 5;
     const int k = a.k, LOG = LOGC >= 0 ? LOGC : a.LOG, K2 = 1 << LOG;
 
-    unsigned char *base = smem_raw + knn_smem_per_warp<T, W_t, WITH_IDX>(K2) * wib;
     Queue<T, W_t> q;
     q.LOG = LOG; q.K2 = K2;
-    q.hd = reinterpret_cast<Key *>(base) + lane;
-    unsigned char *after = base + (size_t)K2 * 32 * sizeof(Key);
     q.hi = nullptr;
-    q.W = reinterpret_cast<W_t *>(after) + lane;
-    after += (size_t)K2 * 32 * sizeof(W_t);
-    T *tile = reinterpret_cast<T *>(after);       // 16-byte aligned: every array above is a multiple of 32 bytes
+    q.hb = q.wb = 0;
+    T *tile;
+    if (LOGC >= 0) {
+        // one block per SM: [pad][leaves of every warp][winner bytes of every warp][candidate tiles]; the leaves start
+        // at a multiple of one warp's leaf region (K2 * 128 bytes) in the shared window, so every warp's leaf and winner
+        // regions are aligned to their own size (queue_replace_max_fast)
+        static_assert(LOGC < 0 || sizeof(Key) == 4, "leaf stride");
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+        const uint32_t A = (uint32_t)K2 * 128u;
+        const uint32_t pad = (A - (sbase & (A - 1u))) & (A - 1u);
+        unsigned char *leaves = smem_raw + pad + (size_t)wib * A;
+        unsigned char *wins = smem_raw + pad + (size_t)warps * A + (size_t)wib * K2 * 32;
+        q.hd = reinterpret_cast<Key *>(leaves) + lane;
+        q.W = reinterpret_cast<W_t *>(wins) + lane * 4;      // swizzled winner bytes: wofs()
+        q.hb = sbase + pad + (uint32_t)wib * A + (uint32_t)lane * 4u;
+        q.wb = sbase + pad + (uint32_t)warps * A + (uint32_t)wib * (uint32_t)K2 * 32u + (uint32_t)lane * 4u;
+        tile = reinterpret_cast<T *>(smem_raw + pad + (size_t)warps * (A + (size_t)K2 * 32)) + (size_t)wib * 96;
+    } else {
+        unsigned char *base = smem_raw + knn_smem_per_warp<T, W_t, WITH_IDX>(K2) * wib;
+        q.hd = reinterpret_cast<Key *>(base) + lane;
+        unsigned char *after = base + (size_t)K2 * 32 * sizeof(Key);
+        q.W = reinterpret_cast<W_t *>(after) + lane;
+        after += (size_t)K2 * 32 * sizeof(W_t);
+        tile = reinterpret_cast<T *>(after);      // 16-byte aligned: every array above is a multiple of 32 bytes
+    }
     q.lo = a.lo_scratch ? a.lo_scratch + ((size_t)blockIdx.x * warps + wib) * (size_t)K2 * 32 + lane : nullptr;
     const T L = tv.period;
 
@@ -384,8 +577,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         const int64_t bucket = (int64_t)__shfl_sync(FULL, b64, 0);
         if (bucket >= tv.nsplit) return;
 
-        const int start = tv.bucket_start[bucket];
-        const int cnt = tv.bucket_start[bucket + 1] - start;
+        const int start = (int)min(tv.n, (int64_t)32 * bucket);
+        const int cnt = (int)min(tv.n, (int64_t)32 * (bucket + 1)) - start;
         const bool active = lane < cnt && (!tv.query_mask || tv.query_mask[start + lane]);
         if (!__any_sync(FULL, active)) continue;    // no query of this bucket is selected
         T qx = 0, qy = 0, qz = 0;
@@ -417,6 +610,16 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
         // be pushed out again (CPU model of the walk, scripts/knn_walk_model.py: -10 % buckets visited, -18 % insert
         // rounds).  The result does not depend on the order (exact ties at the k-th distance aside).
         int64_t cell = tv.nsplit + bucket;
+        // the walk tests one sibling per level on the way up: lane l asks for the bounds of the one l levels up now
+        // (a 48-byte record can straddle two lines)
+        {
+            const int64_t up = cell >> lane;
+            if (lane < 31 && up > 1) {
+                const T *b = tv.box + (up ^ 1) * 6;
+                prefetch_l1(b);
+                prefetch_l1(b + 5);
+            }
+        }
         while (cell != 1) {
             int64_t cp = cell ^ 1;
             int depth = 0;
@@ -441,6 +644,18 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                                                                  PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
                     } else {
                         const Box6<T> bl = load_box(tv.box, 2 * cp), br = load_box(tv.box, 2 * cp + 1);
+                        // one level ahead, by otherwise idle lanes: the four grandchildren's bounds (contiguous), or,
+                        // under a parent of leaves, the coordinates of both candidate buckets (contiguous per axis)
+                        if (4 * cp < 2 * tv.nsplit) {
+                            if (2 * cp < tv.nsplit) {
+                                if (lane < 3) prefetch_l1(reinterpret_cast<const char *>(tv.box + 4 * cp * 6) + min(lane * 96, 4 * 6 * (int)sizeof(T) - 1));
+                            } else if (lane < 12) {
+                                const int ax = lane >> 2;
+                                const T *c = ax == 0 ? tv.x : (ax == 1 ? tv.y : tv.z);
+                                const int64_t first = 32 * (2 * cp - tv.nsplit) + (lane & 3) * (128 / (int)sizeof(T));
+                                if (first < tv.n && ((lane & 3) * 128 < 64 * (int)sizeof(T))) prefetch_l1(c + first);
+                            }
+                        }
                         STAT(5, 2);
                         T lx_, ly_, lz_, rx_, ry_, rz_;
                         const T gl = box_gap2<T, PERIODIC>(bl, qx, qy, qz, L, lx_, ly_, lz_);
@@ -500,11 +715,18 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn(KnnArgs<T> a)
                 const T norm = (T)(0.31830988618379067154 * (double)ih * (double)ih2);
                 const T m = (T)a.uniform_mass;
                 T rho = 0;
-                for (int e = 0; e < k; ++e) {
-                    T q2 = queue_value(q, e) * ih2;
-                    T w = (T)kern_w(a.kernel_id, a.wendland_self, q2);
-                    w *= norm;
-                    rho += w * m;
+                for (int e0 = 0; e0 < k; e0 += 8) {                 // eight queue entries in flight (float64: their low
+                    T d2v[8];                                       // words come from the L2-resident scratch)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) d2v[u] = e0 + u < k ? queue_value(q, e0 + u) : (T)0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (e0 + u >= k) break;
+                        T q2 = d2v[u] * ih2;
+                        T w = (T)kern_w(a.kernel_id, a.wendland_self, q2);
+                        w *= norm;
+                        rho += w * m;
+                    }
                 }
                 a.rho_t[p] = rho;
             }
@@ -531,11 +753,21 @@ static void launch_knn_p(Tree &t, KnnArgs<T> &a)
 {
     auto kern = k_knn<T, W_t, LOGC, WITH_IDX, FUSE_RHO, PERIODIC>;
     const int K2 = 1 << a.LOG;
-    // two warps per block unless one warp's queues already need more than half the shared memory
     const size_t per_warp = knn_smem_per_warp<T, W_t, WITH_IDX>(K2);
-    const int warps = per_warp * KNN_WARPS <= 227 * 1024 ? KNN_WARPS : 1;
-    const size_t smem = per_warp * warps;
-    if (smem > 227 * 1024)
+    int warps;
+    size_t smem;
+    if (LOGC >= 0) {
+        // one block per SM; up to K2 * 128 bytes of alignment padding in front (see k_knn)
+        const size_t pad = (size_t)K2 * 128;
+        warps = (int)std::min<size_t>(KNN_MAX_WARPS, (227 * 1024 - pad) / per_warp);
+        if (g_opt_knn_blocks_per_sm > 0) warps = std::min(warps, 2 * g_opt_knn_blocks_per_sm);
+        smem = pad + per_warp * warps;
+    } else {
+        // two warps per block unless one warp's queues already need more than half the shared memory
+        warps = per_warp * KNN_WARPS <= 227 * 1024 ? KNN_WARPS : 1;
+        smem = per_warp * warps;
+    }
+    if (smem > 227 * 1024 || warps < 1)
         throw Error(PNB_ERR_VALUE, "number of smoothing neighbours too large for the on-chip neighbour queues "
                                    "(at most 1024)");
     PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -546,7 +778,7 @@ static void launch_knn_p(Tree &t, KnnArgs<T> &a)
     if (per_sm < 1) per_sm = 1;
     // a search running beside other work (multi-GPU: interior queries on one thread, halo pipeline on another) leaves
     // part of each SM's shared memory to the kernels of the other thread
-    if (g_opt_knn_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt_knn_blocks_per_sm);
+    if (LOGC < 0 && g_opt_knn_blocks_per_sm > 0) per_sm = std::min(per_sm, g_opt_knn_blocks_per_sm);
     const int64_t want = (t.nsplit + warps - 1) / warps;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);    // persistent: one resident wave
     DevBuf counter(sizeof(unsigned long long)), lo;

@@ -234,6 +234,146 @@ __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__
     }
 }
 
+// ---- fused stable partition (packed device tree): one pass per level, no prefix-sum array --------------------
+// A tile is PF_TILE consecutive entries of one list.  Node ranges of the packed tree are powers of two and tiles are
+// aligned, so a tile either holds whole nodes (range <= PF_TILE: everything is decided inside the CTA) or lies inside
+// one node; in that case the number of lower-child entries in the node's earlier tiles comes from a decoupled
+// look-back over per-tile status words (aggregate / inclusive prefix; the chain starts at the node's first tile).
+// Tiles are handed out by a ticket counter, so every predecessor of a waiting tile is already running.  Status words
+// carry the level as a tag: nothing is reset between levels.  Compared with mark + CUB scan over 3n flags + partition
+// this reads every list entry and side flag once and writes no 3n-long prefix array (per level 0.45 -> see
+// profiles/r2_tree_build_variants.md).
+constexpr int PF_THREADS = 256, PF_ITEMS = 8, PF_TILE = PF_THREADS * PF_ITEMS, PF_CHUNKS = PF_TILE / 32;
+
+__device__ __forceinline__ unsigned long long pf_load(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pf_store(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(PF_THREADS)
+k_partition_fused(TreeShape s, int level, const uint32_t *__restrict__ L, const uint8_t *__restrict__ side,
+                  const int8_t *__restrict__ dim, uint32_t *__restrict__ Lnew, unsigned long long *status,
+                  unsigned int *ticket)
+{
+    __shared__ unsigned s_tile;
+    __shared__ uint32_t s_pre[PF_CHUNKS + 1];
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t n = s.n;
+    const int64_t tiles_per_list = (n + PF_TILE - 1) / PF_TILE;
+    const int d = (int)(tile / tiles_per_list);
+    const int64_t tl = tile - (int64_t)d * tiles_per_list;
+    const int64_t p0 = tl * PF_TILE;
+    const int sh = 5 + s.levels - level;                    // log2 of the node capacity at this level
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t *Ld = L + (int64_t)d * n;
+    uint32_t *Lo = Lnew + (int64_t)d * n;
+    const int64_t first_node = (int64_t)1 << level;
+
+    uint32_t id[PF_ITEMS];
+    bool keep[PF_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+        const int64_t p = p0 + k * PF_THREADS + threadIdx.x;
+        id[k] = 0xffffffffu;
+        keep[k] = true;
+        if (p < n) {
+            id[k] = Ld[p];
+            keep[k] = dim[first_node + (p >> sh)] == d;    // the list of the split axis is partitioned as it stands
+        }
+    }
+    bool left[PF_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) left[k] = (id[k] != 0xffffffffu && !keep[k]) ? side[id[k]] == 0 : false;
+    unsigned bal[PF_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+        bal[k] = __ballot_sync(0xffffffffu, left[k]);
+        if (lane == 0) s_pre[k * (PF_THREADS / 32) + w + 1] = __popc(bal[k]);
+    }
+    if (threadIdx.x == 0) s_pre[0] = 0;
+    __syncthreads();
+    if (w == 0) {                                           // inclusive scan of the PF_CHUNKS chunk counts
+        constexpr int PER = PF_CHUNKS / 32;
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[i] = s_pre[1 + lane * PER + i]; sum += v[i]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { run += v[i]; s_pre[1 + lane * PER + i] = run; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        // a node spanning several tiles: lower-child entries of the node's earlier tiles
+        if (((int64_t)1 << sh) > PF_TILE) {
+            const bool tile_keeps = dim[first_node + (p0 >> sh)] == d;
+            uint32_t base = 0;
+            if (!tile_keeps) {
+                const unsigned long long tag = (unsigned long long)(level + 1) << 34;
+                const int64_t first_tl = ((p0 >> sh) << sh) / PF_TILE;
+                unsigned long long *st = status + (int64_t)d * tiles_per_list;
+                if (tl == first_tl) {
+                    if (lane == 0) pf_store(st + tl, tag | (2ull << 32) | total);
+                } else {
+                    if (lane == 0) pf_store(st + tl, tag | (1ull << 32) | total);
+                    int64_t look = tl - 1;                  // window [look-31, look]
+                    for (;;) {
+                        const int64_t mine = look - lane;
+                        unsigned long long word = tag | (2ull << 32);          // before the node's first tile: prefix 0
+                        if (mine >= first_tl) {
+                            do { word = pf_load(st + mine); } while ((word >> 34) != (unsigned long long)(level + 1));
+                        }
+                        const bool incl = ((word >> 32) & 3ull) == 2ull;
+                        const unsigned im = __ballot_sync(0xffffffffu, incl);
+                        const int stop = im ? __ffs(im) - 1 : 32;             // nearest tile with an inclusive prefix
+                        uint32_t add = lane <= stop ? (uint32_t)word : 0u;
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                        base += add;
+                        if (im) break;
+                        look -= 32;
+                    }
+                    if (lane == 0) pf_store(st + tl, tag | (2ull << 32) | (unsigned long long)(base + total));
+                }
+            }
+            if (lane == 0) s_base = base;
+        }
+    }
+    __syncthreads();
+    const bool wide = ((int64_t)1 << sh) > PF_TILE;
+    const uint32_t base = wide ? s_base : 0u;
+    const int64_t cap = (int64_t)1 << sh;
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+        if (id[k] == 0xffffffffu) continue;
+        const int64_t p = p0 + k * PF_THREADS + threadIdx.x;
+        if (keep[k]) { Lo[p] = id[k]; continue; }
+        const int c = k * (PF_THREADS / 32) + w;
+        const int64_t lo = (p >> sh) << sh;
+        int64_t hi = lo + cap - 1;
+        if (hi > n - 1) hi = n - 1;
+        int64_t m = lo + (cap >> 1) - 1;
+        if (m > hi) m = hi;
+        uint32_t before = s_pre[c] + __popc(bal[k] & ((1u << lane) - 1u));
+        if (wide) before += base;
+        else before -= s_pre[(int)((lo - p0) >> 5)];
+        const int64_t dest = left[k] ? lo + (int64_t)before : (m + 1) + (p - lo) - (int64_t)before;
+        Lo[dest] = id[k];
+    }
+}
+
 template <typename T>
 __global__ void k_gather_tree_order(int64_t n, const uint32_t *__restrict__ order, const T *__restrict__ c,
                                     const T *__restrict__ mass, T *__restrict__ x, T *__restrict__ y,
@@ -279,14 +419,23 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     t.box.alloc(sizeof(T) * 6 * 2 * t.nsplit);
     if (!(shape.packed && want_soa && g_opt_tree_build == 1)) t.bucket_start.alloc(sizeof(int32_t) * (t.nsplit + 1));
     DevBuf dim(sizeof(int8_t) * 2 * t.nsplit), split(sizeof(T) * 2 * t.nsplit);
-    DevBuf side(sizeof(uint8_t) * n), S(sizeof(uint32_t) * 3 * n);
+    // packed device tree: fused one-pass partition per level; reference-shaped tree (arbitrary ranges) and
+    // pnb_set_option("tree_build", 3): flags -> CUB prefix sum over the three lists -> partition
+    const bool fused = shape.packed && g_opt_tree_build != 3;
+    DevBuf side(sizeof(uint8_t) * n), S(fused ? 0 : sizeof(uint32_t) * 3 * n);
+    const int64_t pf_tiles = 3 * ((n + PF_TILE - 1) / PF_TILE);
+    DevBuf pf_state;
+    if (fused) {
+        pf_state.alloc(sizeof(unsigned long long) * (pf_tiles + 32));
+        PNB_CUDA(cudaMemsetAsync(pf_state.p, 0, pf_state.bytes, s));
+    }
     DevBuf inherited;                                  // reference-shaped tree: split axis from the inherited boxes
     if (!shape.packed) inherited.alloc(sizeof(T) * 6 * 2 * t.nsplit);
     PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2 * t.nsplit, s));
 
     uint32_t *L = La.as<uint32_t>(), *Ln = Lb.as<uint32_t>();
     size_t scan_bytes = 0;
-    {
+    if (!fused) {
         LeftFlag f{L, side.as<uint8_t>()};
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
         PNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
@@ -303,11 +452,19 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
         PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
                    dim.as<int8_t>(), split.as<T>(), false, (int32_t *)nullptr, inherited.as<T>());
         PNB_LAUNCH(k_mark_sides, nblk(n, BS * LEVEL_ITEMS), BS, 0, s, shape, level, L, dim.as<int8_t>(), side.as<uint8_t>());
-        LeftFlag f{L, side.as<uint8_t>()};
-        auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
-        PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
-        g_launches += 2;
-        PNB_LAUNCH(k_partition, nblk(3 * n, BS * LEVEL_ITEMS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
+        if (fused) {
+            // status words [pf_tiles], then one ticket counter per level (level < 32)
+            unsigned long long *status = pf_state.as<unsigned long long>();
+            unsigned int *ticket = reinterpret_cast<unsigned int *>(status + pf_tiles) + level;
+            PNB_LAUNCH(k_partition_fused, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
+                       dim.as<int8_t>(), Ln, status, ticket);
+        } else {
+            LeftFlag f{L, side.as<uint8_t>()};
+            auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
+            PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
+            g_launches += 2;
+            PNB_LAUNCH(k_partition, nblk(3 * n, BS * LEVEL_ITEMS), BS, 0, s, shape, level, L, side.as<uint8_t>(), dim.as<int8_t>(), S.as<uint32_t>(), Ln);
+        }
         uint32_t *tmp = L; L = Ln; Ln = tmp;
     }
     if (lseg > 0) {
