@@ -345,7 +345,10 @@ static void update_mass_uniformity(Tree &t)
 
 int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 auto (keep them if they fit), 0 never, 1 always
 // pnb_set_option("tree_build"): how the device tree is built (results never depend on it).
-//   2 (default)  median-split kd-tree, every level by global passes over three per-axis sorted lists (tree_build.cu)
+//   2 (default)  median-split kd-tree from three per-axis sorted lists: one fused global pass per level (stable partition with
+//                decoupled look-back), the lowest 6 levels per 2048-particle sub-tree in shared memory (tree_build.cu)
+//   3            the same tree by mark + CUB prefix sum + partition per level (the round-1 formulation)
+//   4            the same tree with the fused global pass for every level
 //   1            the same, but the lowest 6-7 levels per sub-tree in shared memory (tree_morton.cu: k_build_segment)
 //   0            one Morton-key sort for the upper levels + shared-memory kd levels below
 // Measured at 16.7 M float64 particles (profiles/r2_tree_build_variants.md): build 15.8 / 17.9 / 7.6 ms, kNN kernel

@@ -101,6 +101,78 @@ __global__ void k_make_keys(const T *__restrict__ c, int64_t n, K *__restrict__ 
     ids[i] = (uint32_t)i;
 }
 
+// ---- float64 coordinates: sort on 32-bit keys, then put the (rare) ties right ---------------------------------
+// A 64-bit radix sort takes eight passes.  key32 = floor((v - min) * 2^32 / (max - min)) is a monotone map of the
+// coordinate (each step is monotone under rounding), so a four-pass sort on it orders everything except particles that
+// share a key -- closer than 2^-32 of the extent -- and those runs are finished by rank counting on the exact
+// (coordinate, id) pairs: the result is the list the stable 64-bit sort gives.  Long runs (coordinates on a lattice)
+// raise a flag and that axis falls back to the 64-bit sort.
+constexpr int TIE_RUN_MAX = 48;
+
+__global__ void k_minmax_orderable(const double *__restrict__ c, int64_t n, unsigned long long *__restrict__ mm)
+{
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long u = orderable(c[i]);
+        lo = u < lo ? u : lo;
+        hi = u > hi ? u : hi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+__device__ inline double from_orderable(unsigned long long u)
+{
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void k_make_keys32(const double *__restrict__ c, int64_t n, const unsigned long long *__restrict__ mm,
+                              uint32_t *__restrict__ keys, uint32_t *__restrict__ ids, int *__restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mn = from_orderable(mm[0]), mx = from_orderable(mm[1]);
+    const double ext = mx - mn;
+    const double v = c[i];
+    uint32_t key = 0;
+    if (ext > 0 && ext < 1.7e308 && v == v) {
+        double t = (v - mn) * (4294967295.0 / ext);          // monotone in v; <= 2^32 - 1 up to rounding
+        t = t < 0.0 ? 0.0 : (t > 4294967295.0 ? 4294967295.0 : t);
+        key = (uint32_t)t;                                     // truncation: monotone
+    } else if (!(v == v) || !(ext < 1.7e308)) {
+        *flag = 1;                                             // NaN / infinite extent: leave it to the 64-bit sort
+    }
+    keys[i] = key;
+    ids[i] = (uint32_t)i;
+}
+
+__global__ void k_fix_ties(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ids, const double *__restrict__ c,
+                           int64_t n, uint32_t *__restrict__ out, int *__restrict__ flag)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t k = keys[p], id = ids[p];
+    const bool le = p > 0 && keys[p - 1] == k, re = p + 1 < n && keys[p + 1] == k;
+    if (!le && !re) { out[p] = id; return; }
+    int64_t a = p, b = p;
+    while (a > 0 && keys[a - 1] == k && p - a <= TIE_RUN_MAX) --a;
+    while (b + 1 < n && keys[b + 1] == k && b - p <= TIE_RUN_MAX) ++b;
+    if (b - a + 1 > TIE_RUN_MAX) { *flag = 1; return; }
+    const unsigned long long me = orderable(c[id]);
+    int rank = 0;
+    for (int64_t q = a; q <= b; ++q) {
+        const uint32_t oid = ids[q];
+        const unsigned long long o = orderable(c[oid]);
+        rank += (o < me) || (o == me && oid < id);
+    }
+    out[a + rank] = id;
+}
+
 template <typename T> __device__ inline T pos_inf();
 template <> __device__ inline float pos_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ inline double pos_inf<double>() { return __longlong_as_double(0x7ff0000000000000ll); }
@@ -256,7 +328,8 @@ __device__ __forceinline__ void pf_store(unsigned long long *p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(PF_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(PF_THREADS, MINB)
 k_partition_fused(TreeShape s, int level, const uint32_t *__restrict__ L, const uint8_t *__restrict__ side,
                   const int8_t *__restrict__ dim, uint32_t *__restrict__ Lnew, unsigned long long *status,
                   unsigned int *ticket)
@@ -374,6 +447,195 @@ k_partition_fused(TreeShape s, int level, const uint32_t *__restrict__ L, const 
     }
 }
 
+// ---- lowest levels on chip, from the presorted lists (packed device tree) --------------------------------------
+// Once a node holds at most PS_SEG particles its three list segments fit into shared memory.  One CTA then finishes
+// the sub-tree: particles get LOCAL ids (their rank in the segment's x-list; global id -> local id through one
+// scatter / two gathers of a scratch array) and every further level -- bounds off the list ends, longest axis, side
+// flags, stable partition of the other two lists -- runs on 16-bit local ids in shared memory with the same index
+// arithmetic as the global passes, so the tree is the SAME tree.  Only the list ends touch the coordinates (a few
+// hundred gathers per segment); the kernel also writes the leaf bounds and the particle order, replacing the
+// per-level passes of these levels and the leaf-bounds pass.
+constexpr int PS_LEVELS = 6, PS_SEG = 32 << PS_LEVELS, PS_THREADS = 256, PS_ITEMS = PS_SEG / PS_THREADS,
+              PS_CHUNKS = PS_SEG / 32;
+
+static size_t partition_segment_smem()
+{
+    return (size_t)PS_SEG * (sizeof(uint32_t) + 6 * sizeof(uint16_t) + 1) + 3 * (PS_CHUNKS + 1) * sizeof(uint32_t)
+           + PS_CHUNKS * sizeof(int) + 64;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PS_THREADS, 4)
+k_partition_segment(TreeShape s, int ls, const uint32_t *__restrict__ L, const T *__restrict__ c,
+                    uint16_t *__restrict__ loc, T *__restrict__ box, int8_t *__restrict__ dim_out, T *__restrict__ split_out,
+                    int32_t *__restrict__ bucket_start, uint32_t *__restrict__ order)
+{
+    extern __shared__ __align__(16) unsigned char ps_raw[];
+    const int64_t n = s.n;
+    const int SEG = 32 << ls;                       // particles per segment (ls <= PS_LEVELS)
+    const int gl = s.levels - ls;                   // level of this CTA's root node
+    const int64_t seg = blockIdx.x, lo0 = seg * SEG;
+    const int cnt = (int)max((int64_t)0, min((int64_t)SEG, n - lo0));
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t nsplit = (int64_t)1 << s.levels;
+
+    uint32_t *gid = reinterpret_cast<uint32_t *>(ps_raw);                   // [PS_SEG] global id by local id
+    uint16_t *la = reinterpret_cast<uint16_t *>(gid + PS_SEG);              // [3][PS_SEG] lists of local ids
+    uint16_t *lb = la + 3 * PS_SEG;                                         // the other buffer
+    uint32_t *pre = reinterpret_cast<uint32_t *>(lb + 3 * PS_SEG);          // [3][PS_CHUNKS + 1] chunk prefix sums
+    int *ndim = reinterpret_cast<int *>(pre + 3 * (PS_CHUNKS + 1));         // split axis of every node of the level
+    uint8_t *side = reinterpret_cast<uint8_t *>(ndim + PS_CHUNKS);          // [PS_SEG] by local id
+
+    // local ids = ranks in the x-list (all loads of a thread in flight together)
+    {
+        uint32_t g[PS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PS_ITEMS; ++k) {
+            const int i = k * PS_THREADS + tid;
+            g[k] = i < cnt ? L[lo0 + i] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < PS_ITEMS; ++k) {
+            const int i = k * PS_THREADS + tid;
+            if (i < cnt) { gid[i] = g[k]; loc[g[k]] = (uint16_t)i; la[i] = (uint16_t)i; }
+        }
+    }
+    __syncthreads();                                // (block-wide visibility of the scratch writes)
+    {
+        uint32_t gy[PS_ITEMS], gz[PS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PS_ITEMS; ++k) {
+            const int i = k * PS_THREADS + tid;
+            gy[k] = i < cnt ? L[n + lo0 + i] : 0u;
+            gz[k] = i < cnt ? L[2 * n + lo0 + i] : 0u;
+        }
+        uint16_t ly[PS_ITEMS], lz[PS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PS_ITEMS; ++k) {
+            const int i = k * PS_THREADS + tid;
+            ly[k] = i < cnt ? loc[gy[k]] : (uint16_t)0;
+            lz[k] = i < cnt ? loc[gz[k]] : (uint16_t)0;
+        }
+#pragma unroll
+        for (int k = 0; k < PS_ITEMS; ++k) {
+            const int i = k * PS_THREADS + tid;
+            if (i < cnt) { la[PS_SEG + i] = ly[k]; la[2 * PS_SEG + i] = lz[k]; }
+        }
+    }
+    __syncthreads();
+
+    const T inf = pos_inf<T>();
+    for (int l = 0; l <= ls; ++l) {
+        const int sh = 5 + ls - l;                  // log2 of the node capacity at this level
+        const int cap = 1 << sh, nn = 1 << l;
+        const bool leaf = l == ls;
+        // bounds straight off the list ends, split axis and value (k_node_bounds): six lanes per node, one list end each
+        for (int t = tid; t < nn * 8; t += PS_THREADS) {
+            const int j = t >> 3, r = t & 7;
+            const int lo = j << sh, hi = min(cnt, lo + cap) - 1;
+            const int64_t node = ((int64_t)1 << (gl + l)) + seg * nn + j;
+            T *b = box + node * 6;
+            const bool empty = hi < lo;
+            T v = r < 3 ? inf : -inf;
+            if (!empty && r < 6) {
+                const int d = r < 3 ? r : r - 3;
+                v = c[(int64_t)d * n + gid[la[d * PS_SEG + (r < 3 ? lo : hi)]]];
+            }
+            if (r < 6) b[r] = v;
+            // the eight lanes of a node share its bounds by shuffle (nodes never straddle a warp: 8 divides 32)
+            const unsigned grp = 0xffu << (lane & 24);
+            T mn[3], mx[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                mn[d] = __shfl_sync(grp, v, (lane & 24) + d);
+                mx[d] = __shfl_sync(grp, v, (lane & 24) + 3 + d);
+            }
+            if (r == 0) {
+                if (leaf) {
+                    const int64_t bj = seg * nn + j;
+                    bucket_start[bj] = (int32_t)min(n, lo0 + lo);
+                    if (bj == nsplit - 1) bucket_start[nsplit] = (int32_t)n;
+                } else if (empty) {
+                    dim_out[node] = 0; split_out[node] = 0; ndim[j] = 0;
+                } else {
+                    int d = 0;
+                    for (int e = 1; e < 3; ++e)
+                        if (mx[e] - mn[e] > mx[d] - mn[d]) d = e;
+                    const int mr = min(lo + (cap >> 1) - 1, hi);
+                    dim_out[node] = (int8_t)d;
+                    split_out[node] = c[(int64_t)d * n + gid[la[d * PS_SEG + mr]]];
+                    ndim[j] = d;
+                }
+            }
+        }
+        if (leaf) break;
+        __syncthreads();
+        // side flags from the split-axis list (k_mark_sides)
+        for (int p = tid; p < cnt; p += PS_THREADS) {
+            const int j = p >> sh, lo = j << sh, hi = min(cnt, lo + cap) - 1;
+            const int mr = min(lo + (cap >> 1) - 1, hi);
+            side[la[ndim[j] * PS_SEG + p]] = (uint8_t)(p > mr);
+        }
+        __syncthreads();
+        // stable partition of the other two lists (k_partition_fused, whole nodes inside the CTA)
+        uint16_t id[3][PS_ITEMS];
+        unsigned bal[3][PS_ITEMS];
+        bool left[3][PS_ITEMS];
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+#pragma unroll
+            for (int k = 0; k < PS_ITEMS; ++k) {
+                const int p = k * PS_THREADS + tid;
+                id[e][k] = 0; left[e][k] = false;
+                if (p < cnt) {
+                    id[e][k] = la[e * PS_SEG + p];
+                    left[e][k] = ndim[p >> sh] != e && side[id[e][k]] == 0;
+                }
+                bal[e][k] = __ballot_sync(0xffffffffu, left[e][k]);
+                if (lane == 0) pre[e * (PS_CHUNKS + 1) + k * (PS_THREADS / 32) + w + 1] = __popc(bal[e][k]);
+            }
+        if (tid < 3) pre[tid * (PS_CHUNKS + 1)] = 0;
+        __syncthreads();
+        if (w < 3) {                                // warp e: inclusive scan of list e's chunk counts
+            constexpr int PER = PS_CHUNKS / 32;
+            uint32_t *pp = pre + w * (PS_CHUNKS + 1) + 1;
+            uint32_t v[PER], sum = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { v[i] = pp[lane * PER + i]; sum += v[i]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { run += v[i]; pp[lane * PER + i] = run; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+#pragma unroll
+            for (int k = 0; k < PS_ITEMS; ++k) {
+                const int p = k * PS_THREADS + tid;
+                if (p >= cnt) continue;
+                const int j = p >> sh;
+                if (ndim[j] == e) { lb[e * PS_SEG + p] = id[e][k]; continue; }
+                const int lo = j << sh, hi = min(cnt, lo + cap) - 1;
+                const int mr = min(lo + (cap >> 1) - 1, hi);
+                const uint32_t *pp = pre + e * (PS_CHUNKS + 1);
+                const int before = (int)(pp[k * (PS_THREADS / 32) + w] - pp[lo >> 5]) + __popc(bal[e][k] & ((1u << lane) - 1u));
+                const int dest = left[e][k] ? lo + before : (mr + 1) + (p - lo) - before;
+                lb[e * PS_SEG + dest] = id[e][k];
+            }
+        __syncthreads();
+        uint16_t *t2 = la; la = lb; lb = t2;
+    }
+    __syncthreads();
+    // tree order = the x-list
+    for (int p = tid; p < cnt; p += PS_THREADS) order[lo0 + p] = gid[la[p]];
+}
+
 template <typename T>
 __global__ void k_gather_tree_order(int64_t n, const uint32_t *__restrict__ order, const T *__restrict__ c,
                                     const T *__restrict__ mass, T *__restrict__ x, T *__restrict__ y,
@@ -387,6 +649,37 @@ __global__ void k_gather_tree_order(int64_t n, const uint32_t *__restrict__ orde
 }
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// float64: the three lists through the 32-bit-key sort; done[d] is set for every axis that needed no fallback
+static void presort_f64(DevBuf &c, int64_t n, DevBuf &keys_in, DevBuf &keys_out, DevBuf &ids_in, DevBuf &tmp, size_t tmp_bytes,
+                        DevBuf &La, cudaStream_t s, bool done[3])
+{
+    const int BS = 256;
+    DevBuf ids_out(sizeof(uint32_t) * n), aux(64);
+    // aux: [0..5] min / max per axis (orderable), then three flags
+    unsigned long long init[8] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull, 0ull};
+    PNB_CUDA(cudaMemcpyAsync(aux.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    unsigned long long *mm = aux.as<unsigned long long>();
+    int *flags = reinterpret_cast<int *>(mm + 6);
+    size_t need = 0;
+    PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, uint32_t, int64_t>(
+        nullptr, need, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(), ids_in.as<uint32_t>(), ids_out.as<uint32_t>(), n, 0, 32, s)));
+    if (need > tmp_bytes) return;                           // (never: the 64-bit sort needs more)
+    for (int d = 0; d < 3; ++d) {
+        const double *cd = c.as<double>() + (int64_t)d * n;
+        PNB_LAUNCH(k_minmax_orderable, 148 * 8, BS, 0, s, cd, n, mm + 2 * d);
+        PNB_LAUNCH(k_make_keys32, nblk(n, BS), BS, 0, s, cd, n, mm + 2 * d, keys_in.as<uint32_t>(), ids_in.as<uint32_t>(), flags + d);
+        PNB_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, uint32_t, int64_t>(
+            tmp.p, need, keys_in.as<uint32_t>(), keys_out.as<uint32_t>(), ids_in.as<uint32_t>(), ids_out.as<uint32_t>(), n, 0, 32, s)));
+        PNB_LAUNCH(k_fix_ties, nblk(n, BS), BS, 0, s, keys_out.as<uint32_t>(), ids_out.as<uint32_t>(), cd, n,
+                   La.as<uint32_t>() + (int64_t)d * n, flags + d);
+        g_launches += 3;
+    }
+    int hflags[3];
+    PNB_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, s));
+    PNB_CUDA(cudaStreamSynchronize(s));
+    for (int d = 0; d < 3; ++d) done[d] = hflags[d] == 0;
+}
 
 template <typename T, typename K>
 static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
@@ -405,7 +698,10 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
             nullptr, tmp_bytes, keys_in.as<K>(), keys_out.as<K>(), ids_in.as<uint32_t>(), La.as<uint32_t>(), n, 0,
             (int)sizeof(K) * 8, s)));
         DevBuf tmp(tmp_bytes);
+        bool presorted[3] = {false, false, false};
+        if (sizeof(K) == 8 && g_opt_tree_build != 3) presort_f64(c, n, keys_in, keys_out, ids_in, tmp, tmp_bytes, La, s, presorted);
         for (int d = 0; d < 3; ++d) {
+            if (presorted[d]) continue;
             PNB_LAUNCH((k_make_keys<T, K>), nblk(n, BS), BS, 0, s, c.as<T>() + d * n, n, keys_in.as<K>(),
                        ids_in.as<uint32_t>());
             PNB_CUDA((cub::DeviceRadixSort::SortPairs<K, uint32_t, int64_t>(
@@ -446,7 +742,10 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     // medians by an in-CTA sort, tight bounds, tree-ordered structure of arrays) instead of one global pass +
     // prefix sum per level; the reference-shaped tree (export) runs every level here.
     const int lseg = (shape.packed && want_soa && g_opt_tree_build == 1) ? std::min(levels, segment_levels(t.dtype)) : 0;
-    const int global_levels = levels - lseg;
+    // default (2): the lowest PS_LEVELS levels from the presorted lists in shared memory (k_partition_segment);
+    // 4: every level by the fused global pass
+    const int lps = (fused && want_soa && g_opt_tree_build == 2) ? std::min(levels, PS_LEVELS) : 0;
+    const int global_levels = levels - lseg - lps;
     for (int level = 0; level < global_levels; ++level) {
         int64_t nn = (int64_t)1 << level;
         PNB_LAUNCH((k_node_bounds<T>), nblk(nn, 128), 128, 0, s, shape, level, L, c.as<T>(), t.box.as<T>(),
@@ -456,8 +755,16 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
             // status words [pf_tiles], then one ticket counter per level (level < 32)
             unsigned long long *status = pf_state.as<unsigned long long>();
             unsigned int *ticket = reinterpret_cast<unsigned int *>(status + pf_tiles) + level;
-            PNB_LAUNCH(k_partition_fused, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
-                       dim.as<int8_t>(), Ln, status, ticket);
+            static const int minb = getenv("PNB_PF_MINB") ? atoi(getenv("PNB_PF_MINB")) : 6;   // resident CTAs per SM (4: 11.75, 6 / 8: 10.78 ms per build)
+            if (minb == 8)
+                PNB_LAUNCH(k_partition_fused<8>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
+                           dim.as<int8_t>(), Ln, status, ticket);
+            else if (minb == 6)
+                PNB_LAUNCH(k_partition_fused<6>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
+                           dim.as<int8_t>(), Ln, status, ticket);
+            else
+                PNB_LAUNCH(k_partition_fused<4>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
+                           dim.as<int8_t>(), Ln, status, ticket);
         } else {
             LeftFlag f{L, side.as<uint8_t>()};
             auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
@@ -469,6 +776,23 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     }
     if (lseg > 0) {
         build_tree_segments(t, c.p, mass, L, lseg);
+    } else if (lps > 0 || (fused && want_soa && g_opt_tree_build == 2)) {
+        t.order.alloc(sizeof(uint32_t) * n);
+        {
+            DevBuf loc(sizeof(uint16_t) * n);
+            auto kern = k_partition_segment<T>;
+            const size_t smem = partition_segment_smem();
+            PNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PNB_LAUNCH(kern, (unsigned)(t.nsplit >> lps), PS_THREADS, smem, s, shape, lps, L, c.as<T>(), loc.as<uint16_t>(),
+                       t.box.as<T>(), dim.as<int8_t>(), split.as<T>(), t.bucket_start.as<int32_t>(), t.order.as<uint32_t>());
+            t.x.alloc(sizeof(T) * n); t.y.alloc(sizeof(T) * n); t.z.alloc(sizeof(T) * n);
+            if (mass) t.mass.alloc(sizeof(T) * n);
+            t.has_mass = mass != nullptr;
+            if (t.mass_ready) PNB_CUDA(cudaStreamWaitEvent(s, t.mass_ready, 0));   // masses uploaded behind the sorts
+            PNB_LAUNCH((k_gather_tree_order<T>), nblk(n, BS), BS, 0, s, n, t.order.as<uint32_t>(), c.as<T>(), mass,
+                       t.x.as<T>(), t.y.as<T>(), t.z.as<T>(), t.mass.as<T>());
+            PNB_CUDA(cudaStreamSynchronize(s));            // `loc` goes back to the block cache on scope exit
+        }
     } else {
         PNB_LAUNCH((k_node_bounds<T>), nblk(t.nsplit, 128), 128, 0, s, shape, levels, L, c.as<T>(), t.box.as<T>(),
                    dim.as<int8_t>(), split.as<T>(), true, t.bucket_start.as<int32_t>(), (T *)nullptr);

@@ -95,7 +95,8 @@ def test_tree_invariants(n, dtype):
             assert np.all(bounds[b, :3] == np.inf) and np.all(bounds[b, 3:] == -np.inf)
 
 
-@pytest.mark.parametrize("build", [0, 1, 2], ids=["morton", "kd_hybrid", "kd_levelwise"])
+@pytest.mark.parametrize("build", [0, 1, 2, 3, 4], ids=["morton", "kd_hybrid", "kd_lists_onchip_tail", "kd_levelwise_cub",
+                                                        "kd_levelwise_fused"])
 @pytest.mark.parametrize("n,dtype", [(40, np.float64), (2048, np.float64), (2049, np.float64), (4096, np.float32),
                                      (70_001, np.float32), (300_000, np.float64)])
 def test_both_tree_builds_give_a_valid_tree_and_the_same_answers(build, n, dtype):
@@ -538,6 +539,46 @@ def test_full_size_box_properties(dtype):
     m2[::2] = torch.nextafter(m2[::2], torch.full_like(m2[::2], 2.0))     # masses no longer identical
     _, rho_g = run(pos, m2)
     assert float(((rho_g - rho).abs() / rho).max()) < rtol
+
+
+@pytest.mark.parametrize("n,dtype", [(33, np.float64), (2047, np.float32), (2049, np.float64), (65_537, np.float64),
+                                     (150_000, np.float32), (1_000_003, np.float64)])
+def test_levelwise_build_variants_give_the_same_tree(n, dtype):
+    """tree_build 2 (default: global fused passes + the lowest levels from the presorted lists in shared memory), 3 (mark +
+    CUB prefix sum + partition per level) and 4 (fused pass for every level) are the same algorithm: identical particle
+    order and identical bounds of every node."""
+    from pynbody_b200 import _lib
+    pos, vel, mass = synth.clumpy_box(n, 5 + n % 11, dtype)
+    if n == 65_537:
+        # coordinates closer than 2^-32 of the extent, exact duplicates and signed zeros: the runs of equal 32-bit sort keys
+        # that the float64 build finishes by rank counting (tree_build.cu: k_fix_ties)
+        pos[1000:2000] = pos[:1000] + 1e-13
+        pos[2000:2500, 0] = pos[:500, 0]
+        pos[3000:3010, 1] = 0.0
+        pos[3010:3020, 1] = -0.0
+    if n == 150_000:
+        pos = pos.astype(np.float64)            # a lattice along x and y: long runs of equal keys -> 64-bit sort for those axes
+        mass = mass.astype(np.float64)
+        pos[:, 0] = np.round(pos[:, 0] * 40) / 40
+        pos[:, 1] = np.round(pos[:, 1] * 3000) / 3000
+    L = _lib.lib()
+    got = {}
+    for build in (2, 3, 4):
+        kdmain.set_option("tree_build", build)
+        try:
+            kd = _tree(pos, mass, 1.0 if n > 1000 else None)
+        finally:
+            kdmain.set_option("tree_build", 2)
+        h = kd.kdtree.handle
+        nb = L.pnb_tree_num_buckets(h)
+        boxes = np.empty((2 * nb, 6))
+        _lib.check(L.pnb_tree_node_bounds(h, boxes.ctypes.data))
+        order = np.empty(n, np.int64)
+        _lib.check(L.pnb_tree_order(h, order.ctypes.data))
+        got[build] = (order, boxes[1:])
+    for build in (3, 4):
+        assert np.array_equal(got[2][0], got[build][0]), build
+        assert np.array_equal(got[2][1], got[build][1]), build
 
 
 def _bruteforce_d2(q, x, L):
