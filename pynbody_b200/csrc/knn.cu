@@ -39,6 +39,8 @@
 // L2-resident scratch array in global memory and are read only for the new maximum and to break ties
 // between equal high words.  Every ordering decision is still made on the exact 64-bit value.
 #include "traverse.cuh"
+#include <cmath>
+#include <limits>
 
 namespace pnb {
 #ifdef KNN_STATS
@@ -66,6 +68,10 @@ struct KnnArgs {
     T *nn_d2;               // same layout: the queued distances, written once at the end of a search, or null
     unsigned long long *next_bucket;   // work counter
     uint32_t *lo_scratch;   // [resident warps][K2][32] low words of the queued d2 (float64 only)
+    // periodic boxes: a ball that stays inside (face_lo, face_hi) on every axis cannot contain a wrapped image of any
+    // particle (all particles lie within one period: face_lo = root_max - L rounded up, face_hi = root_min + L rounded
+    // down); face_eps covers the rounding of q +- r
+    T face_lo[3], face_hi[3], face_eps;
 };
 
 // key held in shared memory for a queued distance
@@ -427,6 +433,15 @@ __device__ __forceinline__ void queue_build(Queue<T, W_t> &q)
     set_top_from_leaf(q, (int)q.W[wofs<LOGC>(wpos<LOGC>(K2, LOG, 0))]);
 }
 
+// cell test with the periodic wrap switched off at run time (warp-uniform) once no query ball of the warp can reach
+// across a face of the period
+template <typename T, bool PERIODIC>
+__device__ __forceinline__ T box_gap2_w(bool wrap, const Box6<T> &b, T qx, T qy, T qz, T L, T &sx, T &sy, T &sz)
+{
+    if (PERIODIC && wrap) return box_gap2<T, true>(b, qx, qy, qz, L, sx, sy, sz);
+    return box_gap2<T, false>(b, qx, qy, qz, L, sx, sy, sz);
+}
+
 template <typename T, typename W_t, int LOGC, bool WITH_IDX>
 __device__ __forceinline__ void knn_visit_bucket(const TreeView<T> &tv, int64_t bucket, bool pass, T sx, T sy, T sz,
                                                  Queue<T, W_t> &q, T *tile, int lane, bool wide, T qx, T qy, T qz,
@@ -610,6 +625,10 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
         // be pushed out again (CPU model of the walk, scripts/knn_walk_model.py: -10 % buckets visited, -18 % insert
         // rounds).  The result does not depend on the order (exact ties at the k-th distance aside).
         int64_t cell = tv.nsplit + bucket;
+        // PERIODIC: the wrapped images are tested until the queues are full; from then on the k-th distance only
+        // shrinks, and if no active query's ball reaches a face of the period the rest of the walk runs the plain
+        // (cheaper) cell test -- an interior warp never sees a wrapped image
+        bool wrap = PERIODIC, undecided = PERIODIC;
         // the walk tests one sibling per level on the way up: lane l asks for the bounds of the one l levels up now
         // (a 48-byte record can straddle two lines)
         {
@@ -629,7 +648,7 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
             {
                 const Box6<T> b = load_box(tv.box, cp);
                 STAT(5, 1);    // nodes tested
-                const T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
+                const T gap2 = box_gap2_w<T, PERIODIC>(wrap, b, qx, qy, qz, L, sx, sy, sz);
                 // (top * slack overflows to +inf while the queue still holds its initial huge keys; empty
                 // nodes have inverted bounds and an infinite gap)
                 pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
@@ -639,7 +658,7 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
                 if (__any_sync(FULL, pass)) {
                     if (cp >= tv.nsplit) {
                         bool amb = false;
-                        if (PERIODIC) amb = pass && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, cp), sx, sy, sz, L);
+                        if (PERIODIC && wrap) amb = pass && shift_is_ambiguous<T, PERIODIC>(load_box(tv.box, cp), sx, sy, sz, L);
                         knn_visit_bucket<T, W_t, LOGC, WITH_IDX>(tv, cp - tv.nsplit, pass, sx, sy, sz, q, tile, lane,
                                                                  PERIODIC && __any_sync(FULL, amb), qx, qy, qz, filled, k, active);
                     } else {
@@ -658,8 +677,8 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
                         }
                         STAT(5, 2);
                         T lx_, ly_, lz_, rx_, ry_, rz_;
-                        const T gl = box_gap2<T, PERIODIC>(bl, qx, qy, qz, L, lx_, ly_, lz_);
-                        const T gr = box_gap2<T, PERIODIC>(br, qx, qy, qz, L, rx_, ry_, rz_);
+                        const T gl = box_gap2_w<T, PERIODIC>(wrap, bl, qx, qy, qz, L, lx_, ly_, lz_);
+                        const T gr = box_gap2_w<T, PERIODIC>(wrap, br, qx, qy, qz, L, rx_, ry_, rz_);
                         const T bound = q.top * Ex<T>::slack();
                         const bool pl = active && gl <= bound && gl < Ex<T>::inf();
                         const bool pr = active && gr <= bound && gr < Ex<T>::inf();
@@ -697,10 +716,17 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
                 if (!found) break;
                 const Box6<T> b = load_box(tv.box, cp);
                 STAT(5, 1);
-                const T gap2 = box_gap2<T, PERIODIC>(b, qx, qy, qz, L, sx, sy, sz);
+                const T gap2 = box_gap2_w<T, PERIODIC>(wrap, b, qx, qy, qz, L, sx, sy, sz);
                 pass = active && gap2 <= q.top * Ex<T>::slack() && gap2 < Ex<T>::inf();
             }
             cell >>= 1;
+            if (PERIODIC && undecided && filled < 0) {
+                undecided = false;
+                const T r = Ex<T>::sqrt(q.top) * (T)1.0001 + a.face_eps;        // q.top: (an upper bound of) the k-th d2
+                const bool reaches = active && (qx - r <= a.face_lo[0] || qx + r >= a.face_hi[0] || qy - r <= a.face_lo[1]
+                                                || qy + r >= a.face_hi[1] || qz - r <= a.face_lo[2] || qz + r >= a.face_hi[2]);
+                wrap = __any_sync(FULL, reaches);
+            }
         }
 
         if (active) {
@@ -850,6 +876,19 @@ static void run_knn_typed(Tree &t, int k, double period, bool fuse_rho, const Ke
     if (!keep_ids) {
         t.nn_ids.release();
         t.nn_d2.release();
+    }
+    for (int d = 0; d < 3; ++d) {
+        const double lo = t.root_max[d] - period, hi = t.root_min[d] + period;
+        T flo = (T)lo, fhi = (T)hi;
+        if ((double)flo < lo) flo = std::nextafter(flo, std::numeric_limits<T>::infinity());     // rounded towards the inside
+        if ((double)fhi > hi) fhi = std::nextafter(fhi, -std::numeric_limits<T>::infinity());
+        a.face_lo[d] = flo;
+        a.face_hi[d] = fhi;
+    }
+    {
+        double scale = std::fabs(period);
+        for (int d = 0; d < 3; ++d) scale = std::max(scale, std::max(std::fabs(t.root_min[d]), std::fabs(t.root_max[d])) + std::fabs(period));
+        a.face_eps = (T)(16.0 * (double)std::numeric_limits<T>::epsilon() * scale);
     }
     a.smooth_t = t.smooth_t.as<T>();
     a.rho_t = t.rho_t.as<T>();
