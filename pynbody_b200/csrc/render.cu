@@ -340,6 +340,15 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
     const int nchunks = (int)((last - first + CHUNK - 1) / CHUNK);
 
     for (int i = tid; i < g.ns + 3; i += 256) slut[i] = i < g.ns ? lut[i] : 0.0f;
+    // the table is read through its 32-bit shared-window address: with a generic pointer nvcc rebuilds the window base
+    // (S2UR SR_CgaCtaId + ULEA) in front of EVERY lookup of the record loop -- 6 % of the kernel's stall samples (ncu)
+    uint32_t slut_s = (uint32_t)__cvta_generic_to_shared(slut);
+    asm volatile("mov.u32 %0, %0;" : "+r"(slut_s));           // opaque: computed here once, kept in a register
+    auto table = [&](unsigned idx) {
+        float v;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(slut_s + idx * 4u));
+        return v;
+    };
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -411,10 +420,12 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
             if (GRID) in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
             if (!in_xz) continue;
+            // (fused multiply-adds here: the float index is only trusted away from the bin borders -- BORDER below -- and
+            // re-evaluated exactly otherwise, so contraction cannot change a table index)
             const float ddx = R.xr - cx;
-            float d2xz = ddx * ddx;
-            if (GRID) { const float ddz = R.zr - cz; d2xz += ddz * ddz; }
-            else d2xz += R.zr;
+            float d2xz;
+            if (GRID) { const float ddz = R.zr - cz; d2xz = fmaf(ddz, ddz, ddx * ddx); }
+            else d2xz = fmaf(ddx, ddx, R.zr);
             // every pixel of the rectangle receives w * (LUT or 0) as in the reference, so that a non-finite
             // weight poisons the same pixels (w * 0 = NaN); the table in shared memory is followed by zeros, so
             // indices past its end need no test
@@ -425,18 +436,22 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                 for (int q = 0; q < NPIX; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
                     const float ddy = R.yr - cy[q];
-                    const float d2 = ddy * ddy + d2xz;
+                    const float d2 = fmaf(ddy, ddy, d2xz);
                     const float t = fminf(d2 * inv, nsf + 2.0f);
                     unsigned idx = (unsigned)t;
                     const float fr = t - (float)idx;
-                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) idx = min(exact_index<GRID>(g, R, px, py + q, pz), ns);
-                    a[q] += slut[idx] * wq;
+                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) {
+                        int pxo = px;
+                        asm volatile("" : "+r"(pxo));          // keeps the double-precision pixel arithmetic of the exact
+                        idx = min(exact_index<GRID>(g, R, pxo, py + q, pz), ns);   // path inside this rare branch (nvcc hoists it)
+                    }
+                    a[q] = fmaf(table(idx), wq, a[q]);
                 }
             } else {                                           // tiny kernels: exact index only
 #pragma unroll
                 for (int q = 0; q < NPIX; ++q) {
                     if (!(rel + (unsigned)q < wy)) continue;
-                    a[q] += slut[min(exact_index<GRID>(g, R, px, py + q, pz), ns)] * wq;
+                    a[q] = fmaf(table(min(exact_index<GRID>(g, R, px, py + q, pz), ns)), wq, a[q]);
                 }
             }
         }
