@@ -319,7 +319,7 @@ def _box_gap2(x, lo, hi, period):
     g = gap(x)
     if period is not None:
         g = torch.minimum(g, torch.minimum(gap(x + period), gap(x - period)))
-    return (g * g).sum(dim=1)
+    return (g * g).sum(dim=-1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,16 +347,21 @@ def _alltoallv(per_dest, group=None):
     return list(recv.split(rc))
 
 
-def _alltoall_rows(send, counts, group=None):
-    """The same for rows that already lie destination-major in one tensor: (received rows, rows per source)."""
+def _alltoall_rows(send, counts, group=None, rcounts=None):
+    """The same for rows that already lie destination-major in one tensor: (received rows, rows per source).
+    ``rcounts``: the rows every source will send, when an earlier exchange over the same routes has told us
+    (then no count exchange and no host synchronisation precede the data)."""
     dev = send.device
     if dev.type == "cuda" and _staged(group):
-        recv, rc = _alltoall_rows(send.cpu(), counts, group)
+        recv, rc = _alltoall_rows(send.cpu(), counts, group, rcounts)
         return recv.to(dev), rc
-    sc = torch.tensor(counts, dtype=torch.int64, device=dev)
-    rcounts = torch.empty_like(sc)
-    dist.all_to_all_single(rcounts, sc, group=group)
-    rc = rcounts.tolist()
+    if rcounts is not None:
+        rc = list(rcounts)
+    else:
+        sc = torch.tensor(counts, dtype=torch.int64, device=dev)
+        rct = torch.empty_like(sc)
+        dist.all_to_all_single(rct, sc, group=group)
+        rc = rct.tolist()
     recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
     dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=list(counts), group=group)
     return recv, rc
@@ -444,8 +449,8 @@ class DistributedKDTree:
         """Owned-order values -> the rank/order the particles came from."""
         if self.world == 1:
             return owned_values
-        back = _alltoallv(list(owned_values.split(self._own_counts)), self.group)
-        flat = torch.cat(back)
+        # the routes of the particle exchange, backwards: every count is known
+        flat, _ = _alltoall_rows(owned_values.contiguous(), self._own_counts, self.group, self._ret_counts)
         out = torch.empty((self.n_in,) + tuple(flat.shape[1:]), dtype=flat.dtype, device=flat.device)
         out[self._ret_index] = flat
         return out
@@ -455,7 +460,7 @@ class DistributedKDTree:
         if self.world == 1:
             return values
         v = values[self._ret_index]
-        return torch.cat(_alltoallv(list(v.split(self._ret_counts)), self.group))
+        return _alltoall_rows(v.contiguous(), self._ret_counts, self.group, self._own_counts)[0]
 
     def _faces(self):
         """(lo[3], hi[3]) of this rank's domain as numpy arrays, +-inf where there is no face (open outer faces, or a
@@ -531,27 +536,37 @@ class DistributedKDTree:
         # boundary queries -> the ranks whose domain their ball touches
         fidx = torch.nonzero(flagged).squeeze(1)
         fpos, frad = self.pos[fidx], r_ub[fidx] * (1 + 1e-6)      # cover rounding of r = 2h = sqrt(d2_k)
-        sends = []
-        for r in range(self.world):
-            if r == self.rank:
-                sends.append(torch.empty((0, 4), dtype=self.dt, device=self.dev))
-                continue
-            lo, hi = (t.to(self.dev) for t in self.domains[r])
-            touch = _box_gap2(fpos, lo, hi, period) <= frad * frad * (1 + 1e-6)
-            sends.append(torch.cat([fpos[touch], frad[touch, None]], dim=1))
-        balls = _alltoallv(sends, self.group)
+        # (query, rank) pairs for every domain the ball touches -- all ranks in one pass (a block of ranks at a time), one
+        # size read-back and one exchange of rows that already lie destination-major, instead of a test, a compaction and
+        # a host synchronisation per rank
+        lim = frad * frad * (1 + 1e-6)
+        touch = torch.zeros((self.world, fpos.shape[0]), dtype=torch.bool, device=self.dev)
+        for r0 in range(0, self.world, 8):
+            rr = range(r0, min(self.world, r0 + 8))
+            lo = torch.stack([self.domains[r][0] for r in rr]).to(self.dev)[:, None, :]          # [b][1][3]
+            hi = torch.stack([self.domains[r][1] for r in rr]).to(self.dev)[:, None, :]
+            touch[r0:r0 + len(rr)] = _box_gap2(fpos[None, :, :], lo, hi, period) <= lim[None, :]
+        touch[self.rank] = False
+        pairs = touch.nonzero()                                    # sorted by rank, then by query
+        counts = touch.sum(dim=1).tolist()
+        sel = pairs[:, 1]
+        balls_flat, rcounts = _alltoall_rows(torch.cat([fpos[sel], frad[sel, None]], dim=1), counts, self.group)
+        balls = list(balls_flat.split(rcounts))
         self._tick("select_and_send_boundary_queries")
-        # which of my particles do they need?
-        self._halo_send = []
+        # which of my particles do they need?  One flag row per requesting rank, one compaction for all of them
+        need = torch.zeros((self.world, self.n_own), dtype=torch.bool, device=self.dev)
         for r in range(self.world):
             b = balls[r]
             if r == self.rank or b.shape[0] == 0:
-                self._halo_send.append(torch.empty(0, dtype=torch.int64, device=self.dev))
                 continue
             rad = torch.where(torch.isfinite(b[:, 3]), b[:, 3], torch.full_like(b[:, 3], 1e30))
-            self._halo_send.append(torch.nonzero(self.tree1.mark_in_balls(b[:, :3].contiguous(), rad)).squeeze(1))
-        halo = torch.cat(_alltoallv([torch.cat([self.pos[i], self.mass[i, None].to(self.dt)], dim=1) for i in self._halo_send],
-                                    self.group))
+            need[r] = self.tree1.mark_in_balls(b[:, :3].contiguous(), rad).to(torch.bool)
+        self._halo_flat = need.nonzero()[:, 1]                     # grouped by requesting rank, ascending within a rank
+        self._halo_counts = need.sum(dim=1).tolist()
+        self._halo_send = list(self._halo_flat.split(self._halo_counts))
+        del need
+        halo, self._halo_rcounts = _alltoall_rows(torch.cat([self.pos[self._halo_flat], self.mass[self._halo_flat, None].to(self.dt)],
+                                                            dim=1), self._halo_counts, self.group)
         halo_pos, halo_mass = halo[:, :3], halo[:, 3]
         self.n_halo = int(halo_pos.shape[0])
         self._tick("mark_and_exchange_halo")
@@ -614,7 +629,7 @@ class DistributedKDTree:
 
     def _halo_values(self, owned_values):
         """Halo exchange #2: per-particle values of the halo particles, in tree2's halo order."""
-        return torch.cat(_alltoallv([owned_values[i] for i in self._halo_send], self.group))
+        return _alltoall_rows(owned_values[self._halo_flat].contiguous(), self._halo_counts, self.group, self._halo_rcounts)[0]
 
     def smooth_rho(self, k, kernel_id=0):
         """(smooth, rho) aligned with the input particles."""
