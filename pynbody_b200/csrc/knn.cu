@@ -51,7 +51,7 @@ __device__ unsigned long long g_stats[8];
 #endif
 
 constexpr int KNN_WARPS = 2;          // k > 128: warps per block (several blocks per SM)
-constexpr int KNN_MAX_WARPS = 20;     // k <= 128: ONE block per SM with as many warps as its shared memory holds
+constexpr int KNN_MAX_WARPS = 21;     // k <= 128: ONE block per SM with as many warps as its shared memory holds
 constexpr int MAXLOG = 10;              // k <= 1024
 
 template <typename T>
@@ -574,7 +574,19 @@ __global__ void __launch_bounds__(LOGC >= 0 ? KNN_MAX_WARPS * 32 : KNN_WARPS * 3
         q.W = reinterpret_cast<W_t *>(wins) + lane * 4;      // swizzled winner bytes: wofs()
         q.hb = sbase + pad + (uint32_t)wib * A + (uint32_t)lane * 4u;
         q.wb = sbase + pad + (uint32_t)warps * A + (uint32_t)wib * (uint32_t)K2 * 32u + (uint32_t)lane * 4u;
-        tile = reinterpret_cast<T *>(smem_raw + pad + (size_t)warps * (A + (size_t)K2 * 32)) + (size_t)wib * 96;
+        // candidate tiles: as many as fit into the alignment gap in front of the leaves, the rest behind the winner bytes
+        // (this is what lets the 21st warp in: 8 KB of alignment would otherwise be lost)
+        const uint32_t tile_bytes = 96u * (uint32_t)sizeof(T);
+        const uint32_t nfront = pad / tile_bytes;
+        const uint32_t behind = pad + (uint32_t)warps * (A + (uint32_t)K2 * 32u);
+        if ((uint32_t)wib < nfront) tile = reinterpret_cast<T *>(smem_raw + (size_t)wib * tile_bytes);
+        else tile = reinterpret_cast<T *>(smem_raw + behind + (size_t)((uint32_t)wib - nfront) * tile_bytes);
+        {
+            uint32_t dyn;
+            asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+            const uint32_t nback = (uint32_t)warps > nfront ? (uint32_t)warps - nfront : 0u;
+            if (behind + nback * tile_bytes > dyn) __trap();       // the host sized the block for another window base
+        }
     } else {
         unsigned char *base = smem_raw + knn_smem_per_warp<T, W_t, WITH_IDX>(K2) * wib;
         q.hd = reinterpret_cast<Key *>(base) + lane;
@@ -784,10 +796,18 @@ static void launch_knn_p(Tree &t, KnnArgs<T> &a)
     size_t smem;
     if (LOGC >= 0) {
         // one block per SM; up to K2 * 128 bytes of alignment padding in front (see k_knn)
-        const size_t pad = (size_t)K2 * 128;
-        warps = (int)std::min<size_t>(KNN_MAX_WARPS, (227 * 1024 - pad) / per_warp);
+        // The dynamic shared memory starts behind the per-block reservation (1 KB), so the leaves start `gap` bytes in;
+        // that gap holds candidate tiles.  (Sized for that base; the kernel traps if its window base disagrees.)
+        const size_t A = (size_t)K2 * 128, tile_bytes = 96 * sizeof(T), per_queue = A + (size_t)K2 * 32;
+        int dev0 = 0, reserved = 1024;
+        PNB_CUDA(cudaGetDevice(&dev0));
+        if (cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev0) != cudaSuccess) { cudaGetLastError(); reserved = 1024; }
+        const size_t gap = (A - (size_t)reserved % A) % A, nfront = gap / tile_bytes;
+        auto need = [&](int w) { return gap + per_queue * w + ((size_t)w > nfront ? (size_t)w - nfront : 0) * tile_bytes; };
+        warps = KNN_MAX_WARPS;
+        while (warps > 1 && need(warps) > (size_t)227 * 1024) --warps;
         if (g_opt_knn_blocks_per_sm > 0) warps = std::min(warps, 2 * g_opt_knn_blocks_per_sm);
-        smem = pad + per_warp * warps;
+        smem = need(warps);
     } else {
         // two warps per block unless one warp's queues already need more than half the shared memory
         warps = per_warp * KNN_WARPS <= 227 * 1024 ? KNN_WARPS : 1;
