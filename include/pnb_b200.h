@@ -77,16 +77,18 @@ int pnb_device_count(void);
  *                      they fit in half of the free device memory, so that rho / mean / dispersion / div / curl
  *                      stream over them instead of searching again; 0 never; 1 always.  (env PNB_NEIGHBOUR_LISTS)
  *   "gather_walk"      1: the reductions always use the tree-walking fixed-radius gather.  (env PNB_GATHER_WALK)
- *   "tree_build"       how the device tree is built; results do not depend on it.  2 (default): median-split kd-tree,
- *                      every level by global passes over three per-axis sorted lists; 1: the same with the lowest levels
- *                      built per sub-tree in shared memory; 0: one Morton-key sort for the upper levels + shared-memory
- *                      kd levels (cheapest build, slower searches).  (env PNB_TREE_BUILD)
+ *   "tree_build"       how the device tree is built; results do not depend on it.  2 (default): median-split kd-tree from
+ *                      three per-axis sorted lists, one fused partition pass per level, the lowest 6 levels per sub-tree in
+ *                      shared memory; 3 and 4: the SAME tree by the per-level formulations it replaced (mark + prefix sum +
+ *                      partition / fused pass for every level); 1: the lowest levels by an in-CTA sort per node; 0: one
+ *                      Morton-key sort for the upper levels + shared-memory kd levels (cheapest build, slower searches).
+ *                      (env PNB_TREE_BUILD)
  *   "streams"          1 (default): every host thread that calls the library works on its own non-blocking CUDA stream
  *                      (ordered after whatever the caller had enqueued on the default stream when the call was made,
  *                      drained before the call returns), so calls from two threads overlap on the device;
  *                      0: everything on the default stream.  (env PNB_STREAMS)
- *   "knn_blocks_per_sm" > 0 caps the resident blocks per SM of the (persistent) neighbour-search kernel so that kernels
- *                      launched from another thread find room beside it; 0 (default): as many as fit.
+ *   "knn_blocks_per_sm" > 0 caps the resident warps per SM of the (persistent) neighbour-search kernel (2 warps per unit)
+ *                      so that kernels launched from another thread find room beside it; 0 (default): as many as fit.
  * PNB_ERR_VALUE for an unknown name. */
 int pnb_set_option(const char *name, int value);
 /* select the device subsequent calls from this thread use */

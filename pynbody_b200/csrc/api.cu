@@ -351,9 +351,8 @@ int g_opt_neighbour_lists = -1;     // pnb_set_option("neighbour_lists"): -1 aut
 //   4            the same tree with the fused global pass for every level
 //   1            the same, but the lowest 6-7 levels per sub-tree in shared memory (tree_morton.cu: k_build_segment)
 //   0            one Morton-key sort for the upper levels + shared-memory kd levels below
-// Measured at 16.7 M float64 particles (profiles/r2_tree_build_variants.md): build 15.8 / 17.9 / 7.6 ms, kNN kernel
-// 51.3 / 51.3 / 65.5 ms: the Morton tree is the cheapest to build but its buckets cost the neighbour search +28 %,
-// and the shared-memory sorting network (5.8 ms for 6 levels) does not yet beat six global passes (3.6 ms).
+// Measured at 16.7 M float64 particles (profiles/r2_tree_build_variants.md): build 9.2 (2) / 15.3 (3) / 10.8 (4) / 16.1 (1) /
+// 6.2 ms (0); the Morton tree is the cheapest to build but its buckets cost the neighbour search +25 %.
 int g_opt_tree_build = 2;
 int g_opt_gather_walk = 0;          // pnb_set_option("gather_walk"): 1 = reductions always walk the tree
 static struct OptionsFromEnv {
