@@ -89,8 +89,8 @@ struct alignas(16) Rec {
     double xi, yi, zd, kmax2;     // exact path only.  zd: image -> dz = (z - z0) * use_z ; grid -> z
     float xr, yr, zr, inv;        // tile-relative position; image: zr = dz^2; inv = ns / kmax2 (<0: exact path only)
     float wq;                     // weight / h^dim
-    uint32_t box;                 // lxa | wx << 8 | lya << 16 | wy << 24   (rectangle clipped to the tile)
-    uint32_t boxz;                // lza | wz << 8
+    uint32_t box;                 // grid: lxa | wx << 8 | lya << 16 | wy << 24 (rectangle clipped to the tile); image: column mask
+    uint32_t boxz;                // grid: lza | wz << 8;  image: row mask (16 rows)
     uint32_t tile;
 };
 static_assert(sizeof(Rec) == 64, "record must be 64 bytes");
@@ -273,8 +273,16 @@ __global__ void k_make_records(Geom g, Cols c, int64_t i0, Images im, int64_t np
     const int lxa = max(f.xa - px0, 0), lxb = min(f.xb - px0, sx);
     const int lya = max(f.ya - py0, 0), lyb = min(f.yb - py0, sy);
     const int lza = max(f.za - pz0, 0), lzb = min(f.zb - pz0, sz);
-    R.box = (uint32_t)lxa | ((uint32_t)(lxb - lxa) << 8) | ((uint32_t)lya << 16) | ((uint32_t)(lyb - lya) << 24);
-    R.boxz = (uint32_t)lza | ((uint32_t)(lzb - lza) << 8);
+    if (!g.grid) {
+        // image tiles: the rectangle as a lane mask (columns) and a row mask, so that the tile kernel's tests are single
+        // bit operations -- the unpack-and-compare of a packed rectangle cost 14 of its ~67 instructions per record and warp
+        const int wx = lxb - lxa, wy = lyb - lya;
+        R.box = wx <= 0 ? 0u : ((wx >= 32 ? 0xffffffffu : ((1u << wx) - 1u)) << lxa);
+        R.boxz = wy <= 0 ? 0u : ((((1u << wy) - 1u) << lya) & 0xffffu);
+    } else {
+        R.box = (uint32_t)lxa | ((uint32_t)(lxb - lxa) << 8) | ((uint32_t)lya << 16) | ((uint32_t)(lyb - lya) << 24);
+        R.boxz = (uint32_t)lza | ((uint32_t)(lzb - lza) << 8);
+    }
     R.tile = tile;
     recs[j] = R;
 }
@@ -413,13 +421,21 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
                 }
             }
             const uint32_t box = R.box;
-            // rows of this thread inside the record's rectangle (image: the same for the whole warp)
+            // rows of this thread inside the record's rectangle (image: the same for the whole warp, one bit per row)
             const int row0 = GRID ? ly : NPIX * ly;
-            const unsigned rel = (unsigned)(row0 - (int)((box >> 16) & 0xff)), wy = box >> 24;
-            if (!(rel < wy) && !(NPIX > 1 && rel + 1u < wy)) continue;
-            bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
-            if (GRID) in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
-            if (!in_xz) continue;
+            unsigned rel = 0, wy = 0;
+            uint32_t rows = 0;
+            if (GRID) {
+                rel = (unsigned)(row0 - (int)((box >> 16) & 0xff)); wy = box >> 24;
+                if (!(rel < wy)) continue;
+                bool in_xz = (unsigned)(lx - (int)(box & 0xff)) < ((box >> 8) & 0xff);
+                in_xz &= (unsigned)(lz - (int)(R.boxz & 0xff)) < ((R.boxz >> 8) & 0xff);
+                if (!in_xz) continue;
+            } else {
+                rows = R.boxz >> (NPIX * ly);               // bit q: this warp's row q lies inside the rectangle
+                if (!(rows & (NPIX > 1 ? 3u : 1u))) continue;
+                if (!((box >> lx) & 1u)) continue;
+            }
             // (fused multiply-adds here: the float index is only trusted away from the bin borders -- BORDER below -- and
             // re-evaluated exactly otherwise, so contraction cannot change a table index)
             const float ddx = R.xr - cx;
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
                 for (int q = 0; q < NPIX; ++q) {
-                    if (!(rel + (unsigned)q < wy)) continue;
+                    if (GRID ? !(rel + (unsigned)q < wy) : !(rows & (1u << q))) continue;
                     const float ddy = R.yr - cy[q];
                     const float d2 = fmaf(ddy, ddy, d2xz);
                     const float t = fminf(d2 * inv, nsf + 2.0f);
@@ -450,7 +466,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             } else {                                           // tiny kernels: exact index only
 #pragma unroll
                 for (int q = 0; q < NPIX; ++q) {
-                    if (!(rel + (unsigned)q < wy)) continue;
+                    if (GRID ? !(rel + (unsigned)q < wy) : !(rows & (1u << q))) continue;
                     a[q] = fmaf(table(min(exact_index<GRID>(g, R, px, py + q, pz), ns)), wq, a[q]);
                 }
             }
