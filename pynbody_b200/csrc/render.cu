@@ -450,18 +450,22 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             if (inv > 0.0f) {                                  // (a property of the record: uniform)
 #pragma unroll
                 for (int q = 0; q < NPIX; ++q) {
-                    if (GRID ? !(rel + (unsigned)q < wy) : !(rows & (1u << q))) continue;
+                    // image: a row of the warp's pair outside the rectangle (its top or bottom edge: ~5 % of the records of
+                    // a warp) is evaluated with weight 0 instead of branched around -- cheaper than a test and a branch per pixel
+                    if (GRID && !(rel + (unsigned)q < wy)) continue;
+                    const float wqq = GRID ? wq : (((rows >> q) & 1u) ? wq : 0.0f);
                     const float ddy = R.yr - cy[q];
                     const float d2 = fmaf(ddy, ddy, d2xz);
-                    const float t = fminf(d2 * inv, nsf + 2.0f);
+                    // (clamped to a value whose fraction is 0.5, so that clamped indices never look like a bin border)
+                    const float t = fminf(d2 * inv, nsf + 2.5f);
                     unsigned idx = (unsigned)t;
                     const float fr = t - (float)idx;
-                    if (fabsf(fr - 0.5f) > 0.5f - BORDER && t < nsf + 1.0f) {
+                    if (fabsf(fr - 0.5f) > 0.5f - BORDER) {
                         int pxo = px;
                         asm volatile("" : "+r"(pxo));          // keeps the double-precision pixel arithmetic of the exact
                         idx = min(exact_index<GRID>(g, R, pxo, py + q, pz), ns);   // path inside this rare branch (nvcc hoists it)
                     }
-                    a[q] = fmaf(table(idx), wq, a[q]);
+                    a[q] = fmaf(table(idx), wqq, a[q]);
                 }
             } else {                                           // tiny kernels: exact index only
 #pragma unroll
