@@ -383,6 +383,8 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
 #pragma unroll
     for (int q = 0; q < NPIX; ++q) cy[q] = (float)(g.pdy * (NPIX * ly + q + 0.5));
     const float nsf = (float)g.ns;
+    uint32_t lanebit = 1u << (lx & 31);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lanebit));          // kept in a register (nvcc otherwise rebuilds lane and shift per record)
 
     // a pixel's partial sum over this CTA's slice of one tile (at most SEG terms) is kept in float, as the
     // reference keeps its whole sum; slices are combined in double
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(256) k_render_tiles(const Rec *__restrict__ re
             } else {
                 rows = R.boxz >> (NPIX * ly);               // bit q: this warp's row q lies inside the rectangle
                 if (!(rows & (NPIX > 1 ? 3u : 1u))) continue;
-                if (!((box >> lx) & 1u)) continue;
+                if (!(box & lanebit)) continue;
             }
             // (fused multiply-adds here: the float index is only trusted away from the bin borders -- BORDER below -- and
             // re-evaluated exactly otherwise, so contraction cannot change a table index)
