@@ -802,7 +802,9 @@ __global__ void k_hp_pixel_vectors(int nside_i, double4 *__restrict__ vec)
     vec[hp_pixel_index(nside, iring, ip)] = make_double4(st * cphi, st * sphi, ct, 0.0);
 }
 
-__global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *__restrict__ lut, double *__restrict__ acc,
+// (six resident CTAs per SM: the kernel waits on the gathers of the pixel-centre table, not on arithmetic -- 3 CTAs of 80 registers:
+// 95.7 ms, 4 of 64: 76.9, 5 of 48: 70.5, 6 of 40: 67.8 ms for the 6.9 M-particle shell at nside 256)
+__global__ void __launch_bounds__(256, 6) k_render_healpix(HpArgs a, const float *__restrict__ lut, double *__restrict__ acc,
                                                         const double4 *__restrict__ pixvec)
 {
     const double PI = 3.14159265358979323846, twopi = 2.0 * PI;
@@ -842,6 +844,8 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
     const size_t irmin = hp_ring_num_from_z(nside, cos(thetamin)), irmax = hp_ring_num_from_z(nside, cos(thetamax));
     const double cos_radius = cos(radius);
     const float radiusf = (float)radius, distancef = (float)distance, nsf = (float)a.ns;
+    const float radius2f = radiusf * radiusf, ns_over_radius2f = (float)((double)a.ns / (radius * radius));
+    const bool small_disc = a.projected && radiusf <= 0.2f;             // (warp-uniform: one particle per warp)
     // the particle's mass and density, loaded once (they enter every pixel's weight chain in their own element type)
     const double mass_d = ldv(a.mass, a.mass_f64, i), rho_d = ldv(a.rho, a.rho_f64, i);
     const float mass_f = (float)mass_d, rho_f = (float)rho_d;
@@ -902,8 +906,8 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             if (f >= total) continue;
             const HpRing R = wr[r];
             const size_t n_in_ring = R.n_in_ring, shift = R.shift;
-            size_t ip = (size_t)R.ip_lo + (size_t)(f - first);
-            if (ip > n_in_ring) ip -= n_in_ring;
+            unsigned ip = R.ip_lo + (unsigned)(f - first);             // (32-bit: at most two turns of a ring)
+            if (ip > R.n_in_ring) ip -= R.n_in_ring;
             const size_t ipix = (size_t)(R.base + ip);
             // Fast path (the pixel's centre vector comes from the table): the angle between the two unit vectors is
             // taken from their chord -- c^2 = |v - p|^2 in double without cancellation, angle = 2 asin(c / 2) in float
@@ -913,23 +917,38 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
             // directions.  For the thin-shell kernel cos(angle) = 1 - c^2/2 is used directly (no transcendental at all).
             unsigned idx = 0;
             bool exact = !(pixvec && ip >= 1);
-            double dot = 0.0;
+            double4 pv = make_double4(0.0, 0.0, 0.0, 0.0);
             if (!exact) {
-                const double4 pv = pixvec[ipix];
+                pv = pixvec[ipix];
                 const double ex = v0 - pv.x, ey = v1 - pv.y, ez = v2 - pv.z;
                 const double chord2 = ex * ex + ey * ey + ez * ez;
-                dot = v0 * pv.x + v1 * pv.y + v2 * pv.z;
                 if (a.projected) {
-                    const float chord = sqrtf((float)chord2);
-                    const float distf = 2.0f * asinf(fminf(0.5f * chord, 1.0f));
-                    if (chord > 1.9f || fabsf(distf - radiusf) <= 1e-5f * radiusf) exact = true;
-                    else {
-                        if (distf > radiusf) continue;
-                        const float off = distancef * distf;
-                        const float tf = nsf * (off * off) * inv_kmax2f;
-                        idx = (unsigned)fminf(tf, nsf + 2.0f);
-                        const float fr = tf - (float)idx;
-                        if (fabsf(fr - 0.5f) > 0.5f - 5e-4f && tf < nsf + 1.0f) exact = true;
+                    const float c2 = (float)chord2;
+                    if (small_disc && c2 <= 0.09f) {
+                        // discs of the usual size: the SQUARED angle straight from the squared chord,
+                        // (2 asin(c/2))^2 = c^2 (1 + c^2/12 + c^4/90 + c^6/560 + ...) (truncation < 2.2e-8 for c <= 0.3) -- no
+                        // square root, no arcsine; t = ns d2 / kmax2 = (ns / radius^2) angle^2 in this mode
+                        const float ang2 = c2 * fmaf(c2, fmaf(c2, fmaf(c2, 1.0f / 560.0f, 1.0f / 90.0f), 1.0f / 12.0f), 1.0f);
+                        if (fabsf(ang2 - radius2f) <= 2e-5f * radius2f) exact = true;
+                        else {
+                            if (ang2 > radius2f) continue;
+                            const float tf = ns_over_radius2f * ang2;
+                            idx = (unsigned)fminf(tf, nsf + 2.0f);
+                            const float fr = tf - (float)idx;
+                            if (fabsf(fr - 0.5f) > 0.5f - 5e-4f && tf < nsf + 1.0f) exact = true;
+                        }
+                    } else {
+                        const float chord = sqrtf(c2);
+                        const float distf = 2.0f * asinf(fminf(0.5f * chord, 1.0f));
+                        if (chord > 1.9f || fabsf(distf - radiusf) <= 1e-5f * radiusf) exact = true;
+                        else {
+                            if (distf > radiusf) continue;
+                            const float off = distancef * distf;
+                            const float tf = nsf * (off * off) * inv_kmax2f;
+                            idx = (unsigned)fminf(tf, nsf + 2.0f);
+                            const float fr = tf - (float)idx;
+                            if (fabsf(fr - 0.5f) > 0.5f - 5e-4f && tf < nsf + 1.0f) exact = true;
+                        }
                     }
                 } else {
                     const double cosd = 1.0 - 0.5 * chord2;
@@ -946,6 +965,7 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
                 }
             }
             if (exact) {
+                double dot;
                 if (!(pixvec && ip >= 1)) {      // (ip = 0 happens at phi ~ 0: the reference then takes the direction
                                                  // of "pixel 0" of the ring but the index before the ring's first)
                     double phi = (twopi * ((double)ip - 0.5 * ((double)shift)) / n_in_ring);
@@ -953,6 +973,10 @@ __global__ void __launch_bounds__(256) k_render_healpix(HpArgs a, const float *_
                     double sphi, cphi;
                     sincos(phi, &sphi, &cphi);
                     dot = v0 * (R.st * cphi) + v1 * (R.st * sphi) + v2 * R.ct;
+                } else {
+                    double px_ = pv.x;
+                    asm volatile("" : "+d"(px_));                  // (the dot product belongs to this rare branch only)
+                    dot = v0 * px_ + v1 * pv.y + v2 * pv.z;
                 }
                 if (dot > 1.0) dot = 1.0;
                 if (dot < -1.0) dot = -1.0;
