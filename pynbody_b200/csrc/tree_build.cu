@@ -755,16 +755,9 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
             // status words [pf_tiles], then one ticket counter per level (level < 32)
             unsigned long long *status = pf_state.as<unsigned long long>();
             unsigned int *ticket = reinterpret_cast<unsigned int *>(status + pf_tiles) + level;
-            static const int minb = getenv("PNB_PF_MINB") ? atoi(getenv("PNB_PF_MINB")) : 6;   // resident CTAs per SM (4: 11.75, 6 / 8: 10.78 ms per build)
-            if (minb == 8)
-                PNB_LAUNCH(k_partition_fused<8>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
-                           dim.as<int8_t>(), Ln, status, ticket);
-            else if (minb == 6)
-                PNB_LAUNCH(k_partition_fused<6>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
-                           dim.as<int8_t>(), Ln, status, ticket);
-            else
-                PNB_LAUNCH(k_partition_fused<4>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
-                           dim.as<int8_t>(), Ln, status, ticket);
+            // six resident CTAs per SM (40 registers): the pass is latency-bound (4 CTAs: 11.75 ms per build, 6 or 8: 10.78 ms)
+            PNB_LAUNCH(k_partition_fused<6>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
+                       dim.as<int8_t>(), Ln, status, ticket);
         } else {
             LeftFlag f{L, side.as<uint8_t>()};
             auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
