@@ -292,7 +292,23 @@ __global__ void k_all_equal(const unsigned char *a, const unsigned char *b, size
     size_t stride = (size_t)gridDim.x * blockDim.x;
     const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a), *b4 = reinterpret_cast<const uint32_t *>(b);
     bool d = false;
-    for (size_t j = i; j < bytes / 4; j += stride)
+    size_t done = 0;
+    if (!mask && (((uintptr_t)a | (uintptr_t)b) & 15) == 0) {       // the usual case: 16-byte loads, two in flight per array
+        const uint4 *av = reinterpret_cast<const uint4 *>(a), *bv = reinterpret_cast<const uint4 *>(b);
+        const size_t nv = bytes / 16;
+        size_t j = i;
+        for (; j + stride < nv; j += 2 * stride) {
+            const uint4 x0 = av[j], y0 = bv[j], x1 = av[j + stride], y1 = bv[j + stride];
+            d |= (x0.x != y0.x) | (x0.y != y0.y) | (x0.z != y0.z) | (x0.w != y0.w) | (x1.x != y1.x) | (x1.y != y1.y) | (x1.z != y1.z)
+                 | (x1.w != y1.w);
+        }
+        for (; j < nv; j += stride) {
+            const uint4 x0 = av[j], y0 = bv[j];
+            d |= (x0.x != y0.x) | (x0.y != y0.y) | (x0.z != y0.z) | (x0.w != y0.w);
+        }
+        done = nv * 4;
+    }
+    for (size_t j = done + i; j < bytes / 4; j += stride)
         if (!mask || mask[j / words_per_elem]) d |= a4[j] != b4[j];
     if (d) *differs = 1;
 }
