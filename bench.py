@@ -577,6 +577,11 @@ def run_ours_distributed(args):
     step_e2e()
     e2e_ms = timed(step_e2e, args.steps) / args.steps
     d = last["d"]
+    # the dominant kernel of the decomposed step is the search of a rank's OWNED particles; later launches (the masked
+    # re-search of the boundary queries) overwrite its timer, so it is run once more, untimed, on the last step's tree
+    d.tree1.knn_smooth(K_NEIGHBOURS, None, 1)
+    torch.cuda.synchronize()
+    knn_owned_ms = kdmain.last_kernel_ms(0)
     if d.timings:                                   # PNB_DIST_PROFILE=1: phase table of every rank
         names = list(d.timings)
         mine = torch.tensor([d.timings[k] for k in names], device="cuda", dtype=torch.float64)
@@ -619,7 +624,8 @@ def run_ours_distributed(args):
                 "ms": ms, "mpix_per_s": res * res / (ms * 1e-3) / 1e6}
     if rank == 0:
         peak, peak_src = load_peaks()
-        knn_ms = kdmain.last_kernel_ms(0)
+        algo = 6 * tsz * d.n_own                        # 6 s bytes per particle incl. the fused density
+        achieved = algo / (knn_owned_ms * 1e-3) / 1e9 if knn_owned_ms and knn_owned_ms > 0 else None
         cfg = distributed_config(args, world)          # (identical to the reference arm's config for the same N)
         line = {"metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -627,10 +633,13 @@ def run_ours_distributed(args):
                 "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": n_local * tsz * 4, "d2h_bytes_per_step": n_local * tsz * 2},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "k_knn (last launch on rank 0: masked re-search of boundary queries)",
-                             "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                             "peak_source": peak_src, "kernel_ms": knn_ms,
-                             "note": "per-kernel roofline is reported by the N=1 run; see DESIGN.md"},
+                "roofline": {"bound": "hbm", "kernel": "k_knn (rank 0: search of the rank's %d owned particles, re-run once after "
+                                                         "the timed steps)" % d.n_own,
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                             "traffic": None, "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                             "kernel_ms": knn_owned_ms,
+                             "note": "irregular tree search, bound by instruction issue (SURVEY.md 8d); DRAM traffic of the "
+                                     "kernel is captured by the N=1 run"},
                 "per_rank_owned_boundary_halo": [[int(v) for v in st_.tolist()] for st_ in allst],
                 "stages_ms": stages, "render": render}
         print(json.dumps(line))
