@@ -55,13 +55,17 @@ KERNEL_SOURCES = {"k_knn": ("knn.cu", "traverse.cuh"), "k_render_tiles": ("rende
 
 
 def source_hash(kernel="k_knn"):
-    """Hash of the sources a kernel is compiled from; ncu-derived constants are only quoted for the sources they
-    were captured on."""
+    """Hash of the CODE a kernel is compiled from (comments and white space do not count); ncu-derived constants are
+    only quoted for the code they were captured on."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for f in KERNEL_SOURCES[kernel]:
-        with open(os.path.join(ROOT, "pynbody_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "pynbody_b200", "csrc", f), "r") as fh:
+            text = fh.read()
+        text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)          # block comments
+        text = re.sub(r"//[^\n]*", " ", text)                        # line comments (no '//' occurs inside a string here)
+        h.update(" ".join(text.split()).encode())
     return h.hexdigest()[:16]
 
 

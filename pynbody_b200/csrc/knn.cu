@@ -33,6 +33,18 @@
 // (profiles/r1_knn_v1_summary.txt, r1_knn_v2_summary.txt for the binary heap / grouped max-cache it
 // replaced).
 //
+// LAYOUT (k <= 128, i.e. tree depth known at compile time).  ONE block per SM with as many warps as its shared memory holds
+// (21 for k = 64): [candidate tiles of the first warps | leaves of every warp | winner bytes of every warp | remaining tiles].
+// The leaves start at a multiple of one warp's leaf region (K2 * 128 bytes) of the shared window -- the gap in front of them
+// holds candidate tiles -- and the winner bytes of a warp at a multiple of K2 * 32, in IN-ORDER positions ((a << l) | (1 << (l-1))
+// for the node above leaves [a 2^l, (a+1) 2^l)) and swizzled [pos / 4][lane][pos % 4] (lane = bank): every node and sibling
+// address on a replacement path is then ONE logic instruction away from the leaf index, and the accesses go through 32-bit
+// shared-window addresses (queue_replace_max_fast; 113 SASS instructions per insert round against 140 with heap positions
+// and generic pointers).  Larger k keeps the generic formulation (heap positions, two warps per block).
+// PERIODIC boxes: wrapped images are tested until the queues are full; afterwards a warp none of whose query balls reaches a
+// face of the period runs the plain cell test.  Bucket ranges are computed (bucket j = ranks [32 j, 32 j + 32)), and the bounds /
+// coordinates the walk will need next are prefetched to L1 by otherwise idle lanes.
+//
 // float64 positions: shared memory, not arithmetic, bounds the number of resident warps, and latency
 // hiding is what the kernel lives on.  The queue therefore keeps only the HIGH 32 bits of each d2 in
 // shared memory (non-negative doubles order like their bit patterns); the low words sit in an

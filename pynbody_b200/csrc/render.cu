@@ -12,16 +12,20 @@
 //   2. a prefix sum and a second footprint pass emit (tile, particle) pairs, which one radix sort
 //      groups by tile;
 //   3. a record pass writes one 64-byte record per pair (float position relative to the tile origin,
-//      1/kernel support, weight, rectangle clipped to the tile; the doubles of the exact path) in sorted
-//      order, so that a tile's particles are contiguous;
+//      1/kernel support, weight, the rectangle clipped to the tile -- for images as a COLUMN MASK (one bit per
+//      lane) and a ROW MASK (one bit per tile row), so that the render kernel's tests are single bit operations;
+//      the doubles of the exact path) in sorted order, so that a tile's particles are contiguous;
 //   4. the render kernel gives every CTA a fixed-length slice of the sorted pair list (perfect load
 //      balance for clustered data), streams the records through shared memory with TMA bulk copies
 //      (cp.async.bulk + mbarrier, double buffered), and its 256 threads accumulate the pixels of the current
 //      tile in registers: image tiles are 32 x 16 pixels, a warp is one 32-pixel row segment and owns two
 //      adjacent rows, so a record's row test is warp-uniform; grid tiles are 4 x 8 x 8 voxels, one per thread.
 //      Pixels are flushed with one double-precision atomicAdd per (pixel, slice).
+//      (C3 image: 54.1 ms in round 1, 35.6 ms now -- the table read through an opaque shared-window address, the exact
+//      path's double arithmetic pinned inside its branch, bit-mask rectangle tests, edge rows by zero weight:
+//      profiles/r2b_render_summary.txt.)
 //      Three re-designs of the image kernel were built, verified against the goldens and measured SLOWER than
-//      this one (54 ms for the C3 image; profiles/r2_render_variants.md): 8 fixed pixels per thread on 64 x 32
+//      the round-1 kernel (54 ms then; profiles/r2_render_variants.md): 8 fixed pixels per thread on 64 x 32
 //      tiles (84 ms: same 58 G warp instructions, issue efficiency 87 -> 60 %); one record per warp adding into
 //      a shared-memory tile with float atomics (71 ms: those are CAS loops, ATOMS.CAST.SPIN); warps owning
 //      row bands of a shared-memory tile (73 ms: 46 G instructions but the warps of a CTA wait for the busiest
