@@ -369,3 +369,52 @@ for nfree in (2,3,4,6,8):
         s=walk_bulkfill(int(h),nfree)
         for k,v in s.items(): tot[k]=tot.get(k,0)+v
     print("bulk fill of first",nfree,"buckets:",{k:round(v/len(homes),1) for k,v in tot.items()})
+
+
+# ---- two home buckets per warp (sibling pair, lane = one query of each): rounds when a lane serves both queues -------------
+def walk_pair(home):
+    """Sibling buckets `home` and `home ^ 1` walked together; per candidate bucket the warp needs
+    max over lanes of (survivors of the lane's query in A + survivors of its query in B) rounds."""
+    hqs = [pos[leaves[home]], pos[leaves[home ^ 1]]]
+    c0 = np.concatenate(hqs)
+    cur, top = [], []
+    for hq in hqs:
+        d = ((hq[:, None, :] - c0[None, :, :]) ** 2).sum(-1)
+        cs = [sorted(d[i]) for i in range(32)]
+        cur.append(cs); top.append(np.array([c[-1] for c in cs]))
+    st = dict(tiles=0, rounds_pooled=0, rounds_separate=0)
+
+    def visit(node):
+        c = pos[leaves[node]]
+        st['tiles'] += 1
+        per = np.zeros((2, 32), int)
+        for s in range(2):
+            d = ((hqs[s][:, None, :] - c[None, :, :]) ** 2).sum(-1)
+            passl = gap2(hqs[s], node) <= top[s]
+            for i in range(32):
+                if not passl[i]:
+                    continue
+                sv = np.nonzero(d[i] < top[s][i])[0]
+                per[s, i] = len(sv)
+                for j in sv:
+                    if d[i, j] < top[s][i]:
+                        cur[s][i][-1] = d[i, j]; cur[s][i].sort(); top[s][i] = cur[s][i][-1]
+        st['rounds_pooled'] += int((per[0] + per[1]).max())
+        st['rounds_separate'] += int(per[0].max() + per[1].max())
+    cell = home >> 1
+    while cell != 1:
+        cp = cell ^ 1; stop = next_node(cp)
+        while True:
+            g = np.minimum(gap2(hqs[0], cp) - top[0], gap2(hqs[1], cp) - top[1])
+            if (g <= 0).any():
+                if cp < NB: cp = 2 * cp; continue
+                visit(cp)
+            cp = next_node(cp)
+            if cp == stop: break
+        cell >>= 1
+    return st
+tot = {}
+for h in homes[:20]:
+    s = walk_pair(int(h) & ~1)
+    for k, v in s.items(): tot[k] = tot.get(k, 0) + v
+print("sibling pair per warp (per PAIR of home buckets):", {k: round(v / 20, 1) for k, v in tot.items()})
