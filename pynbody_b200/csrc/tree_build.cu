@@ -241,8 +241,9 @@ __global__ void k_mark_sides(TreeShape s, int level, const uint32_t *__restrict_
                              uint8_t *__restrict__ side)
 {
     const int64_t base = (int64_t)blockIdx.x * blockDim.x * LEVEL_ITEMS + threadIdx.x;
+    // only the upper halves are read and written: the flag of a particle is "went to the upper child AT THIS LEVEL"
+    // (side[] starts at 0xff; lower-half particles keep an older level's tag)
     uint32_t id[LEVEL_ITEMS];
-    uint8_t sd[LEVEL_ITEMS];
 #pragma unroll
     for (int k = 0; k < LEVEL_ITEMS; ++k) {
         const int64_t p = base + (int64_t)k * blockDim.x;
@@ -250,19 +251,19 @@ __global__ void k_mark_sides(TreeShape s, int level, const uint32_t *__restrict_
         if (p >= s.n) continue;
         int64_t lo, hi, node;
         seg_of_pos(s, level, p, lo, hi, node);
-        const int d = dim[node];
-        id[k] = L[(int64_t)d * s.n + p];
-        sd[k] = (uint8_t)(p > split_rank(s, level, lo, hi));
+        if (!(p > split_rank(s, level, lo, hi))) continue;
+        id[k] = L[(int64_t)dim[node] * s.n + p];
     }
 #pragma unroll
     for (int k = 0; k < LEVEL_ITEMS; ++k)
-        if (id[k] != 0xffffffffu) side[id[k]] = sd[k];
+        if (id[k] != 0xffffffffu) side[id[k]] = (uint8_t)level;
 }
 
 struct LeftFlag {
     const uint32_t *L;
     const uint8_t *side;
-    __host__ __device__ uint32_t operator()(int64_t i) const { return side[L[i]] ? 0u : 1u; }
+    uint8_t level;
+    __host__ __device__ uint32_t operator()(int64_t i) const { return side[L[i]] == level ? 0u : 1u; }
 };
 
 // stable partition of all three lists about each node's split rank, using the global prefix sum S of
@@ -294,7 +295,7 @@ __global__ void k_partition(TreeShape s, int level, const uint32_t *__restrict__
     // phase 2: the dependent gathers of the side flags
     uint8_t sd[LEVEL_ITEMS];
 #pragma unroll
-    for (int k = 0; k < LEVEL_ITEMS; ++k) sd[k] = (dd[k] >= 0 && !keep[k]) ? side[id[k]] : 0;
+    for (int k = 0; k < LEVEL_ITEMS; ++k) sd[k] = (dd[k] >= 0 && !keep[k]) ? (uint8_t)(side[id[k]] == (uint8_t)level) : 0;
 #pragma unroll
     for (int k = 0; k < LEVEL_ITEMS; ++k) {
         if (dd[k] < 0) continue;
@@ -365,7 +366,7 @@ k_partition_fused(TreeShape s, int level, const uint32_t *__restrict__ L, const 
     }
     bool left[PF_ITEMS];
 #pragma unroll
-    for (int k = 0; k < PF_ITEMS; ++k) left[k] = (id[k] != 0xffffffffu && !keep[k]) ? side[id[k]] == 0 : false;
+    for (int k = 0; k < PF_ITEMS; ++k) left[k] = (id[k] != 0xffffffffu && !keep[k]) ? side[id[k]] != (uint8_t)level : false;
     unsigned bal[PF_ITEMS];
 #pragma unroll
     for (int k = 0; k < PF_ITEMS; ++k) {
@@ -728,11 +729,12 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
     DevBuf inherited;                                  // reference-shaped tree: split axis from the inherited boxes
     if (!shape.packed) inherited.alloc(sizeof(T) * 6 * 2 * t.nsplit);
     PNB_CUDA(cudaMemsetAsync(t.box.p, 0, sizeof(T) * 6 * 2 * t.nsplit, s));
+    PNB_CUDA(cudaMemsetAsync(side.p, 0xff, sizeof(uint8_t) * n, s));      // "never went up" (levels are < 64)
 
     uint32_t *L = La.as<uint32_t>(), *Ln = Lb.as<uint32_t>();
     size_t scan_bytes = 0;
     if (!fused) {
-        LeftFlag f{L, side.as<uint8_t>()};
+        LeftFlag f{L, side.as<uint8_t>(), 0};
         auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
         PNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
     }
@@ -759,7 +761,7 @@ static void build_typed(Tree &t, DevBuf &c, const T *mass, bool want_soa)
             PNB_LAUNCH(k_partition_fused<6>, (unsigned)pf_tiles, PF_THREADS, 0, s, shape, level, L, side.as<uint8_t>(),
                        dim.as<int8_t>(), Ln, status, ticket);
         } else {
-            LeftFlag f{L, side.as<uint8_t>()};
+            LeftFlag f{L, side.as<uint8_t>(), (uint8_t)level};
             auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), f);
             PNB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, it, S.as<uint32_t>(), 3 * n, s));
             g_launches += 2;
